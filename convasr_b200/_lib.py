@@ -1,0 +1,104 @@
+"""ctypes binding of libconvasr_b200.so (the C ABI declared in include/convasr_b200.h).
+
+There is no fallback: if the shared object is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_int = ctypes.c_int
+c_i32 = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+
+
+class ConvSource(ctypes.Structure):
+	_fields_ = [
+		('act', c_void_p), ('wgt', c_void_p), ('T_in', c_i32), ('T_rows', c_i32), ('ld_ch', c_i32), ('ch_off', c_i32),
+		('C_in', c_i32), ('w_rows', c_i32), ('w_ld_ch', c_i32), ('w_ch_off', c_i32), ('taps', c_i32),
+		('dilation', c_i32), ('pad_left', c_i32)
+	]
+
+
+class ConvEpilogue(ctypes.Structure):
+	_fields_ = [
+		('B', c_i32), ('T_out', c_i32), ('C_out', c_i32), ('block_n', c_i32), ('epilogue', c_i32), ('act', c_i32),
+		('act_a', c_float), ('act_b', c_float), ('bias', c_void_p), ('xlen_frac', c_void_p), ('out_hi', c_void_p),
+		('out_lo', c_void_p), ('out_T_rows', c_i32), ('out_ld_ch', c_i32), ('logits', c_void_p),
+		('log_probs', c_void_p), ('argmax', c_void_p)
+	]
+
+
+ACT_NONE, ACT_RELU, ACT_HARDTANH, ACT_LEAKY_RELU = 0, 1, 2, 3
+EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
+MAX_CONV_SOURCES = 12
+
+# name -> argtypes; every function returns int except the three introspection calls
+SIGNATURES = {
+	'cab_frontend_logmel': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+							c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
+	'cab_instnorm_pack': [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+						c_void_p, c_void_p],
+	'cab_conv1d_fused': [ctypes.POINTER(ConvSource), c_int, ctypes.POINTER(ConvEpilogue), c_void_p],
+	'cab_grouped_conv1d_relu': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+								c_void_p, c_int, c_void_p],
+	'cab_log_softmax_argmax': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+	'cab_log_softmax_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+	'cab_ctc_loss_fwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+						c_void_p, c_void_p, c_void_p],
+	'cab_ctc_loss_bwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+						c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
+	'cab_ctc_alignment': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+						c_void_p, c_void_p, c_void_p],
+	'cab_topk_ids': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+	'cab_greedy_collapse': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+							c_void_p, c_int, c_void_p, c_void_p],
+	'cab_entropy': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+}
+INTROSPECTION = {'cab_abi_version': c_int, 'cab_last_error': ctypes.c_char_p, 'cab_launch_count': c_i64}
+
+
+def lib_path():
+	return _build.LIB_PATH
+
+
+def load():
+	"""Load (building first if the .so is absent and nvcc exists).  Raises loudly otherwise."""
+	global _LIB
+	if _LIB is not None:
+		return _LIB
+	path = lib_path()
+	if not os.path.exists(path):
+		try:
+			_build.build()
+		except Exception as e:
+			raise RuntimeError(
+				f'convasr_b200: native library {path} is missing and could not be built ({e}); there is no fallback path'
+			) from e
+	lib = ctypes.CDLL(path)
+	for name, argtypes in SIGNATURES.items():
+		fn = getattr(lib, name)
+		fn.argtypes = argtypes
+		fn.restype = c_int
+	for name, restype in INTROSPECTION.items():
+		fn = getattr(lib, name)
+		fn.argtypes = []
+		fn.restype = restype
+	if lib.cab_abi_version() != 1:
+		raise RuntimeError(f'convasr_b200: ABI version mismatch ({lib.cab_abi_version()} != 1)')
+	_LIB = lib
+	return lib
+
+
+def check(rc, what):
+	if rc != 0:
+		msg = load().cab_last_error()
+		raise RuntimeError(f'convasr_b200: {what} failed (rc={rc}): {msg.decode() if msg else "?"}')
+
+
+def launch_count():
+	return int(load().cab_launch_count())

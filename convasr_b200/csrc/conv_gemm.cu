@@ -1,0 +1,476 @@
+// Conv1d (+folded BN) + residual 1x1 convs + activation + temporal mask as one persistent,
+// warp-specialised tcgen05/TMEM implicit GEMM for sm_100a.
+//
+// Replaces (reference file:line): ConvBn1d.forward models.py:127-139 in fuse_conv_bn_eval form
+// (:141-151), ConvSamePadding :47-77, ResidualActivation.forward :357-371, temporal mask
+// :136-138/:611-619, Decoder :23-44 + log_softmax :316 + argmax transcript_generators.py:27.
+//
+// Mapping
+//   M = 128 consecutive output frames of ONE utterance (tiles never straddle utterances)
+//   N = block_n output channels (<= 256, runtime), K = sum over sources/taps of C_in
+//   A tile  = x[b, t0 + tap*dil - pad : +128, ci0 : ci0+64]  -- a 3-D TMA box; rows outside
+//             [0, T_in) are zero-filled by the TMA unit, which IS the conv zero padding.
+//   B tile  = W[tap, n0 : n0+block_n, ci0 : ci0+64]          -- 3-D TMA box, K-major.
+//   Both land in shared memory with the 128-byte swizzle and are consumed by
+//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16) accumulating fp32 in TMEM.
+//   TMEM holds two 256-column accumulators so the epilogue of tile i overlaps the MMAs of
+//   tile i+1.
+// Warp roles (256 threads): warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM allocator,
+//   warps4-7 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include "common.cuh"
+#include "../../include/convasr_b200.h"
+#include <mutex>
+#include <atomic>
+
+namespace cab {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle row
+constexpr int kStages = 4;
+constexpr int kMaxBlockN = 256;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;     // 16 KB
+constexpr int kBTileBytes = kMaxBlockN * kBlockK * 2;  // 32 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int kNumThreads = 256;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct SrcDev {
+    int a_ch_off, w_ch_off, n_chunks, taps, dil, pad_left;
+};
+
+struct alignas(64) ConvParams {
+    CUtensorMap amap[CAB_MAX_CONV_SOURCES];
+    CUtensorMap wmap[CAB_MAX_CONV_SOURCES];
+    SrcDev src[CAB_MAX_CONV_SOURCES];
+    int n_src;
+    int B, T_out, C_out, block_n;
+    int mtiles_per_b, n_ntiles, n_tiles;
+    int epilogue, act;
+    float act_a, act_b;
+    const float* bias;
+    const float* xlen;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    int out_T_rows, out_ld;
+    float* logits;
+    float* log_probs;
+    int* argmax;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act, float a, float b) {
+    switch (act) {
+        case CAB_ACT_RELU: return fmaxf(x, 0.f);
+        case CAB_ACT_HARDTANH: return fminf(fmaxf(x, a), b);
+        case CAB_ACT_LEAKY_RELU: return x > 0.f ? x : x * a;
+        default: return x;
+    }
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment required by the 128B swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
+    uint64_t* tmem_empty = tmem_full + kAccStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.n_src; ++s) {
+            tma_prefetch_desc(&p.amap[s]);
+            tma_prefetch_desc(&p.wmap[s]);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int block_n = p.block_n;
+    const uint32_t stage_tx_bytes = kATileBytes + block_n * kBlockK * 2;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_ntiles;
+                const int mt = tile / p.n_ntiles;
+                const int b = mt / p.mtiles_per_b;
+                const int t0 = (mt % p.mtiles_per_b) * kBlockM;
+                const int n0 = nt * block_n;
+                for (int s = 0; s < p.n_src; ++s) {
+                    const SrcDev sd = p.src[s];
+                    for (int tap = 0; tap < sd.taps; ++tap) {
+                        const int trow = t0 + tap * sd.dil - sd.pad_left;
+                        for (int ch = 0; ch < sd.n_chunks; ++ch) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            uint8_t* a_dst = smem + stage * kStageBytes;
+                            uint8_t* b_dst = a_dst + kATileBytes;
+                            mbar_expect_tx(&full_bar[stage], stage_tx_bytes);
+                            tma_load_3d(a_dst, &p.amap[s], &full_bar[stage],
+                                        sd.a_ch_off + ch * kBlockK, trow, b);
+                            tma_load_3d(b_dst, &p.wmap[s], &full_bar[stage],
+                                        sd.w_ch_off + ch * kBlockK, n0, tap);
+                            if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kBlockM, block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.n_src; ++s) {
+                    const int ksteps = p.src[s].taps * p.src[s].n_chunks;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+                        const uint32_t b_addr = a_addr + kATileBytes;
+                        const uint64_t a_desc = umma_desc_sw128(a_addr);
+                        const uint64_t b_desc = umma_desc_sw128(b_addr);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // +32 bytes per K=16 slice inside the 128B swizzle row (>>4 => +2)
+                            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);  // frees the smem slot when MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_ntiles;
+            const int mt = tile / p.n_ntiles;
+            const int b = mt / p.mtiles_per_b;
+            const int t0 = (mt % p.mtiles_per_b) * kBlockM;
+            const int n0 = nt * block_n;
+            const int t = t0 + row;
+            const bool row_ok = t < p.T_out;
+
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * kMaxBlockN + (uint32_t(q * 32) << 16);
+
+            if (p.epilogue == CAB_EPI_ACT_BF16) {
+                int len = p.T_out;
+                if (p.xlen != nullptr) len = frac_len(__ldg(p.xlen + b), p.T_out);
+                const bool keep = t < len;
+                const size_t out_row = (size_t(b) * p.out_T_rows + t) * p.out_ld;
+                for (int c0 = 0; c0 < block_n; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    const int n = n0 + c0;
+                    if (row_ok && n < p.C_out) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            float x0 = __uint_as_float(v[j]);
+                            float x1 = __uint_as_float(v[j + 1]);
+                            if (p.bias != nullptr) {
+                                x0 += __ldg(p.bias + n + j);
+                                x1 += __ldg(p.bias + n + j + 1);
+                            }
+                            x0 = apply_act(x0, p.act, p.act_a, p.act_b);
+                            x1 = apply_act(x1, p.act, p.act_a, p.act_b);
+                            if (!keep) { x0 = 0.f; x1 = 0.f; }
+                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                            hi[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                            if (p.out_lo != nullptr) {
+                                float2 hf = __bfloat1622float2(h);
+                                lo[j >> 1] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+                            }
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.out_hi + out_row + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        if (p.out_lo != nullptr) {
+                            uint4* dlo = reinterpret_cast<uint4*>(p.out_lo + out_row + n);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                dlo[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            } else if (p.epilogue == CAB_EPI_LOGSOFTMAX) {
+                // Single N tile holds all classes.  Three passes over TMEM (cheap) keep the
+                // register footprint small: max/argmax, sum of exp, then write.
+                const int C = p.C_out;
+                float vmax = -INFINITY;
+                int imax = 0;
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        if (c < C) {
+                            float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                            if (x > vmax) { vmax = x; imax = c; }
+                        }
+                    }
+                }
+                float ssum = 0.f;
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        if (c < C) {
+                            float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                            ssum += expf(x - vmax);
+                        }
+                    }
+                }
+                const float lse = vmax + logf(ssum);
+                for (int c0 = 0; c0 < C; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = c0 + j;
+                            if (c < C) {
+                                float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                                const size_t o = (size_t(b) * C + c) * p.T_out + t;  // lanes -> consecutive t
+                                if (p.logits) p.logits[o] = x;
+                                if (p.log_probs) p.log_probs[o] = x - lse;
+                            }
+                        }
+                    }
+                }
+                if (row_ok && p.argmax) p.argmax[size_t(b) * p.T_out + t] = imax;
+            } else {  // CAB_EPI_LOGITS_F32
+                const int C = p.C_out;
+                for (int c0 = 0; c0 < block_n; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = n0 + c0 + j;
+                            if (c < C) {
+                                float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
+                                p.logits[(size_t(b) * C + c) * p.T_out + t] = x;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+                cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+// 3-D bf16 map: dims (innermost first) {d0, d1, d2}, row pitch / slab pitch in elements.
+static int encode_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                         uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0,
+                         uint32_t box1) {
+    EncodeTiledFn enc = get_encode_fn();
+    CAB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CAB_CHECK_ARG(r == CUDA_SUCCESS,
+                  "cuTensorMapEncodeTiled failed (%d): base=%p dims=%llu,%llu,%llu pitch=%llu,%llu "
+                  "box=%u,%u",
+                  (int)r, base, (unsigned long long)d0, (unsigned long long)d1,
+                  (unsigned long long)d2, (unsigned long long)pitch1_elems,
+                  (unsigned long long)pitch2_elems, box0, box1);
+    return 0;
+}
+
+static int pick_block_n(int C_out, int epilogue) {
+    if (epilogue == CAB_EPI_LOGSOFTMAX) return ((C_out + 15) / 16) * 16;
+    // fewest N tiles first, then least padding; multiples of 32 so the epilogue works in
+    // 32-column TMEM loads.
+    const int n_tiles = (C_out + kMaxBlockN - 1) / kMaxBlockN;
+    int bn = (C_out + n_tiles - 1) / n_tiles;
+    bn = ((bn + 31) / 32) * 32;
+    return bn;
+}
+
+extern std::atomic<int64_t> g_launch_count;
+
+}  // namespace cab
+
+using namespace cab;
+
+extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
+                                const cab_conv_epilogue_t* ep, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(srcs && ep, "null sources/epilogue");
+    CAB_CHECK_ARG(n_src >= 1 && n_src <= CAB_MAX_CONV_SOURCES, "n_sources=%d out of [1,%d]", n_src,
+                  CAB_MAX_CONV_SOURCES);
+    CAB_CHECK_ARG(ep->B > 0 && ep->T_out > 0 && ep->C_out > 0, "bad output shape B=%d T=%d C=%d",
+                  ep->B, ep->T_out, ep->C_out);
+
+    static thread_local ConvParams p;  // too big for the stack of small threads; reused
+    p.n_src = n_src;
+    p.B = ep->B;
+    p.T_out = ep->T_out;
+    p.C_out = ep->C_out;
+    int bn = ep->block_n > 0 ? ep->block_n : pick_block_n(ep->C_out, ep->epilogue);
+    CAB_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= kMaxBlockN, "block_n=%d must be a multiple of 16 in [16,256]", bn);
+    if (ep->epilogue == CAB_EPI_ACT_BF16) {
+        CAB_CHECK_ARG(bn % 32 == 0, "block_n=%d must be a multiple of 32 for the bf16 epilogue", bn);
+        CAB_CHECK_ARG(ep->C_out % 32 == 0, "C_out=%d must be a multiple of 32 (pad on the host)", ep->C_out);
+        CAB_CHECK_ARG(ep->out_hi != nullptr, "out_hi is null");
+        CAB_CHECK_ARG(ep->out_ld_ch >= ep->C_out && ep->out_ld_ch % 8 == 0, "bad out_ld_ch=%d", ep->out_ld_ch);
+        CAB_CHECK_ARG(ep->out_T_rows >= ep->T_out, "out_T_rows=%d < T_out=%d", ep->out_T_rows, ep->T_out);
+        CAB_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->out_hi) & 15) == 0, "out_hi must be 16-byte aligned");
+    } else if (ep->epilogue == CAB_EPI_LOGSOFTMAX) {
+        CAB_CHECK_ARG(ep->C_out <= kMaxBlockN, "log_softmax epilogue supports at most %d classes (got %d)", kMaxBlockN, ep->C_out);
+        CAB_CHECK_ARG(bn >= ep->C_out, "block_n=%d must cover all %d classes", bn, ep->C_out);
+    } else if (ep->epilogue == CAB_EPI_LOGITS_F32) {
+        CAB_CHECK_ARG(ep->logits != nullptr, "logits is null");
+    } else {
+        CAB_CHECK_ARG(false, "unknown epilogue %d", ep->epilogue);
+    }
+    p.block_n = bn;
+    p.mtiles_per_b = (ep->T_out + kBlockM - 1) / kBlockM;
+    p.n_ntiles = (ep->C_out + bn - 1) / bn;
+    p.n_tiles = p.B * p.mtiles_per_b * p.n_ntiles;
+    p.epilogue = ep->epilogue;
+    p.act = ep->act;
+    p.act_a = ep->act_a;
+    p.act_b = ep->act_b;
+    p.bias = ep->bias;
+    p.xlen = ep->xlen_frac;
+    p.out_hi = static_cast<__nv_bfloat16*>(ep->out_hi);
+    p.out_lo = static_cast<__nv_bfloat16*>(ep->out_lo);
+    p.out_T_rows = ep->out_T_rows;
+    p.out_ld = ep->out_ld_ch;
+    p.logits = ep->logits;
+    p.log_probs = ep->log_probs;
+    p.argmax = ep->argmax;
+
+    for (int s = 0; s < n_src; ++s) {
+        const cab_conv_source_t& c = srcs[s];
+        CAB_CHECK_ARG(c.act && c.wgt, "source %d: null pointer", s);
+        CAB_CHECK_ARG(c.C_in > 0 && c.C_in % kBlockK == 0, "source %d: C_in=%d must be a multiple of 64", s, c.C_in);
+        CAB_CHECK_ARG(c.ch_off >= 0 && c.ch_off + c.C_in <= c.ld_ch && c.ld_ch % 8 == 0, "source %d: bad channel window off=%d C_in=%d ld=%d", s, c.ch_off, c.C_in, c.ld_ch);
+        CAB_CHECK_ARG(c.w_ch_off >= 0 && c.w_ch_off + c.C_in <= c.w_ld_ch && c.w_ld_ch % 8 == 0, "source %d: bad weight channel window", s);
+        CAB_CHECK_ARG(c.taps >= 1 && c.dilation >= 1, "source %d: taps=%d dilation=%d", s, c.taps, c.dilation);
+        CAB_CHECK_ARG(c.T_in >= 1 && c.T_rows >= c.T_in, "source %d: T_in=%d T_rows=%d", s, c.T_in, c.T_rows);
+        CAB_CHECK_ARG((reinterpret_cast<uintptr_t>(c.act) & 15) == 0 && (reinterpret_cast<uintptr_t>(c.wgt) & 15) == 0, "source %d: pointers must be 16-byte aligned", s);
+        int rc = encode_map_3d(&p.amap[s], c.act, (uint64_t)c.ld_ch, (uint64_t)c.T_in, (uint64_t)ep->B,
+                               (uint64_t)c.ld_ch, (uint64_t)c.T_rows * c.ld_ch, kBlockK, kBlockM);
+        if (rc) return rc;
+        rc = encode_map_3d(&p.wmap[s], c.wgt, (uint64_t)c.w_ld_ch, (uint64_t)c.w_rows, (uint64_t)c.taps,
+                           (uint64_t)c.w_ld_ch, (uint64_t)c.w_rows * c.w_ld_ch, kBlockK, (uint32_t)bn);
+        if (rc) return rc;
+        p.src[s].a_ch_off = c.ch_off;
+        p.src[s].w_ch_off = c.w_ch_off;
+        p.src[s].n_chunks = c.C_in / kBlockK;
+        p.src[s].taps = c.taps;
+        p.src[s].dil = c.dilation;
+        p.src[s].pad_left = c.pad_left;
+    }
+
+    static int num_sms = 0;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_err = cudaFuncSetAttribute(conv1d_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    });
+    CAB_CHECK_ARG(attr_err == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmemBytes, cudaGetErrorString(attr_err));
+    CAB_CHECK_ARG(num_sms > 0, "no CUDA device");
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    conv1d_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}

@@ -1,0 +1,670 @@
+// CTC loss (alpha / beta / gradient), forced alignment, log_softmax(+argmax), top-K ids,
+// greedy CTC collapse and the entropy reductions -- the latency/HBM-bound tail of the path.
+//
+// Replaces (reference file:line): F.ctc_loss call models.py:323 (arithmetic = ATen LossCTC);
+// ctc.alignment ctc.py:6-75; F.log_softmax models.py:316; GreedyDecoder.decode
+// decoders.py:5-16; GreedyCTCGenerator.generate transcript_generators.py:27-83;
+// models.entropy / weighted_mean_entropy models.py:645-673.
+//
+// The recursions are T sequential steps, so each utterance gets one CTA with the extended
+// target states across threads and the previous time step in shared memory.
+#include "common.cuh"
+#include "../../include/convasr_b200.h"
+#include <atomic>
+#include <float.h>
+
+namespace cab {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int kCtcMaxPer = 4;  // extended states per thread (S <= 4 * 1024)
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    const float m = fmaxf(a, fmaxf(b, c));
+    if (m == -INFINITY) return -INFINITY;
+    return logf(expf(a - m) + expf(b - m) + expf(c - m)) + m;
+}
+__device__ __forceinline__ float lse2(float a, float b) {
+    const float m = fmaxf(a, b);
+    if (m == -INFINITY) return -INFINITY;
+    return logf(expf(a - m) + expf(b - m)) + m;
+}
+
+// ------------------------------------------------------------------------------------------
+// CTC forward: alpha recursion.  grid = B, block = threads (multiple of 32).
+// shared: float prev[2][S_max + 2]
+// ------------------------------------------------------------------------------------------
+__global__ void ctc_alpha_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                 const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
+                                 const int64_t* __restrict__ tgt_len, int T, int C, int L_max, int blank,
+                                 float* __restrict__ alpha_ws, float* __restrict__ nll) {
+    extern __shared__ float sh[];
+    const int b = blockIdx.x;
+    const int S_max = 2 * L_max + 1;
+    const int tl = (int)tgt_len[b];
+    const int il = (int)in_len[b];
+    const int S = 2 * tl + 1;
+    float* buf0 = sh;               // index s+2 (two guard cells at the front)
+    float* buf1 = sh + (S_max + 2);
+    const float* lpb = lp + (int64_t)b * sb;
+    float* aw = alpha_ws + (size_t)b * T * S_max;
+
+    int ext[kCtcMaxPer];
+    bool skip[kCtcMaxPer];
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        ext[i] = blank;
+        skip[i] = false;
+        if (s < S && (s & 1)) {
+            ext[i] = (int)targets[(size_t)b * L_max + (s >> 1)];
+            if (s >= 3) skip[i] = ext[i] != (int)targets[(size_t)b * L_max + (s >> 1) - 1];
+        }
+    }
+    if (threadIdx.x < 2) { buf0[threadIdx.x] = -INFINITY; buf1[threadIdx.x] = -INFINITY; }
+    if (il <= 0 || tl > L_max) {
+        if (threadIdx.x == 0) nll[b] = INFINITY;
+        return;
+    }
+    // t = 0
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        if (s < S) {
+            float a = -INFINITY;
+            if (s < 2) a = lpb[(int64_t)ext[i] * sc];
+            buf0[s + 2] = a;
+            aw[s] = a;
+        }
+    }
+    __syncthreads();
+    float* prev = buf0;
+    float* cur = buf1;
+    float lp_next[kCtcMaxPer];
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        lp_next[i] = (s < S && il > 1) ? lpb[st + (int64_t)ext[i] * sc] : 0.f;
+    }
+    for (int t = 1; t < il; ++t) {
+        float lpc[kCtcMaxPer];
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            lpc[i] = lp_next[i];
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S && t + 1 < il) lp_next[i] = lpb[(int64_t)(t + 1) * st + (int64_t)ext[i] * sc];
+        }
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S) {
+                const float a1 = prev[s + 2];
+                const float a2 = prev[s + 1];
+                const float a3 = skip[i] ? prev[s] : -INFINITY;
+                const float v = lse3(a1, a2, a3) + lpc[i];
+                cur[s + 2] = v;
+                aw[(size_t)t * S_max + s] = v;
+            }
+        }
+        __syncthreads();
+        float* tmp = prev; prev = cur; cur = tmp;
+    }
+    if (threadIdx.x == 0) {
+        const float l1 = prev[S - 1 + 2];
+        const float l2 = S > 1 ? prev[S - 2 + 2] : -INFINITY;
+        nll[b] = -lse2(l1, l2);
+    }
+}
+
+// CTC backward: beta recursion, stored to ws_beta
+__global__ void ctc_beta_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
+                                const int64_t* __restrict__ tgt_len, int T, int C, int L_max, int blank,
+                                float* __restrict__ beta_ws) {
+    extern __shared__ float sh[];
+    const int b = blockIdx.x;
+    const int S_max = 2 * L_max + 1;
+    const int tl = (int)tgt_len[b];
+    const int il = (int)in_len[b];
+    const int S = 2 * tl + 1;
+    float* buf0 = sh;  // index s, two guard cells at the END
+    float* buf1 = sh + (S_max + 2);
+    const float* lpb = lp + (int64_t)b * sb;
+    float* bw = beta_ws + (size_t)b * T * S_max;
+    if (il <= 0 || tl > L_max) return;
+
+    int ext[kCtcMaxPer];
+    bool skip[kCtcMaxPer];  // may jump s -> s+2
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        ext[i] = blank;
+        skip[i] = false;
+        if (s < S && (s & 1)) {
+            ext[i] = (int)targets[(size_t)b * L_max + (s >> 1)];
+            if (s + 2 < S) skip[i] = ext[i] != (int)targets[(size_t)b * L_max + (s >> 1) + 1];
+        }
+    }
+    if (threadIdx.x < 2) { buf0[S + threadIdx.x] = -INFINITY; buf1[S + threadIdx.x] = -INFINITY; }
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        if (s < S) {
+            float v = -INFINITY;
+            if (s >= S - 2) v = lpb[(int64_t)(il - 1) * st + (int64_t)ext[i] * sc];
+            buf0[s] = v;
+            bw[(size_t)(il - 1) * S_max + s] = v;
+        }
+    }
+    __syncthreads();
+    float* nxt = buf0;
+    float* cur = buf1;
+    float lp_next[kCtcMaxPer];
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        lp_next[i] = (s < S && il > 1) ? lpb[(int64_t)(il - 2) * st + (int64_t)ext[i] * sc] : 0.f;
+    }
+    for (int t = il - 2; t >= 0; --t) {
+        float lpc[kCtcMaxPer];
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            lpc[i] = lp_next[i];
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S && t >= 1) lp_next[i] = lpb[(int64_t)(t - 1) * st + (int64_t)ext[i] * sc];
+        }
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S) {
+                const float b1 = nxt[s];
+                const float b2 = nxt[s + 1];
+                const float b3 = skip[i] ? nxt[s + 2] : -INFINITY;
+                const float v = lse3(b1, b2, b3) + lpc[i];
+                cur[s] = v;
+                bw[(size_t)t * S_max + s] = v;
+            }
+        }
+        __syncthreads();
+        float* tmp = nxt; nxt = cur; cur = tmp;
+    }
+}
+
+// grad = exp(lp) * go for t < il, else 0.  Thread order follows the contiguous dim of grad.
+__global__ void ctc_grad_init_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                     const int64_t* __restrict__ in_len, const float* __restrict__ go,
+                                     int B, int T, int C, float* __restrict__ grad, int64_t gt, int64_t gb,
+                                     int64_t gc) {
+    const int64_t n = (int64_t)B * T * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int b, c, t;
+        if (gt == 1) {  // [B, C, T]-like: t fastest
+            t = (int)(i % T); c = (int)((i / T) % C); b = (int)(i / ((int64_t)T * C));
+        } else {        // c fastest
+            c = (int)(i % C); const int64_t r = i / C;
+            if (gb < gt) { b = (int)(r % B); t = (int)(r / B); } else { t = (int)(r % T); b = (int)(r / T); }
+        }
+        float g = 0.f;
+        if (t < (int)in_len[b]) g = expf(lp[(int64_t)t * st + (int64_t)b * sb + (int64_t)c * sc]) * go[b];
+        grad[(int64_t)t * gt + (int64_t)b * gb + (int64_t)c * gc] = g;
+    }
+}
+
+// grad[b, t, ext(s)] -= exp(alpha + beta + nll - lp) * go.  One warp per (b, t) row chunk.
+__global__ void ctc_grad_scatter_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                        const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
+                                        const int64_t* __restrict__ tgt_len, int T, int L_max, int blank,
+                                        const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
+                                        const float* __restrict__ nll, const float* __restrict__ go,
+                                        float* __restrict__ grad, int64_t gt, int64_t gb, int64_t gc) {
+    const int b = blockIdx.y;
+    const int S_max = 2 * L_max + 1;
+    const int tl = (int)tgt_len[b];
+    const int il = (int)in_len[b];
+    const int S = 2 * tl + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (t >= il || tl > L_max) return;
+    const float nl = nll[b], g = go[b];
+    const float* lpt = lp + (int64_t)t * st + (int64_t)b * sb;
+    float* gr = grad + (int64_t)t * gt + (int64_t)b * gb;
+    const float lp_blank = lpt[(int64_t)blank * sc];
+    const size_t row = ((size_t)b * T + t) * S_max;
+    float blank_acc = 0.f;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+        const int s = s0 + lane;
+        if (s < S) {
+            const float ab = alpha_ws[row + s] + beta_ws[row + s];
+            if (s & 1) {
+                const int c = (int)targets[(size_t)b * L_max + (s >> 1)];
+                const float occ = expf(ab + nl - lpt[(int64_t)c * sc]);
+                atomicAdd(gr + (int64_t)c * gc, -occ * g);
+            } else {
+                blank_acc += expf(ab + nl - lp_blank);
+            }
+        }
+    }
+    blank_acc = warp_sum(blank_acc);
+    if (lane == 0) atomicAdd(gr + (int64_t)blank * gc, -blank_acc * g);
+}
+
+// ------------------------------------------------------------------------------------------
+// ctc.alignment (ctc.py:6-75)
+// ------------------------------------------------------------------------------------------
+__global__ void ctc_align_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                 const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
+                                 const int64_t* __restrict__ tgt_len, int T, int L_max, int blank,
+                                 uint8_t* __restrict__ bp_ws, int64_t* __restrict__ out) {
+    extern __shared__ float sh[];
+    const float ZERO = -FLT_MAX;  // torch.finfo(float32).min, ctc.py:29
+    const int b = blockIdx.x;
+    const int S_max = 2 * L_max + 1;
+    int tl = (int)tgt_len[b];
+    if (tl > L_max) tl = L_max;
+    const int il = (int)in_len[b];
+    const int S = 2 * tl + 1;
+    float* buf0 = sh;  // index s+2
+    float* buf1 = sh + (S_max + 2);
+    const float* lpb = lp + (int64_t)b * sb;
+    uint8_t* bp = bp_ws + (size_t)b * T * S_max;
+
+    for (int l = threadIdx.x; l < L_max; l += blockDim.x) out[(size_t)b * L_max + l] = 0;
+
+    int ext[kCtcMaxPer];
+    bool diff[kCtcMaxPer];
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        ext[i] = blank;
+        diff[i] = false;
+        if (s < S) {
+            if (s & 1) ext[i] = (int)targets[(size_t)b * L_max + (s >> 1)];
+            if (s >= 2) {
+                const int e2 = ((s - 2) & 1) ? (int)targets[(size_t)b * L_max + ((s - 2) >> 1)] : blank;
+                diff[i] = ext[i] != e2;  // ctc.py:23-27 (blank vs blank -> False)
+            }
+        }
+    }
+    if (threadIdx.x < 2) { buf0[threadIdx.x] = ZERO; buf1[threadIdx.x] = ZERO; }
+#pragma unroll
+    for (int i = 0; i < kCtcMaxPer; ++i) {
+        const int s = threadIdx.x + i * blockDim.x;
+        if (s < S) buf0[s + 2] = (s < 2) ? lpb[(int64_t)ext[i] * sc] : ZERO;  // ctc.py:32-33
+    }
+    __syncthreads();
+    float* prev = buf0;
+    float* cur = buf1;
+    // NB: the reference runs the recursion over ALL T frames of the padded batch (ctc.py:47)
+    for (int t = 1; t < T; ++t) {
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            if (s < S) {
+                const float p0 = prev[s + 2];
+                const float p1 = prev[s + 1];
+                const float p2 = diff[i] ? prev[s] : ZERO;
+                float m = fmaxf(p0, fmaxf(p1, p2));
+                int arg = 0;  // first maximum wins: stay, then step, then skip (ctc.py:50)
+                if (p1 > p0) arg = 1;
+                if (p2 > fmaxf(p0, p1)) arg = 2;
+                const float ms = (fabsf(m) == INFINITY) ? 0.f : m;
+                const float lse = logf(expf(p0 - ms) + expf(p1 - ms) + expf(p2 - ms)) + ms;
+                cur[s + 2] = lpb[(int64_t)t * st + (int64_t)ext[i] * sc] + lse;
+                bp[(size_t)t * S_max + s] = (uint8_t)arg;
+            }
+        }
+        __syncthreads();
+        float* tmp = prev; prev = cur; cur = tmp;
+    }
+    if (threadIdx.x == 0 && il >= 1) {
+        // terminal state from log_alpha after the FULL loop (global T-1), ctc.py:56-61
+        const float l1 = prev[(2 * tl - 1) + 2];  // tl == 0 reads the guard cell (= ZERO)
+        const float l2 = prev[(2 * tl) + 2];
+        int s = 2 * tl - 1 + (l2 > l1 ? 1 : 0);
+        if (s < 0) s = 0;
+        int last_state = -1;
+        for (int t = il - 1; t >= 0; --t) {
+            if (s != last_state) {
+                if (s & 1) out[(size_t)b * L_max + (s >> 1)] = t;  // last frame spent in label s
+                last_state = s;
+            }
+            if (t > 0) {
+                s -= (int)bp[(size_t)t * S_max + s];
+                if (s < 0) s = 0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// log_softmax + argmax over dim 1 of [B, C, T]; block = (32 t) x (8 class groups)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+log_softmax_argmax_kernel(const float* __restrict__ x, int B, int C, int T, float* __restrict__ out,
+                          int* __restrict__ amax) {
+    __shared__ float s_m[8][33], s_s[8][33];
+    __shared__ int s_i[8][33];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const bool ok = t < T;
+    const float* xb = x + (size_t)b * C * T;
+    float m = -INFINITY, s = 0.f;
+    int im = 0x7fffffff;
+    if (ok) {
+        for (int c = grp; c < C; c += 8) {
+            const float v = xb[(size_t)c * T + t];
+            if (v > m) { s = s * expf(m - v) + 1.f; m = v; im = c; }
+            else if (v == -INFINITY && m == -INFINITY) { if (im == 0x7fffffff) im = c; }
+            else s += expf(v - m);
+        }
+    }
+    s_m[grp][lane] = m; s_s[grp][lane] = s; s_i[grp][lane] = im;
+    __syncthreads();
+    float M = -INFINITY; int IM = 0x7fffffff;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float mg = s_m[g][lane]; const int ig = s_i[g][lane];
+        if (mg > M || (mg == M && ig < IM)) { M = mg; IM = ig; }
+    }
+    float Ssum = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const float mg = s_m[g][lane];
+        if (mg != -INFINITY) Ssum += s_s[g][lane] * expf(mg - M);
+    }
+    const float lse = M + logf(Ssum);
+    if (ok) {
+        if (out != nullptr) {
+            float* ob = out + (size_t)b * C * T;
+            for (int c = grp; c < C; c += 8) ob[(size_t)c * T + t] = xb[(size_t)c * T + t] - lse;
+        }
+        if (amax != nullptr && grp == 0) amax[(size_t)b * T + t] = IM == 0x7fffffff ? 0 : IM;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ lp, const float* __restrict__ go, int B, int C, int T,
+                       float* __restrict__ gi) {
+    __shared__ float s_s[8][33];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const bool ok = t < T;
+    const size_t base = (size_t)b * C * T;
+    float s = 0.f;
+    if (ok) for (int c = grp; c < C; c += 8) s += go[base + (size_t)c * T + t];
+    s_s[grp][lane] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) tot += s_s[g][lane];
+    if (ok)
+        for (int c = grp; c < C; c += 8) {
+            const size_t o = base + (size_t)c * T + t;
+            gi[o] = go[o] - expf(lp[o]) * tot;
+        }
+}
+
+// ------------------------------------------------------------------------------------------
+// top-K class ids per frame (K <= 8), ties -> lowest id first
+// ------------------------------------------------------------------------------------------
+constexpr int kTopKMax = 8;
+__global__ void topk_ids_kernel(const float* __restrict__ x, int B, int C, int T, int K, int* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* xb = x + (size_t)b * C * T;
+    float v[kTopKMax];
+    int id[kTopKMax];
+#pragma unroll
+    for (int k = 0; k < kTopKMax; ++k) { v[k] = -INFINITY; id[k] = -1; }
+    for (int c = 0; c < C; ++c) {
+        float cv = xb[(size_t)c * T + t];
+        int ci = c;
+        // insert keeping (value desc, id asc); strict > keeps earlier ids first on ties
+#pragma unroll
+        for (int k = 0; k < kTopKMax; ++k) {
+            if (k < K && (cv > v[k] || id[k] < 0)) {
+                const float tv = v[k]; const int ti = id[k];
+                v[k] = cv; id[k] = ci; cv = tv; ci = ti;
+                if (ci < 0) break;
+            }
+        }
+    }
+    for (int k = 0; k < K; ++k) out[((size_t)b * K + k) * T + t] = id[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// greedy CTC collapse state machine (transcript_generators.py:32-83), one utterance / thread
+// ------------------------------------------------------------------------------------------
+__global__ void greedy_collapse_kernel(const int* __restrict__ ids, const int* __restrict__ lengths, int B,
+                                       int T, int C, int eps_id, int space_id,
+                                       const uint8_t* __restrict__ is_silence,
+                                       const uint8_t* __restrict__ is_word_start, int blank_to_space,
+                                       int* __restrict__ out_tok, int* __restrict__ out_frm, int T_cap,
+                                       int* __restrict__ out_cnt) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int* row = ids + (size_t)b * T;
+    int* tok = out_tok + (size_t)b * T_cap;
+    int* frm = out_frm + (size_t)b * T_cap;
+    const int len = lengths ? lengths[b] : T;
+    int t = 0;
+    // leading silence is skipped over the FULL row, not just `len` (transcript_generators.py:38-40)
+    while (t < T) {
+        const int x = row[t];
+        const bool sil = (x >= 0 && x < C) ? is_silence[x] != 0 : false;
+        if (!sil) break;
+        ++t;
+    }
+    if (t >= T) { out_cnt[b] = -1; return; }
+    int last = eps_id;  // tokens = [eps]
+    bool allow_repeat = false;
+    int count_eps = 0, n = 0;
+    for (; t < len && t < T; ++t) {
+        const int x = row[t];
+        if (x == eps_id && last == space_id) continue;
+        if (x == eps_id) {
+            allow_repeat = true;
+            ++count_eps;
+            const bool last_ws = (last >= 0 && last < C) ? is_word_start[last] != 0 : false;
+            if (count_eps >= blank_to_space && !last_ws) {
+                if (n < T_cap) { tok[n] = space_id; frm[n] = -(t + 1); }
+                ++n;
+                last = space_id;
+            }
+            continue;
+        } else if (x == last && !allow_repeat) {
+            continue;
+        }
+        allow_repeat = false;
+        if (n < T_cap) { tok[n] = x; frm[n] = t; }
+        ++n;
+        last = x;
+        count_eps = 0;
+    }
+    out_cnt[b] = n < T_cap ? n : T_cap;
+}
+
+// ------------------------------------------------------------------------------------------
+// entropy / weighted_mean_entropy (models.py:645-673), block per utterance
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+entropy_kernel(const float* __restrict__ lp, const int64_t* __restrict__ lengths, int B, int C, int T,
+               int eps_id, float* __restrict__ out_e, float* __restrict__ out_w) {
+    const int b = blockIdx.x;
+    const float* xb = lp + (size_t)b * C * T;
+    const int len = lengths ? (int)lengths[b] : T;
+    const int eid = eps_id < 0 ? C + eps_id : eps_id;
+    float se = 0.f, sew = 0.f, sw = 0.f;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        float e = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float l = xb[(size_t)c * T + t];
+            e -= expf(l) * l;
+        }
+        float w = 1.f - expf(xb[(size_t)eid * T + t]);
+        const bool in = t < len;
+        if (lengths != nullptr) { if (!in) w = 0.f; }
+        if (lengths == nullptr || in) se += e;
+        sew += e * w;
+        sw += w;
+    }
+    __shared__ float red[3][8];
+    se = warp_sum(se); sew = warp_sum(sew); sw = warp_sum(sw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = se; red[1][warp] = sew; red[2][warp] = sw; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, bq = 0.f, c = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[0][i]; bq += red[1][i]; c += red[2][i]; }
+        if (out_e) out_e[b] = lengths ? a / (1e-9f + (float)len) : a / (float)T;
+        if (out_w) out_w[b] = bq / (1e-9f + c);
+    }
+}
+
+static int ctc_threads(int S_max) {
+    int th = ((S_max + kCtcMaxPer - 1) / kCtcMaxPer + 31) / 32 * 32;
+    // prefer one state per thread while that stays within a 1024-thread block
+    int one = (S_max + 31) / 32 * 32;
+    if (one <= 1024) th = one;
+    if (th < 32) th = 32;
+    return th;
+}
+
+}  // namespace cab
+
+using namespace cab;
+
+#define CTC_COMMON_CHECKS()                                                                       \
+    CAB_CHECK_ARG(log_probs && targets && input_lengths && target_lengths, "null pointer argument"); \
+    CAB_CHECK_ARG(B > 0 && T > 0 && C > 0 && L_max >= 0, "bad shape B=%d T=%d C=%d L=%d", B, T, C, L_max); \
+    CAB_CHECK_ARG(blank >= 0 && blank < C, "blank=%d out of range", blank);                       \
+    const int S_max = 2 * L_max + 1;                                                              \
+    CAB_CHECK_ARG(S_max <= kCtcMaxPer * 1024, "target too long: L_max=%d", L_max);                \
+    const int threads = ctc_threads(S_max);                                                       \
+    const size_t smem = sizeof(float) * 2 * (S_max + 2);
+
+extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
+                                const int64_t* targets, const int64_t* input_lengths,
+                                const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                                float* ws_alpha, float* nll, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTC_COMMON_CHECKS();
+    CAB_CHECK_ARG(ws_alpha && nll, "null workspace/output");
+    ctc_alpha_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                   input_lengths, target_lengths, T, C, L_max, blank,
+                                                   ws_alpha, nll);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
+                                const int64_t* targets, const int64_t* input_lengths,
+                                const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                                const float* ws_alpha, float* ws_beta, const float* nll,
+                                const float* grad_out, float* grad, int64_t gstride_t, int64_t gstride_b,
+                                int64_t gstride_c, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTC_COMMON_CHECKS();
+    CAB_CHECK_ARG(ws_alpha && ws_beta && nll && grad_out && grad, "null workspace/output");
+    ctc_beta_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                  input_lengths, target_lengths, T, C, L_max, blank, ws_beta);
+    CAB_CHECK_LAUNCH();
+    {
+        const int64_t n = (int64_t)B * T * C;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        ctc_grad_init_kernel<<<blocks, 256, 0, stream>>>(log_probs, stride_t, stride_b, stride_c, input_lengths,
+                                                         grad_out, B, T, C, grad, gstride_t, gstride_b, gstride_c);
+        CAB_CHECK_LAUNCH();
+    }
+    {
+        dim3 grid((T + 7) / 8, B);
+        ctc_grad_scatter_kernel<<<grid, 256, 0, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                          input_lengths, target_lengths, T, L_max, blank, ws_alpha,
+                                                          ws_beta, nll, grad_out, grad, gstride_t, gstride_b,
+                                                          gstride_c);
+        CAB_CHECK_LAUNCH();
+    }
+    g_launch_count.fetch_add(3, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_ctc_alignment(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
+                                 const int64_t* targets, const int64_t* input_lengths,
+                                 const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                                 uint8_t* ws_backptr, int64_t* out_alignment, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CTC_COMMON_CHECKS();
+    CAB_CHECK_ARG(ws_backptr && out_alignment, "null workspace/output");
+    ctc_align_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                   input_lengths, target_lengths, T, L_max, blank, ws_backptr,
+                                                   out_alignment);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_log_softmax_argmax(const void* logits, int in_dtype, int B, int C, int T,
+                                      float* out_log_probs, int32_t* out_argmax, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(logits != nullptr, "null logits");
+    CAB_CHECK_ARG(in_dtype == 0, "only fp32 logits are supported (in_dtype=%d)", in_dtype);
+    CAB_CHECK_ARG(B > 0 && C > 0 && T > 0, "bad shape");
+    dim3 grid((T + 31) / 32, B);
+    log_softmax_argmax_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), B, C, T,
+                                                        out_log_probs, out_argmax);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_log_softmax_bwd(const float* log_probs, const float* grad_out, int B, int C, int T,
+                                   float* grad_in, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(log_probs && grad_out && grad_in, "null pointer argument");
+    dim3 grid((T + 31) / 32, B);
+    log_softmax_bwd_kernel<<<grid, 256, 0, stream>>>(log_probs, grad_out, B, C, T, grad_in);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_topk_ids(const float* log_probs, int B, int C, int T, int K, int32_t* out_ids,
+                            cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(log_probs && out_ids, "null pointer argument");
+    CAB_CHECK_ARG(K >= 1 && K <= kTopKMax && K <= C, "K=%d out of [1,%d] (C=%d)", K, kTopKMax, C);
+    dim3 grid((T + 127) / 128, B);
+    topk_ids_kernel<<<grid, 128, 0, stream>>>(log_probs, B, C, T, K, out_ids);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, int B, int T, int C, int eps_id,
+                                   int space_id, const uint8_t* is_silence, const uint8_t* is_word_start,
+                                   int blank_amount_to_space, int32_t* out_tokens, int32_t* out_frames, int T_cap,
+                                   int32_t* out_counts, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(ids && is_silence && is_word_start && out_tokens && out_frames && out_counts, "null pointer argument");
+    CAB_CHECK_ARG(B > 0 && T > 0 && T_cap > 0, "bad shape");
+    greedy_collapse_kernel<<<(B + 63) / 64, 64, 0, stream>>>(ids, lengths, B, T, C, eps_id, space_id, is_silence,
+                                                             is_word_start, blank_amount_to_space, out_tokens,
+                                                             out_frames, T_cap, out_counts);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_entropy(const float* log_probs, const int64_t* lengths, int B, int C, int T, int eps_id,
+                           float* out_entropy, float* out_weighted_entropy, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(log_probs != nullptr, "null log_probs");
+    entropy_kernel<<<B, 256, 0, stream>>>(log_probs, lengths, B, C, T, eps_id, out_entropy, out_weighted_entropy);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}

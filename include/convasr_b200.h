@@ -1,0 +1,207 @@
+/*
+ * convasr_b200 -- C ABI of the B200-native (sm_100a) acoustic-model hot path of convasr.
+ *
+ * The reference (vadimkantorov/convasr) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b); the boundary it exposes is the Python module surface
+ * `models / ctc / decoders / transcript_generators`.  This header is the C layer that the
+ * drop-in Python modules in `convasr_b200/` bind with ctypes.  Every entry point names the
+ * reference call site (file:line under the reference tree) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - the caller owns all buffers (including workspaces) and passes the CUDA stream;
+ *   - kernels never allocate, never synchronise;
+ *   - return value: 0 = ok, negative = error, message via cab_last_error() (thread local);
+ *   - "frac" lengths are the reference's fp32 fractions in (0, 1]: the integer length of a
+ *     row of extent T is ceil(fp32(frac) * T)  (models.py:611-614).
+ */
+#ifndef CONVASR_B200_H
+#define CONVASR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cab_stream_t; /* cudaStream_t */
+
+#define CAB_ABI_VERSION 1
+
+int cab_abi_version(void);
+const char* cab_last_error(void);
+/* number of kernels launched by this library since load (bench.py reports it) */
+int64_t cab_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * A1 + A2: signal normalisation + log-mel filterbank frontend
+ *   replaces models.normalize_signal (models.py:684-686) and
+ *   LogFilterBankFrontend.forward (models.py:565-597): x/(max|x|+1e-5) -> pre-emphasis
+ *   (y0=x0) -> *mask -> reflect pad (nfft/2) left / zero pad right -> STFT(nfft, hop, win
+ *   centred in nfft, center=False) -> re^2+im^2 -> mel matmul + eps -> log.
+ *   signal: [B, T] fp32 or int16 (int16 is cast without rescaling, models.py:568)
+ *   xlen_frac: [B] or NULL (no mask)
+ *   window: [win_length] fp32, mel_fb: [n_mels, nfft/2+1] fp32 row-major
+ *   mel_band: [n_mels, 2] int32, first / one-past-last non-zero bin of each mel filter
+ *   twiddle: [nfft/2] float2 (cos, -sin)(2*pi*k/nfft) computed by the host in fp64
+ *   out_logmel: [B, n_mels, F] fp32, F = T / hop + 1
+ *   ws_absmax: [B] fp32 workspace (written)
+ * ------------------------------------------------------------------------------------- */
+int cab_frontend_logmel(const void* signal, int signal_is_int16, const float* xlen_frac, int B,
+                        int T, int win_length, int hop, int nfft, int n_mels,
+                        const float* window, const float* mel_fb, const int32_t* mel_band,
+                        const float* twiddle, float preemphasis, float log_eps, int normalize_signal,
+                        float denom_multiplier, float* out_logmel, float* ws_absmax,
+                        cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A3 + A4: masked instance norm (models.py:694-719, called at :298-301) fused with the
+ *   layout change the conv stack wants: fp32 [B, C, F] -> bf16 channels-last [B, F_pad, C].
+ *   With xlen_frac: statistics over the valid frames only, biased variance, output exactly 0
+ *   for frames >= ceil(frac*F).  Without: plain biased instance norm over all F frames.
+ *   out_hi: bf16 [B, F_pad, C_pad]  (frames F..F_pad-1 and channels C..C_pad-1 are zeroed)
+ *   out_lo: NULL, or bf16 residual (x - float(hi)) for the split-bf16 "fp32" tier
+ *   out_f32: NULL, or fp32 [B, C, F] normalised features in the reference layout
+ *   ws_stats: [B, C, 2] fp32 workspace (mean, rstd)
+ * ------------------------------------------------------------------------------------- */
+int cab_instnorm_pack(const float* feat, const float* xlen_frac, int B, int C, int F, float eps,
+                      int F_pad, int C_pad, void* out_hi, void* out_lo, float* out_f32,
+                      float* ws_stats, cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A5-A9: Conv1d (+folded BatchNorm) + residual 1x1 convs + activation + temporal mask as ONE
+ *   tcgen05/TMEM implicit GEMM.  Replaces ConvBn1d.forward (models.py:127-139) in its
+ *   fuse_conv_bn_eval form (models.py:141-151), ResidualActivation.forward (models.py:357-371)
+ *   and the Decoder 1x1 projection + log_softmax + argmax
+ *   (models.py:23-44, :316; transcript_generators.py:27).
+ *
+ *   out[b, t, :] = act( bias + sum_src sum_tap W_src[tap] . x_src[b, t + tap*dil - pad_left, :] )
+ *                  * (t < ceil(frac_b * T_out))
+ *   Activations are bf16 channels-last; a "source" is one (activation tensor, packed weight)
+ *   pair: the main conv, each residual 1x1 conv, and -- in the split-bf16 "fp32" tier -- the
+ *   hi*hi, hi*lo, lo*hi partial products.  Stride-2 convs are expressed by the host as
+ *   stride-1 convs over the frame-pair view [B, T/2, 2C] with re-packed weights.
+ * ------------------------------------------------------------------------------------- */
+#define CAB_MAX_CONV_SOURCES 12
+
+typedef struct {
+    const void* act;   /* bf16 [B, T_rows, ld_ch]; rows >= T_in are never read (zero fill) */
+    const void* wgt;   /* bf16 [taps, w_rows, w_ld_ch] (K-major: channel contiguous) */
+    int32_t T_in;      /* valid rows per utterance */
+    int32_t T_rows;    /* allocated rows per utterance (batch stride = T_rows * ld_ch) */
+    int32_t ld_ch;     /* channels per activation row (allocation) */
+    int32_t ch_off;    /* first channel of this source inside the row */
+    int32_t C_in;      /* channels contracted, multiple of 64 */
+    int32_t w_rows;    /* output-channel rows in the packed weight */
+    int32_t w_ld_ch;   /* channels per weight row (allocation) */
+    int32_t w_ch_off;  /* first channel inside the weight row */
+    int32_t taps, dilation, pad_left;
+} cab_conv_source_t;
+
+enum { CAB_ACT_NONE = 0, CAB_ACT_RELU = 1, CAB_ACT_HARDTANH = 2, CAB_ACT_LEAKY_RELU = 3 };
+enum {
+    CAB_EPI_ACT_BF16 = 0,   /* bf16 channels-last activation (+ optional lo residual) */
+    CAB_EPI_LOGSOFTMAX = 1, /* fp32 [B,C,T] logits + log_probs + int32 argmax, C <= 256 */
+    CAB_EPI_LOGITS_F32 = 2  /* fp32 [B,C,T] logits only (large vocabularies) */
+};
+
+typedef struct {
+    int32_t B, T_out, C_out; /* C_out: real output channels / classes */
+    int32_t block_n;         /* N tile: multiple of 16 (32 for ACT_BF16), <= 256; 0 = auto */
+    int32_t epilogue;        /* CAB_EPI_* */
+    int32_t act;             /* CAB_ACT_* */
+    float act_a, act_b;      /* hardtanh (min,max) or leaky slope in act_a */
+    const float* bias;       /* [C_out] fp32 or NULL */
+    const float* xlen_frac;  /* [B] or NULL: temporal mask (ACT_BF16 only) */
+    void* out_hi;            /* ACT_BF16: bf16 [B, out_T_rows, out_ld_ch] */
+    void* out_lo;            /* ACT_BF16: NULL or bf16 residual of the fp32 value */
+    int32_t out_T_rows, out_ld_ch;
+    float* logits;           /* LOGSOFTMAX / LOGITS_F32: fp32 [B, C_out, T_out] or NULL */
+    float* log_probs;        /* LOGSOFTMAX: fp32 [B, C_out, T_out] or NULL */
+    int32_t* argmax;         /* LOGSOFTMAX: int32 [B, T_out] or NULL (ties -> lowest id) */
+} cab_conv_epilogue_t;
+
+int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
+                     const cab_conv_epilogue_t* epilogue_host, cab_stream_t stream);
+
+/* grouped Conv1d + bias + ReLU of the separable blocks (models.py:50-64): bf16 channels-last
+ * in/out, weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1. */
+int cab_grouped_conv1d_relu(const void* act, int B, int T, int T_rows, int C_in, const float* wgt,
+                            const float* bias, int C_out, int groups, int k, int pad_left,
+                            void* out, int out_T_rows, cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A10 (+A13/A14 argmax): log_softmax over the class dim of [B, C, T] (models.py:316) fused
+ *   with the per-frame argmax (transcript_generators.py:27).  in_dtype: 0 fp32, 1 bf16.
+ * ------------------------------------------------------------------------------------- */
+int cab_log_softmax_argmax(const void* logits, int in_dtype, int B, int C, int T,
+                           float* out_log_probs, int32_t* out_argmax, cab_stream_t stream);
+/* backward of log_softmax over dim 1: gin = gout - exp(lp) * sum_c gout */
+int cab_log_softmax_bwd(const float* log_probs, const float* grad_out, int B, int C, int T,
+                        float* grad_in, cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A11: CTC loss, the arithmetic of torch.nn.functional.ctc_loss(reduction='none',
+ *   zero_infinity=False) as called at models.py:323.  log_probs is addressed through
+ *   element strides so both [T,B,C] and the permuted [B,C,T] view work without a copy.
+ *   targets: int64 [B, L_max] padded; input_lengths / target_lengths: int64 [B].
+ *   ws_alpha / ws_beta: fp32 [B, T, 2*L_max+1] workspaces.  nll: fp32 [B].
+ *   The backward returns ATen's convention: (exp(lp) - occupancy) * grad_out, zero for
+ *   t >= input_length, laid out like log_probs (grad strides given separately).
+ * ------------------------------------------------------------------------------------- */
+int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
+                     const int64_t* targets, const int64_t* input_lengths,
+                     const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                     float* ws_alpha, float* nll, cab_stream_t stream);
+int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
+                     const int64_t* targets, const int64_t* input_lengths,
+                     const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                     const float* ws_alpha, float* ws_beta, const float* nll,
+                     const float* grad_out, float* grad, int64_t gstride_t, int64_t gstride_b,
+                     int64_t gstride_c, cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A12: forced alignment, ctc.alignment (ctc.py:6-75) with all of its quirks: finite "zero"
+ *   (finfo.min), logsumexp alpha with argmax back-pointers (stay preferred on ties), the
+ *   recursion runs over all T frames of the padded batch, terminal state read at global T-1,
+ *   back-trace from input_length-1, output = last frame index per target label.
+ *   ws_backptr: uint8 [B, T, 2*L_max+1] workspace.  out: int64 [B, L_max].
+ * ------------------------------------------------------------------------------------- */
+int cab_ctc_alignment(const float* log_probs, int64_t stride_t, int64_t stride_b,
+                      int64_t stride_c, const int64_t* targets, const int64_t* input_lengths,
+                      const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
+                      uint8_t* ws_backptr, int64_t* out_alignment, cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A13: GreedyDecoder.decode (decoders.py:5-16): per-frame top-K class ids of [B, C, T],
+ *   out int32 [B, K, T], ordered by descending value, ties -> lowest id first.
+ * ------------------------------------------------------------------------------------- */
+int cab_topk_ids(const float* log_probs, int B, int C, int T, int K, int32_t* out_ids,
+                 cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * A14: the collapse state machine of GreedyCTCGenerator.generate
+ *   (transcript_generators.py:32-83) on device: one utterance per thread.
+ *   ids: int32 [B, T] per-frame argmax; lengths: int32 [B] (loop bound, "sample_len").
+ *   is_silence / is_word_start: uint8 [C] token class tables.
+ *   out_tokens / out_frames: int32 [B, T_cap]; out_frames[i] is the frame the token came
+ *   from, or -(frame+1) for a space synthesised by the blank_amount_to_space rule.
+ *   out_counts: int32 [B]; -1 marks "only silence in the whole row" (empty transcript).
+ * ------------------------------------------------------------------------------------- */
+int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, int B, int T, int C,
+                        int eps_id, int space_id, const uint8_t* is_silence,
+                        const uint8_t* is_word_start, int blank_amount_to_space,
+                        int32_t* out_tokens, int32_t* out_frames, int T_cap, int32_t* out_counts,
+                        cab_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * section 8(f) "next" #1: uncertainty reductions on log_probs (models.py:645-678), fused:
+ *   per utterance entropy (masked mean) and weighted_mean_entropy with eps_id weights.
+ * ------------------------------------------------------------------------------------- */
+int cab_entropy(const float* log_probs, const int64_t* lengths, int B, int C, int T, int eps_id,
+                float* out_entropy, float* out_weighted_entropy, cab_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONVASR_B200_H */
