@@ -1,0 +1,71 @@
+"""Import the REAL reference (read-only tree at /root/reference) on CPU, with stub modules for
+the dependencies this image lacks.
+
+TEST INFRASTRUCTURE ONLY, and only usable where /root/reference exists (the build container):
+it is used by oracle/make_golden.py to mint tests/golden/ and by the `reference`-marked tests
+that pin oracle/oracle.py against the reference itself.  Nothing is copied from the reference.
+"""
+import importlib
+import importlib.machinery
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get('CONVASR_REFERENCE_DIR', '/root/reference')
+
+
+def available():
+	return os.path.isfile(os.path.join(REFERENCE_DIR, 'models.py'))
+
+
+_CACHE = {}
+
+
+def load():
+	"""Returns a namespace with the reference modules: models, ctc, decoders, transcript_generators,
+	text_tokenizers."""
+	if _CACHE:
+		return types.SimpleNamespace(**_CACHE)
+	if not available():
+		raise RuntimeError(f'reference tree not found at {REFERENCE_DIR}')
+	import numpy as np
+	import torchaudio
+
+	for name in ('onnxruntime', 'apex', 'librosa', 'soundfile', 'Levenshtein'):
+		if name not in sys.modules:
+			m = types.ModuleType(name)
+			m.__spec__ = importlib.machinery.ModuleSpec(name, None)  # torch._dynamo needs a real spec
+			sys.modules[name] = m
+	librosa = sys.modules['librosa']
+	# the only missing arithmetic: librosa's Slaney mel basis == torchaudio's (6.5e-8)
+	librosa.filters = types.SimpleNamespace(
+		mel = lambda sr, n_fft, n_mels = 128, fmin = 0., fmax = None: torchaudio.functional.
+		melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax), n_mels, sr, norm = 'slaney', mel_scale = 'slaney').T.numpy()
+	)
+	librosa.util = types.SimpleNamespace(pad_center = lambda w, size: np.pad(w, ((size - len(w)) // 2, ) * 2))
+
+	# the reference modules are imported by bare name; keep them out of the way of the drop-in
+	# modules of the same names by importing under a private prefix
+	saved_path = list(sys.path)
+	saved_modules = {n: sys.modules.get(n) for n in ('models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers', 'shaping', 'transcripts')}
+	for n in saved_modules:
+		sys.modules.pop(n, None)
+	sys.path.insert(0, REFERENCE_DIR)
+	try:
+		for n in ('shaping', 'transcripts', 'models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers'):
+			_CACHE[n] = importlib.import_module(n)
+	finally:
+		sys.path[:] = saved_path
+		for n, m in saved_modules.items():
+			sys.modules.pop(n, None)
+			if m is not None:
+				sys.modules[n] = m
+	return types.SimpleNamespace(**_CACHE)
+
+
+def make_model(name = 'Wav2Letter', num_classes = (38, ), frontend = True, **kwargs):
+	ref = load()
+	fe = ref.models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window') if frontend else None
+	model = getattr(ref.models, name)(64, list(num_classes), frontend = fe, dropout = 0., **kwargs)
+	model.check_time_dim_padded = False  # Wav2Letter's ctor does not accept the kwarg (models.py:820-835)
+	return model.eval()

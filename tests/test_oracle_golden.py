@@ -1,0 +1,113 @@
+"""The oracle (oracle/oracle.py) against the golden vectors minted from the real reference
+(tests/golden/, generator oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+
+def rel(a, b):
+	return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+def test_mel_filterbank_matches_reference(golden):
+	g = golden('frontend')
+	mel = O.slaney_mel_filterbank(8000, 256, 64, 0.0, 4000)
+	assert mel.shape == g['mel'].shape
+	assert float((mel - g['mel']).abs().max()) < 2e-7  # 6.5e-8 between librosa restatements
+	assert torch.equal(torch.hann_window(160, periodic = True), g['window'])
+
+
+def test_frontend_and_instance_norm(golden):
+	g = golden('frontend')
+	for c in g['cases']:
+		logmel = O.frontend_logmel(c['signal'], c['xlen'], mel = g['mel'])
+		assert logmel.shape == c['logmel'].shape, c['name']
+		assert float((logmel - c['logmel']).abs().max()) < 5e-5, c['name']  # fp32 log-mel, SURVEY appendix C: 7.6e-6
+		feats = O.masked_instance_norm(c['logmel'], c['xlen'])
+		assert float((feats - c['feats']).abs().max()) < 1e-5, c['name']
+		if c['xlen'] is not None:  # padded frames are exactly zero
+			F = feats.shape[-1]
+			for b, n in enumerate(O.output_lengths(F, c['xlen']).tolist()):
+				assert float(feats[b, :, n:].abs().max() if n < F else 0.0) == 0.0
+
+
+def test_models_forward_and_loss(golden):
+	g = golden('models')
+	for c in g['cases']:
+		sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
+		assert abs(sum(float(v.double().abs().sum()) for v in sd.values() if v.is_floating_point()) - c['checksum']) < 1e-6 * c['checksum']
+		over = {k: v for k, v in c['kwargs'].items() if k in ('groups', )}
+		logits, log_probs, olen = O.model_forward(sd, c['signal'], c['xlen'], model = c['model'], **over)
+		assert torch.equal(olen[0], c['olen']), c['model']
+		# fused reference (case 1) == unfused oracle up to BN folding rounding (3.8e-7 rel)
+		assert rel(logits[0], c['logits']) < 1e-4, (c['model'], rel(logits[0], c['logits']))
+		assert rel(log_probs[0], c['log_probs']) < 1e-4
+		C = c['num_classes']
+		loss = O.ctc_loss_torch(log_probs[0].permute(2, 0, 1), c['y'][:, 0], olen[0], c['ylen'][:, 0], C - 1) / c['ylen'][:, 0]
+		assert torch.allclose(loss, c['loss'], rtol = 1e-3, atol = 1e-3), c['model']
+
+
+def test_ctc_loss_restatement_matches_torch(golden):
+	g = golden('ctc')
+	for c in g['cases']:
+		nll, grad = O.ctc_loss_np(c['log_probs'].numpy(), c['targets'].numpy(), c['input_lengths'].numpy(), c['target_lengths'].numpy(), c['blank'])
+		ref = c['loss'].double().numpy()
+		finite = np.isfinite(ref)
+		assert np.array_equal(np.isinf(nll), ~finite)
+		assert np.allclose(nll[finite], ref[finite], rtol = 1e-5)
+		if c['grad'] is not None:
+			assert np.allclose(grad, c['grad'].double().numpy(), atol = 1e-4)  # torch computes in fp32; nll ~ 1e2 => ~1e-5 abs noise
+
+
+def test_alignment_matches_reference(golden):
+	g = golden('ctc')
+	for c in g['cases']:
+		if c['alignment'] is None:
+			continue
+		al = O.ctc_alignment(c['log_probs'], c['targets'], c['input_lengths'], c['target_lengths'], c['blank'])
+		assert torch.equal(al, c['alignment'])
+
+
+def test_greedy_decode_and_generate(golden):
+	g = golden('decode')
+	tok = O.CharTokenizer(g['alphabet'])
+	assert (tok.eps_id, tok.space_id, len(tok.idx2char)) == (37, 36, 38)
+	for c in g['generate']:
+		B, T = len(c['ids']), len(c['ids'][0])
+		ts = [[t * 0.02 for t in range(T)]] * B if c['with_ts'] else None
+		# timestamps are float32 in the reference (torch tensor .tolist())
+		if ts is not None:
+			ts = (torch.arange(T)[None].float() * 0.02).expand(B, -1).tolist()
+		segs = O.greedy_generate(tok, c['ids'], c['olens'], ts, begin = [0.0] * B, end = [float(torch.tensor(T * 0.02))] * B)
+		assert segs == c['segments']
+	d = g['decode']
+	assert O.greedy_decode(d['lp1'], [4]) == d['d1'] == [[0, 0, 3, 1]]
+	assert O.greedy_decode(d['lp2'], K = 2) == d['d2'] == [[[0, 1], [1, 2]]]
+	assert O.greedy_decode(d['lp3'], [33, 20, 1, 7]) == d['d3']
+	assert O.greedy_decode(d['lp3'], [33, 20, 1, 7], K = 3) == d['d4']
+
+
+@pytest.mark.reference
+def test_oracle_against_live_reference():
+	"""Fresh seeded run of the real reference vs the oracle (beyond the frozen fixtures)."""
+	from oracle import reference_shim
+	ref = reference_shim.load()
+	model = reference_shim.make_model('Wav2Letter', (38, ), base_width = 16)
+	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
+	sd = O.synth_state_dict(shapes, seed = 5)
+	model.load_state_dict(sd, strict = False)
+	g = torch.Generator().manual_seed(11)
+	sig = (torch.randn(2, 9600, generator = g) * 2000).round().to(torch.int16)
+	xlen = torch.tensor([0.77, 1.0])
+	with torch.no_grad():
+		out = model(sig, xlen)
+	logits, log_probs, olen = O.model_forward(sd, sig, xlen, model = 'Wav2Letter')
+	assert torch.equal(olen[0], out['olen'][0])
+	assert rel(logits[0], out['logits'][0]) < 1e-4
+	lp = out['log_probs'][0]
+	y = torch.randint(0, 37, (2, 9), generator = g)
+	ylen = torch.tensor([9, 5])
+	al_ref = ref.ctc.alignment(lp.permute(2, 0, 1), y, olen[0], ylen, blank = 37)
+	assert torch.equal(O.ctc_alignment(lp.permute(2, 0, 1), y, olen[0], ylen, 37), al_ref)
