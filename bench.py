@@ -1,0 +1,331 @@
+"""Headline benchmark: audio-seconds per second (RTFx) of the Wav2Letter forward + CTC path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
+
+Workload (BASELINE.json configs[1] shape): Wav2Letter-char (66.5 M params, 38 classes), batch
+80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16 tier.  One step = one pass of the
+hot path over one batch: log-mel frontend -> instance norm -> 19 fused conv launches -> decoder +
+log_softmax + argmax -> CTC loss (alpha) -> CTC gradient w.r.t. the logits (beta + scatter).
+The conv-stack backward (dgrad/wgrad) is NOT part of the step (not native yet).
+
+value  = whole-job audio-seconds / second with the PCM already resident in HBM (CUDA events).
+e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM -> H2D,
+         model(x, xlen, y, ylen), D2H of the per-utterance loss and the greedy ids.
+N > 1  = utterance-sharded replicas (weak scaling, no data-path collective); time = max over ranks.
+--impl reference = the CPU oracle port of the reference path (torch CPU ops, all host threads)
+         on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+	sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOADS = {
+	# name: (model, num_classes, batch, seconds, precision)
+	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16'),
+	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32'),
+	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16'),
+}
+DEFAULT_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'
+SAMPLE_RATE = 8000
+
+
+def synth_batch(B, seconds, C, seed):
+	"""int16 PCM round(3000*N(0,1)), xlen ~ U(0.5, 1] with one full-length row,
+	targets never the blank, lengths such that an alignment exists."""
+	g = torch.Generator().manual_seed(seed)
+	T = int(seconds * SAMPLE_RATE)
+	sig = (torch.randn(B, T, generator = g) * 3000).round().clamp(-32767, 32767).to(torch.int16)
+	xlen = torch.rand(B, generator = g) * 0.5 + 0.5
+	xlen[0] = 1.0
+	t_out = (T // 80 + 1 - 1) // 2 + 1 + 2
+	t_min = int((xlen.min() * t_out).ceil())
+	L = int(0.45 * t_min)
+	ylen = torch.randint(max(1, int(0.2 * t_min / 2)), L + 1, (B, ), generator = g)
+	y = torch.randint(0, C - 1, (B, 1, L), generator = g)
+	return sig, xlen, y, ylen.unsqueeze(1)
+
+
+def model_shapes(model_name, C):
+	from convasr_b200 import models
+	m = getattr(models, model_name)(64, [C], dropout = 0.)
+	return {k: tuple(v.shape) for k, v in m.state_dict().items()}
+
+
+def conv_flops_per_step(model, B, F):
+	"""algorithmic 2*MAC of every conv (real channels, real frames, no padding), SURVEY.md 8(d)"""
+	import torch.nn as nn
+	total = 0
+	t = F
+	for block in model.backbone:
+		for seq in block.conv:
+			for conv in seq:
+				if isinstance(conv, nn.Conv1d):
+					t = (t + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) // conv.stride[0] + 1
+					total += 2 * B * t * conv.out_channels * (conv.in_channels // conv.groups) * conv.kernel_size[0]
+		for rc in block.conv_residual:
+			if isinstance(rc, nn.Conv1d):
+				total += 2 * B * t * rc.out_channels * rc.in_channels
+	d = model.decoder[0]
+	total += 2 * B * t * d.out_channels * d.in_channels
+	return total, t
+
+
+class ClockSampler:
+	"""nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+	def __init__(self, index):
+		self.index, self.rows, self.proc = index, [], None
+
+	def start(self):
+		q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+		try:
+			self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'], stdout = subprocess.PIPE, stderr = subprocess.DEVNULL, text = True)
+			threading.Thread(target = self._read, daemon = True).start()
+		except Exception:
+			self.proc = None
+
+	def _read(self):
+		for line in self.proc.stdout:
+			self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+	def stop(self, t0, t1):
+		if self.proc is None:
+			return None
+		time.sleep(0.15)
+		self.proc.terminate()
+		rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+		if not rows:
+			return None
+		try:
+			sm = sorted(float(r[0]) for r in rows)
+			reasons = set()
+			for r in rows:
+				for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], r[3:7]):
+					if v.lower().startswith('active'):
+						reasons.add(name)
+			return dict(sm_mhz = sm[len(sm) // 2], sm_max_mhz = float(rows[0][1]), power_w_max = max(float(r[2]) for r in rows), reasons = sorted(reasons), samples = len(rows))
+		except Exception:
+			return None
+
+
+def measured_peaks():
+	try:
+		return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+	except Exception:
+		return None
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (oracle/ is the checker AND the CPU baseline)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C):
+	from oracle import oracle as O
+	logits, log_probs, olen = O.model_forward(sd, sig, xlen, model = model_name)
+	lp = log_probs[0].permute(2, 0, 1).detach().requires_grad_(True)
+	loss = O.ctc_loss_torch(lp, y[:, 0], olen[0], ylen[:, 0], C - 1)
+	loss.sum().backward()  # CTC gradient w.r.t. the log-probs: the same work the native step does
+	return loss
+
+
+def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup):
+	from oracle import oracle as O
+	torch.set_num_threads(os.cpu_count())
+	shapes = {k: s for k, s in model_shapes(model_name, C).items() if not k.startswith('frontend.')}
+	sd = O.synth_state_dict(shapes, seed = 0)
+	sig, xlen, y, ylen = synth_batch(sample_B, seconds, C, seed = 0)
+	with torch.no_grad():
+		pass
+	for _ in range(warmup):
+		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C)
+	t0 = time.perf_counter()
+	for _ in range(steps):
+		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C)
+	dt = time.perf_counter() - t0
+	return sample_B * seconds * steps / dt, dt / steps
+
+
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument('--gpus', type = int, default = 1)
+	ap.add_argument('--steps', type = int, default = 50)
+	ap.add_argument('--warmup', type = int, default = 5)
+	ap.add_argument('--impl', default = 'native', choices = ['native', 'reference'])
+	ap.add_argument('--workload', default = DEFAULT_WORKLOAD, choices = sorted(WORKLOADS))
+	ap.add_argument('--no-cpu-baseline', action = 'store_true')
+	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
+	args = ap.parse_args()
+	model_name, C, B, seconds, precision = WORKLOADS[args.workload]
+	rank = int(os.environ.get('RANK', 0))
+	world = int(os.environ.get('WORLD_SIZE', 1))
+	local_rank = int(os.environ.get('LOCAL_RANK', 0))
+	steps, warmup = args.steps, max(args.warmup, 3)
+	config = dict(workload = args.workload, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision,
+				step = 'frontend+instnorm+conv stack+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)', parallelism = f'utterance-sharded replicas x{world}', l2 = 'flushed between timed steps (256 MiB memset)')
+
+	if args.impl == 'reference':
+		if rank != 0:
+			return
+		sB = args.cpu_sample_batch
+		n_steps = max(1, min(steps, 3))
+		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1)
+		line = dict(
+			impl = 'reference', metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = args.gpus, steps = n_steps, warmup = 1, ms_per_step = sec * 1e3,
+			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config,
+			cpu_baseline = dict(value = value, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, {n_steps} steps (oracle port: torch {torch.__version__} CPU ops)'),
+			e2e = dict(value = value, unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0), gpu_launches = 0
+		)
+		print(json.dumps(line))
+		return
+
+	# ------------------------------------------------------------------ native arm
+	assert torch.cuda.is_available(), 'bench.py --impl native needs a CUDA device'
+	torch.cuda.set_device(local_rank)
+	dev = torch.device('cuda', local_rank)
+	if world > 1:
+		import torch.distributed as dist
+		dist.init_process_group('nccl', device_id = dev)
+	from convasr_b200 import _lib, engine, models, ops
+	from oracle import oracle as O  # only for the seeded synthetic weights + the cpu_baseline leg
+
+	cpu_baseline = None
+	if rank == 0 and world == 1 and not args.no_cpu_baseline:
+		v, sec = run_cpu_baseline(model_name, C, seconds, args.cpu_sample_batch, 3, 1)
+		cpu_baseline = dict(value = v, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{args.cpu_sample_batch} x {seconds:g} s utterances per step, 3 steps after 1 warm-up ({sec:.2f} s/step; oracle port: torch {torch.__version__} CPU ops)')
+
+	frontend = models.LogFilterBankFrontend(64, SAMPLE_RATE, .02, .01, 'hann_window')
+	model = getattr(models, model_name)(64, [C], frontend = frontend, dropout = 0., check_time_dim_padded = False)
+	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
+	model.load_state_dict(O.synth_state_dict(shapes, seed = 0), strict = False)
+	model = model.to(dev).eval().set_precision(precision)
+	sig, xlen, y, ylen = synth_batch(B, seconds, C, seed = 1000 + rank)
+	sig_pin, xlen_pin, y_pin, ylen_pin = [t.pin_memory() for t in (sig, xlen, y, ylen)]
+	sig_d, xlen_d, y_d, ylen_d = [t.to(dev) for t in (sig, xlen, y, ylen)]
+	flush = torch.empty(256 << 20, dtype = torch.uint8, device = dev)
+	F = sig.shape[1] // 80 + 1
+	flops, t_out = conv_flops_per_step(model, B, F)
+
+	def step_device():
+		# grad w.r.t. the log-probs/logits only: CTC alpha -> beta -> gradient scatter
+		with torch.no_grad():
+			out = model(sig_d, xlen_d)
+		lp = out['log_probs'][0].requires_grad_(True)
+		nll = ops.ctc_loss(lp.permute(2, 0, 1), y_d[:, 0], out['olen'][0], ylen_d[:, 0], blank = C - 1)
+		nll.sum().backward()
+		return nll, lp
+
+	def step_e2e():
+		s = sig_pin.to(dev, non_blocking = True)
+		xl = xlen_pin.to(dev, non_blocking = True)
+		yy = y_pin.to(dev, non_blocking = True)
+		yl = ylen_pin.to(dev, non_blocking = True)
+		out = model(s, xl, y = yy, ylen = yl)
+		loss_h = out['loss'].cpu()
+		ids_h = out['log_probs'][0]._convasr_argmax.cpu()
+		return loss_h, ids_h
+
+	def barrier():
+		if world > 1:
+			torch.distributed.barrier()
+		torch.cuda.synchronize()
+
+	def timed(fn, n):
+		evs = []
+		for _ in range(n):
+			flush.zero_()
+			e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+			e0.record()
+			fn()
+			e1.record()
+			evs.append((e0, e1))
+		torch.cuda.synchronize()
+		return sum(a.elapsed_time(b) for a, b in evs)  # ms
+
+	for _ in range(warmup):
+		nll, _ = step_device()
+	torch.cuda.synchronize()
+	assert bool(torch.isfinite(nll).all()), 'synthetic targets must admit an alignment'
+	sampler = ClockSampler(local_rank)
+	if rank == 0:
+		sampler.start()
+	barrier()
+	launches0 = _lib.launch_count()
+	t_wall0 = time.time()
+	ms = timed(step_device, steps)
+	barrier()
+	t_wall1 = time.time()
+	launches = _lib.launch_count() - launches0
+	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+	# dominant kernel (conv1d_umma_kernel): per-launch CUDA events on the launching stream
+	conv_events = []
+	orig = ops.conv1d_fused
+
+	def traced(*a, **k):
+		e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+		e0.record()
+		orig(*a, **k)
+		e1.record()
+		conv_events.append((e0, e1))
+
+	ops.conv1d_fused = traced
+	n_prof = min(steps, 5)
+	for _ in range(n_prof):
+		flush.zero_()
+		step_device()
+	torch.cuda.synchronize()
+	ops.conv1d_fused = orig
+	conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / n_prof
+	n_conv = len(conv_events) // n_prof
+
+	# end to end through the public API with host buffers
+	for _ in range(3):
+		step_e2e()
+	barrier()
+	ms_e2e = timed(step_e2e, steps)
+	barrier()
+
+	if world > 1:
+		t = torch.tensor([ms, ms_e2e], device = dev, dtype = torch.float64)
+		torch.distributed.all_reduce(t, op = torch.distributed.ReduceOp.MAX)
+		ms, ms_e2e = t.tolist()
+	if rank != 0:
+		if world > 1:
+			torch.distributed.destroy_process_group()
+		return
+
+	audio_s = B * seconds * world
+	value = audio_s * steps / (ms / 1e3)
+	e2e_value = audio_s * steps / (ms_e2e / 1e3)
+	peaks = measured_peaks()
+	peak = peaks['bf16_tflops_sustained'] if peaks else 1590.0
+	achieved = flops / (conv_ms / 1e3) / 1e12
+	passes = 3 if precision == 'fp32' else 1
+	roofline = dict(
+		bound = 'tensor', kernel = 'conv1d_umma_kernel', achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
+		peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
+		peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = None, launches_per_step = n_conv, kernel_ms_per_step = conv_ms,
+		algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = passes, share_of_step = conv_ms / (ms / steps)
+	)
+	line = dict(
+		metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = world, steps = steps, warmup = warmup, ms_per_step = ms / steps, higher_is_better = True,
+		scaling = 'weak', vs_baseline = None, dtype = 'bf16' if precision == 'bf16' else 'bf16x3 (split-bf16, fp32 accumulate)', data = 'synthetic', config = config,
+		e2e = dict(value = e2e_value, unit = 'audio-s/s', ms_per_step = ms_e2e / steps, h2d_bytes_per_step = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen)), d2h_bytes_per_step = B * 4 + B * t_out * 4),
+		gpu_launches = launches, roofline = roofline, cpu_baseline = cpu_baseline, clocks = clocks
+	)
+	print(json.dumps(line))
+	if world > 1:
+		torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+	main()

@@ -35,17 +35,17 @@ class ConvEpilogue(ctypes.Structure):
 
 ACT_NONE, ACT_RELU, ACT_HARDTANH, ACT_LEAKY_RELU = 0, 1, 2, 3
 EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
-MAX_CONV_SOURCES = 12
+MAX_CONV_SOURCES = 18
 
 # name -> argtypes; every function returns int except the three introspection calls
 SIGNATURES = {
 	'cab_frontend_logmel': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
-	'cab_instnorm_pack': [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
-						c_void_p, c_void_p],
+	'cab_instnorm_pack': [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+						c_void_p, c_void_p, c_void_p],
 	'cab_conv1d_fused': [ctypes.POINTER(ConvSource), c_int, ctypes.POINTER(ConvEpilogue), c_void_p],
-	'cab_grouped_conv1d_relu': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-								c_void_p, c_int, c_void_p],
+	'cab_grouped_conv1d_relu': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+								c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
 	'cab_log_softmax_argmax': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 	'cab_log_softmax_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
 	'cab_ctc_loss_fwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -303,7 +303,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                             const int c = n0 + c0 + j;
                             if (c < C) {
                                 float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c) : 0.f);
-                                p.logits[(size_t(b) * C + c) * p.T_out + t] = x;
+                                p.logits[(size_t(b) * C + c) * p.T_out + t] = apply_act(x, p.act, p.act_a, p.act_b);
                             }
                         }
                     }

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256)
 instnorm_pack_kernel(const float* __restrict__ feat, const float* __restrict__ xlen,
                      const float* __restrict__ stats, int B, int C, int F, int F_pad, int C_pad,
                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                     float* __restrict__ out_f32) {
+                     float* __restrict__ out_f32, int normalize) {
     extern __shared__ float tile[];  // [kPackFrames][C_pad + 1]
     const int b = blockIdx.y;
     const int f0 = blockIdx.x * kPackFrames;
@@ -272,8 +272,11 @@ instnorm_pack_kernel(const float* __restrict__ feat, const float* __restrict__ x
         const int f = f0 + lane;
         float v = 0.f;
         if (c < C && f < n) {
-            const float mean = stats[2 * (b * C + c)], sd = stats[2 * (b * C + c) + 1];
-            v = __fdiv_rn(feat[(size_t(b) * C + c) * F + f] - mean, sd);
+            v = feat[(size_t(b) * C + c) * F + f];
+            if (normalize) {
+                const float mean = stats[2 * (b * C + c)], sd = stats[2 * (b * C + c) + 1];
+                v = __fdiv_rn(v - mean, sd);
+            }
         }
         if (out_f32 != nullptr && c < C && f < F) out_f32[(size_t(b) * C + c) * F + f] = v;
         tile[lane * ldt + c] = v;
@@ -286,7 +289,7 @@ instnorm_pack_kernel(const float* __restrict__ feat, const float* __restrict__ x
             const float v = tile[fl * ldt + c];
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             const size_t o = (size_t(b) * F_pad + f) * C_pad + c;
-            out_hi[o] = h;
+            if (out_hi != nullptr) out_hi[o] = h;
             if (out_lo != nullptr) out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
         }
     }
@@ -349,13 +352,13 @@ extern "C" int cab_frontend_logmel(const void* signal, int signal_is_int16, cons
 }
 
 extern "C" int cab_instnorm_pack(const float* feat, const float* xlen_frac, int B, int C, int F,
-                                 float eps, int F_pad, int C_pad, void* out_hi, void* out_lo,
-                                 float* out_f32, float* ws_stats, cab_stream_t stream_) {
+                                 float eps, int normalize, int F_pad, int C_pad, void* out_hi,
+                                 void* out_lo, float* out_f32, float* ws_stats, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(feat && ws_stats, "null pointer argument");
     CAB_CHECK_ARG(out_hi || out_f32, "no output requested");
     CAB_CHECK_ARG(B > 0 && C > 0 && F > 0 && F_pad >= F && C_pad >= C, "bad shape B=%d C=%d F=%d F_pad=%d C_pad=%d", B, C, F, F_pad, C_pad);
-    {
+    if (normalize) {
         const int warps = B * C;
         const int blocks = (warps * 32 + 255) / 256;
         instnorm_stats_kernel<<<blocks, 256, 0, stream>>>(feat, xlen_frac, B, C, F, eps, ws_stats);
@@ -363,13 +366,12 @@ extern "C" int cab_instnorm_pack(const float* feat, const float* xlen_frac, int 
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
     }
     {
-        CAB_CHECK_ARG(out_hi != nullptr, "out_hi is required (bf16 channels-last output)");
         dim3 grid((F_pad + kPackFrames - 1) / kPackFrames, B);
         size_t smem = sizeof(float) * kPackFrames * (C_pad + 1);
         CAB_CHECK_ARG(smem <= 48 * 1024, "C_pad=%d too large for the pack tile", C_pad);
         instnorm_pack_kernel<<<grid, 256, smem, stream>>>(feat, xlen_frac, ws_stats, B, C, F, F_pad, C_pad,
                                                           static_cast<__nv_bfloat16*>(out_hi),
-                                                          static_cast<__nv_bfloat16*>(out_lo), out_f32);
+                                                          static_cast<__nv_bfloat16*>(out_lo), out_f32, normalize);
         CAB_CHECK_LAUNCH();
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
     }

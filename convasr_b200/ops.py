@@ -84,20 +84,21 @@ def frontend_logmel(
 	return out
 
 
-def instnorm_pack(feat, xlen, eps, F_pad = None, C_pad = None, want_lo = False, want_f32 = False):
+def instnorm_pack(feat, xlen, eps, F_pad = None, C_pad = None, want_lo = False, want_f32 = False, want_hi = None, normalize = True):
 	"""fp32 [B,C,F] -> (bf16 hi [B,F_pad,C_pad], bf16 lo or None, fp32 [B,C,F] or None)"""
 	_need_cuda(feat, xlen)
 	feat = feat.to(torch.float32).contiguous()
 	B, C, F = feat.shape
 	F_pad = F if F_pad is None else F_pad
 	C_pad = C if C_pad is None else C_pad
-	hi = torch.empty(B, F_pad, C_pad, dtype = BF16, device = feat.device)
+	want_hi = (not want_f32 or want_lo) if want_hi is None else want_hi
+	hi = torch.empty(B, F_pad, C_pad, dtype = BF16, device = feat.device) if want_hi or want_lo else None
 	lo = torch.empty_like(hi) if want_lo else None
 	f32 = torch.empty_like(feat) if want_f32 else None
 	stats = torch.empty(B, C, 2, dtype = torch.float32, device = feat.device)
 	xl = None if xlen is None else xlen.to(torch.float32).contiguous()
 	rc = _lib.load().cab_instnorm_pack(
-		_p(feat), _p(xl), B, C, F, float(eps), F_pad, C_pad, _p(hi), _p(lo), _p(f32), _p(stats), _stream()
+		_p(feat), _p(xl), B, C, F, float(eps), int(bool(normalize)), F_pad, C_pad, _p(hi), _p(lo), _p(f32), _p(stats), _stream()
 	)
 	_lib.check(rc, 'cab_instnorm_pack')
 	return hi, lo, f32
@@ -147,17 +148,18 @@ def conv1d_fused(
 	_lib.check(rc, 'cab_conv1d_fused')
 
 
-def grouped_conv1d_relu(act, T, wgt, bias, groups, pad_left, out = None):
-	_need_cuda(act, wgt, bias)
-	B, T_rows, C_in = act.shape
+def grouped_conv1d_relu(act, T, C_in, wgt, bias, groups, pad_left, ld_out = None, act_lo = None, want_lo = False):
+	_need_cuda(act, act_lo, wgt, bias)
+	B, T_rows, ld_in = act.shape
 	C_out, _, k = wgt.shape
-	if out is None:
-		out = torch.empty(B, T, C_out, dtype = BF16, device = act.device)
+	out = torch.empty(B, T, ld_out or C_out, dtype = BF16, device = act.device)
+	out_lo = torch.empty_like(out) if want_lo else None
 	rc = _lib.load().cab_grouped_conv1d_relu(
-		_p(act), B, T, T_rows, C_in, _p(wgt), _p(bias), C_out, groups, k, pad_left, _p(out), out.shape[1], _stream()
+		_p(act), _p(act_lo), B, T, T_rows, C_in, ld_in, _p(wgt), _p(bias), C_out, groups, k, pad_left, _p(out), _p(out_lo),
+		out.shape[1], out.shape[2], _stream()
 	)
 	_lib.check(rc, 'cab_grouped_conv1d_relu')
-	return out
+	return out, out_lo
 
 
 # ------------------------------------------------------------------------------------------

@@ -59,13 +59,14 @@ int cab_frontend_logmel(const void* signal, int signal_is_int16, const float* xl
  *   layout change the conv stack wants: fp32 [B, C, F] -> bf16 channels-last [B, F_pad, C].
  *   With xlen_frac: statistics over the valid frames only, biased variance, output exactly 0
  *   for frames >= ceil(frac*F).  Without: plain biased instance norm over all F frames.
- *   out_hi: bf16 [B, F_pad, C_pad]  (frames F..F_pad-1 and channels C..C_pad-1 are zeroed)
+ *   normalize: 0 = layout change only (model built with normalize_features=False)
+ *   out_hi: NULL, or bf16 [B, F_pad, C_pad]  (frames F..F_pad-1 and channels C..C_pad-1 are zeroed)
  *   out_lo: NULL, or bf16 residual (x - float(hi)) for the split-bf16 "fp32" tier
  *   out_f32: NULL, or fp32 [B, C, F] normalised features in the reference layout
  *   ws_stats: [B, C, 2] fp32 workspace (mean, rstd)
  * ------------------------------------------------------------------------------------- */
 int cab_instnorm_pack(const float* feat, const float* xlen_frac, int B, int C, int F, float eps,
-                      int F_pad, int C_pad, void* out_hi, void* out_lo, float* out_f32,
+                      int normalize, int F_pad, int C_pad, void* out_hi, void* out_lo, float* out_f32,
                       float* ws_stats, cab_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -82,7 +83,7 @@ int cab_instnorm_pack(const float* feat, const float* xlen_frac, int B, int C, i
  *   hi*hi, hi*lo, lo*hi partial products.  Stride-2 convs are expressed by the host as
  *   stride-1 convs over the frame-pair view [B, T/2, 2C] with re-packed weights.
  * ------------------------------------------------------------------------------------- */
-#define CAB_MAX_CONV_SOURCES 12
+#define CAB_MAX_CONV_SOURCES 18
 
 typedef struct {
     const void* act;   /* bf16 [B, T_rows, ld_ch]; rows >= T_in are never read (zero fill) */
@@ -125,10 +126,13 @@ int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
                      const cab_conv_epilogue_t* epilogue_host, cab_stream_t stream);
 
 /* grouped Conv1d + bias + ReLU of the separable blocks (models.py:50-64): bf16 channels-last
- * in/out, weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1. */
-int cab_grouped_conv1d_relu(const void* act, int B, int T, int T_rows, int C_in, const float* wgt,
-                            const float* bias, int C_out, int groups, int k, int pad_left,
-                            void* out, int out_T_rows, cab_stream_t stream);
+ * in [B, T_rows, ld_in] / out [B, out_T_rows, ld_out] (channels C_out..ld_out-1 are zeroed),
+ * weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1.
+ * act_lo / out_lo: NULL, or the bf16 residual halves of the split-bf16 "fp32" tier. */
+int cab_grouped_conv1d_relu(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in,
+                            int ld_in, const float* wgt, const float* bias, int C_out, int groups,
+                            int k, int pad_left, void* out, void* out_lo, int out_T_rows, int ld_out,
+                            cab_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * A10 (+A13/A14 argmax): log_softmax over the class dim of [B, C, T] (models.py:316) fused

@@ -1,0 +1,257 @@
+"""Parity tests proper: the CUDA path (through the drop-in modules and the C ABI) against the
+committed golden vectors of the real reference and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): logits within 1e-3 relative in the fp32 tier and 2e-2 in bf16;
+CTC loss and gradients within 1e-4 relative; alignments / greedy ids / collapsed text bit-exact.
+Relative error = Frobenius norm of the difference over the norm of the reference.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+
+
+def rel(a, b):
+	a, b = a.detach().double().cpu(), b.detach().double().cpu()
+	return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope = 'module')
+def dev():
+	return torch.device('cuda:0')
+
+
+# ---------------------------------------------------------------- frontend / instance norm
+def test_frontend_against_golden(golden, dev):
+	from convasr_b200 import models
+	g = golden('frontend')
+	fe = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window').to(dev)
+	norm = models.MaskedInstanceNorm1d(64, affine = False, eps = 2.0**-14, track_running_stats = False, temporal_mask = True, legacy = True)
+	for c in g['cases']:
+		sig = c['signal'].to(dev)
+		xlen = c['xlen'].to(dev) if c['xlen'] is not None else None
+		logmel = fe(sig, xlen = xlen)
+		assert logmel.shape == c['logmel'].shape and logmel.dtype == torch.float32
+		assert float((logmel.cpu() - c['logmel']).abs().max()) < 2e-4, c['name']
+		# the mask-based entry point of the reference (models.py:290) gives the same result
+		if xlen is not None:
+			T = sig.shape[-1]
+			mask = torch.arange(T, device = dev)[None] < (xlen * T).ceil().long()[:, None]
+			assert torch.equal(fe(sig, mask = mask), logmel)
+		feats = norm(c['logmel'].to(dev), xlen = xlen)
+		assert float((feats.cpu() - c['feats']).abs().max()) < 2e-5, c['name']
+
+
+def test_frontend_against_oracle_at_bench_shape(dev):
+	"""config C2 row shape (15 s of 8 kHz audio), int16 and fp32 input, ragged lengths."""
+	from convasr_b200 import models
+	g = torch.Generator().manual_seed(0)
+	sig = (torch.randn(4, 120000, generator = g) * 3000).round().clamp(-32767, 32767)
+	xlen = torch.tensor([1.0, 0.5, 0.777, 0.9001])
+	ref = O.frontend_logmel(sig, xlen)
+	fe = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window').to(dev)
+	for s in (sig.to(dev), sig.to(torch.int16).to(dev)):
+		got = fe(s, xlen = xlen.to(dev))
+		assert got.shape == (4, 64, 1501)
+		assert float((got.cpu() - ref).abs().max()) < 2e-4
+	# scale invariance up to the +1e-5 (quirk 1): int16 without /32768 == float / 32768
+	assert float((fe(sig.to(dev) / 32768.0, xlen = xlen.to(dev)) - got).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------- conv stack
+def _build(c, dev, precision):
+	from convasr_b200 import models
+	m = getattr(models, c['model'])(64, [c['num_classes']], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, **c['kwargs'])
+	m.load_state_dict(O.synth_state_dict(c['shapes'], seed = c['seed']), strict = False)
+	m = m.to(dev).eval().set_precision(precision)
+	if c['fused']:
+		m.fuse_conv_bn_eval()
+	return m
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-3), ('bf16', 2e-2)])
+def test_models_against_golden(golden, dev, precision, tol):
+	for c in golden('models')['cases']:
+		m = _build(c, dev, precision)
+		with torch.no_grad():
+			out = m(c['signal'].to(dev), c['xlen'].to(dev), y = c['y'].to(dev), ylen = c['ylen'].to(dev))
+		logits, log_probs, olen = out['logits'][0], out['log_probs'][0], out['olen'][0]
+		assert logits.shape == c['logits'].shape and log_probs.dtype == torch.float32
+		assert torch.equal(olen.cpu(), c['olen']), c['model']
+		r = rel(logits, c['logits'])
+		assert r < tol, (c['model'], precision, r)
+		assert rel(log_probs, c['log_probs']) < tol
+		if precision == 'fp32':
+			# greedy ids must agree wherever the reference's own top-2 margin is not a numerical tie
+			ids = log_probs.argmax(1).cpu()
+			top2 = c['log_probs'].topk(2, dim = 1).values
+			clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+			assert torch.equal(ids[clear], c['log_probs'].argmax(1)[clear])
+			assert torch.allclose(out['loss'].cpu(), c['loss'], rtol = 2e-3, atol = 1e-3), c['model']
+		# the fused epilogue's argmax is the argmax of the log_probs it wrote (ties -> lowest id)
+		assert torch.equal(log_probs._convasr_argmax.long(), log_probs.argmax(1))
+
+
+def test_padded_frames_equal_decoder_bias(golden, dev):
+	"""quirk 6: frames past olen are zeroed after every layer, so logits there are the decoder bias."""
+	c = golden('models')['cases'][0]
+	m = _build(c, dev, 'fp32')
+	with torch.no_grad():
+		out = m(c['signal'].to(dev), c['xlen'].to(dev))
+	logits, olen = out['logits'][0], out['olen'][0]
+	bias = m.decoder[0].bias.detach()
+	b = 2
+	assert olen[b] < logits.shape[-1]
+	assert torch.allclose(logits[b, :, int(olen[b]):], bias[:, None].expand(-1, logits.shape[-1] - int(olen[b])), atol = 1e-6)
+
+
+def test_full_width_wav2letter_against_oracle(dev):
+	"""The real Wav2Letter (base_width 128, 66.5 M params) on a small batch, both tiers."""
+	from convasr_b200 import models
+	m = models.Wav2Letter(64, [38], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False)
+	shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')}
+	assert 66e6 < sum(p.numel() for p in m.parameters()) < 67e6  # 66.53 M
+	sd = O.synth_state_dict(shapes, seed = 3)
+	m.load_state_dict(sd, strict = False)
+	m = m.to(dev).eval()
+	g = torch.Generator().manual_seed(5)
+	sig = (torch.randn(2, 24000, generator = g) * 2000).round().to(torch.int16)
+	xlen = torch.tensor([1.0, 0.7])
+	ref_logits, ref_lp, ref_olen = O.model_forward(sd, sig, xlen, model = 'Wav2Letter')
+	for precision, tol in (('fp32', 1e-3), ('bf16', 2e-2)):
+		m.set_precision(precision)
+		with torch.no_grad():
+			out = m(sig.to(dev), xlen.to(dev))
+		assert out['logits'][0].shape == (2, 38, 153)  # t = 151 + 2 (quirk 7)
+		assert torch.equal(out['olen'][0].cpu(), ref_olen[0])
+		r = rel(out['logits'][0], ref_logits[0])
+		assert r < tol, (precision, r)
+
+
+# ---------------------------------------------------------------- CTC loss / alignment
+def test_ctc_loss_and_grad_against_golden(golden, dev):
+	from convasr_b200 import ctc
+	for c in golden('ctc')['cases']:
+		lp = c['log_probs'].to(dev).requires_grad_(True)
+		loss = ctc.ctc_loss(lp, c['targets'].to(dev), c['input_lengths'].to(dev), c['target_lengths'].to(dev), blank = c['blank'])
+		finite = torch.isfinite(c['loss'])
+		assert torch.equal(torch.isinf(loss).cpu(), ~finite)
+		assert torch.allclose(loss.cpu()[finite], c['loss'][finite], rtol = 1e-4)
+		if c['grad'] is not None:
+			loss.sum().backward()
+			assert rel(lp.grad, c['grad']) < 1e-4
+			il = c['input_lengths']
+			for b in range(lp.shape[1]):  # exactly zero past the input length
+				assert float(lp.grad[int(il[b]):, b].abs().max() if il[b] < lp.shape[0] else 0.0) == 0.0
+
+
+def test_ctc_loss_bench_shape_against_float64_oracle(dev):
+	"""C2 shape slice: t=753, C=38, L up to 225, through the [B,C,t]-permuted view the model uses."""
+	from convasr_b200 import ctc
+	g = torch.Generator().manual_seed(1)
+	B, C, T, L = 3, 38, 753, 225
+	lp_bct = torch.randn(B, C, T, generator = g).log_softmax(1)
+	y = torch.randint(0, C - 1, (B, L), generator = g)
+	ylen = torch.tensor([225, 150, 3])
+	olen = torch.tensor([753, 600, 410])
+	nll, grad = O.ctc_loss_np(lp_bct.permute(2, 0, 1).numpy(), y.numpy(), olen.numpy(), ylen.numpy(), C - 1)
+	lp = lp_bct.to(dev).requires_grad_(True)
+	loss = ctc.ctc_loss(lp.permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
+	assert torch.allclose(loss.double().cpu(), torch.from_numpy(nll), rtol = 1e-4)
+	loss.sum().backward()
+	assert rel(lp.grad.permute(2, 0, 1), torch.from_numpy(grad)) < 1e-4
+	assert float(lp.grad.sum(1).abs().max()) < 1e-3  # softmax already folded in: sums to 0 over C
+
+
+def test_alignment_against_golden_and_oracle(golden, dev):
+	from convasr_b200 import ctc
+	for c in golden('ctc')['cases']:
+		if c['alignment'] is None:
+			continue
+		for packed in (False, True):
+			al = ctc.alignment(c['log_probs'].to(dev), c['targets'].to(dev), c['input_lengths'].to(dev), c['target_lengths'].to(dev), blank = c['blank'], pack_backpointers = packed)
+			assert al.dtype == torch.int64 and torch.equal(al.cpu(), c['alignment'])
+	# larger seeded case incl. the padded-batch quirk (input_lengths < T) and the [B,C,T] view
+	g = torch.Generator().manual_seed(2)
+	B, C, T, L = 6, 38, 300, 60
+	lp = (torch.randn(B, C, T, generator = g) * 2).log_softmax(1)
+	y = torch.randint(0, C - 1, (B, L), generator = g)
+	ylen = torch.tensor([60, 41, 17, 1, 0, 33])
+	olen = torch.tensor([300, 250, 299, 120, 300, 70])
+	ref = O.ctc_alignment(lp.permute(2, 0, 1), y, olen, ylen, C - 1)
+	got = ctc.alignment(lp.to(dev).permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
+	assert torch.equal(got.cpu(), ref)
+	# size-independent properties: frames are increasing along the target and inside the input
+	for b in range(B):
+		a = got[b, :int(ylen[b])].cpu()
+		assert bool((a[1:] > a[:-1]).all()) and (len(a) == 0 or int(a.max()) < int(olen[b]))
+
+
+# ---------------------------------------------------------------- decoders / generator
+def test_log_softmax_argmax_and_topk(dev):
+	from convasr_b200 import ops
+	g = torch.Generator().manual_seed(3)
+	for C in (38, 5000):
+		x = torch.randn(2, C, 77, generator = g) * 3
+		lp, am = ops.log_softmax_argmax(x.to(dev))
+		assert rel(lp, x.log_softmax(1)) < 1e-6
+		assert torch.equal(am.long().cpu(), x.argmax(1))
+	# exact ties resolve to the lowest index (SURVEY.md hard parts)
+	x = torch.zeros(1, 9, 5)
+	_, am = ops.log_softmax_argmax(x.to(dev))
+	assert am.tolist() == [[0] * 5]
+	x = torch.randn(3, 38, 40, generator = g)
+	assert torch.equal(ops.topk_ids(x.to(dev), 4).long().cpu(), x.topk(4, dim = 1).indices)
+	# backward of log_softmax
+	xg = x.to(dev).requires_grad_(True)
+	w = torch.randn(3, 38, 40, generator = g)
+	(ops.log_softmax_dim1(xg) * w.to(dev)).sum().backward()
+	xr = x.clone().requires_grad_(True)
+	(xr.log_softmax(1) * w).sum().backward()
+	assert rel(xg.grad, xr.grad) < 1e-5
+
+
+def test_greedy_decoder_and_generator_against_golden(golden, dev):
+	from convasr_b200 import decoders, transcript_generators
+	g = golden('decode')
+	tok = O.CharTokenizer(g['alphabet'])
+	dec = decoders.GreedyDecoder()
+	d = g['decode']
+	assert dec.decode(d['lp1'].to(dev), [4]) == d['d1']
+	assert dec.decode(d['lp2'].to(dev), K = 2) == d['d2']
+	assert dec.decode(d['lp3'].to(dev), [33, 20, 1, 7]) == d['d3']
+	assert dec.decode(d['lp3'].to(dev), [33, 20, 1, 7], K = 3) == d['d4']
+	gen = transcript_generators.GreedyCTCGenerator()
+	for c in g['generate']:
+		ids = torch.tensor(c['ids'])
+		B, T = ids.shape
+		lp = torch.full((B, 38, T), -10.0).scatter_(1, ids[:, None, :], 0.0).to(dev)
+		ts = (torch.arange(T)[None].float() * 0.02).expand(B, -1).to(dev) if c['with_ts'] else None
+		tr = gen.generate(tok, lp, begin = torch.zeros(B, device = dev), end = torch.full((B, ), T * 0.02, device = dev), output_lengths = c['olens'], time_stamps = ts)
+		segs = [[(float(s['begin']), float(s['end']), s['hyp']) for s in t[0]] for t in tr]
+		assert segs == c['segments']
+
+
+def test_entropy_reductions(dev):
+	from convasr_b200 import models
+	g = torch.Generator().manual_seed(4)
+	lp = torch.randn(4, 38, 90, generator = g).log_softmax(1)
+	lens = torch.tensor([90, 45, 1, 77])
+	assert rel(models.entropy(lp.to(dev), lens.to(dev)), O.entropy(lp, lens)) < 1e-5
+	assert rel(models.entropy(lp.to(dev)), O.entropy(lp)) < 1e-5
+	assert rel(models.weighted_mean_entropy(lp.to(dev), lens.to(dev)), O.weighted_mean_entropy(lp, lens)) < 1e-5
+
+
+# ---------------------------------------------------------------- training-mode surface
+def test_training_step_runs_and_matches_oracle_loss(golden, dev):
+	"""model.train(): differentiable ATen conv stack + native frontend / log_softmax / CTC."""
+	from convasr_b200 import models
+	c = golden('models')['cases'][0]
+	m = _build(c, dev, None).train()
+	out = m(c['signal'].to(dev), c['xlen'].to(dev), y = c['y'].to(dev), ylen = c['ylen'].to(dev))
+	loss = (out['loss'] * c['ylen'][:, 0].to(dev)).mean()
+	loss.backward()
+	grads = [p.grad for p in m.parameters() if p.requires_grad]
+	assert all(g is not None and torch.isfinite(g).all() for g in grads)

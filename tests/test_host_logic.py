@@ -1,0 +1,147 @@
+"""Host-side logic of the drop-in modules (no GPU): module tree / state_dict contract, BN
+folding, weight re-packing for the strided prologue, mel basis, precision selection."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from convasr_b200 import engine, models
+from oracle import oracle as O
+
+ALL_MODELS = [
+	'Wav2Letter', 'Wav2LetterResidual', 'Wav2LetterResidualNoDilation', 'Wav2LetterResidualBig', 'Wav2LetterDense', 'Wav2LetterDenseNoDilation',
+	'Wav2LetterDenseNoDilationInplace', 'Wav2LetterDenseLargeKernels', 'Wav2LetterDenseNoDilationLargeKernels', 'Wav2LetterDenseBig',
+	'Wav2LetterDenseBigLargeKernelsNoDropoutReLu', 'Wav2LetterDenseBigLargeKernelsNoDilationNoDropoutReLu',
+	'Wav2LetterDenseBigLargeKernelsNoDilationNoTemporalMaskNoDropoutReLu', 'Wav2LetterFlat', 'JasperNetSeparable', 'JasperNetSmall',
+	'JasperNetSmallInstanceNorm', 'JasperNetSmallTrainableInstanceNorm', 'JasperNetLarge', 'JasperNetBig', 'JasperNetBigNoStride',
+	'JasperNetBigBpeOnly', 'JasperNetResidualBig', 'JasperNetBigInplace'
+]
+
+
+def test_all_24_configurations_resolve():
+	for name in ALL_MODELS:
+		assert issubclass(getattr(models, name), models.JasperNet)
+
+
+def test_state_dict_keys_and_shapes_match_the_reference(golden):
+	"""Keys/shapes recorded from the real reference in tests/golden/models.pt."""
+	for c in golden('models')['cases']:
+		if c['fused']:
+			continue
+		m = getattr(models, c['model'])(64, [c['num_classes']], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., **c['kwargs'])
+		mine = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')}
+		assert mine == c['shapes'], c['model']
+		fe_keys = sorted(k for k in m.state_dict() if k.startswith('frontend.'))
+		assert fe_keys == ['frontend.mel.bias', 'frontend.mel.weight', 'frontend.window']
+
+
+@pytest.mark.reference
+def test_state_dict_keys_match_live_reference_for_every_class():
+	from oracle import reference_shim
+	ref = reference_shim.load()
+	for name in ALL_MODELS:
+		kw = dict(base_width = 128, groups = 128) if 'Separable' in name else dict(base_width = 8)
+		if 'Separable' in name:
+			kw = dict(base_width = 128)
+		theirs = getattr(ref.models, name)(64, [38], **kw)
+		ours = getattr(models, name)(64, [38], **kw)
+		a = {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+		b = {k: tuple(v.shape) for k, v in ours.state_dict().items()}
+		assert a == b, name
+		assert len(theirs.backbone) == len(ours.backbone)
+
+
+def test_wav2letter_accepts_the_callers_extra_kwargs():
+	# transcribe.py:44-52 / benchmark.py:97-104 pass dict= and check_time_dim_padded=
+	m = models.Wav2Letter(64, [38], base_width = 8, dict = lambda logits, log_probs, olen, **kw: logits[0], check_time_dim_padded = False)
+	assert m.check_time_dim_padded is False and callable(m.dict)
+	assert len(m.backbone) == 8 and [len(b.conv) for b in m.backbone] == [1, 3, 3, 3, 3, 3, 1, 1]
+	assert m.backbone[6].conv[0][0].padding[0] == 29 and m.backbone[6].conv[0][0].dilation[0] == 2  # +2 frames quirk
+	assert m.backbone[1].activation.nonlinearity == ('hardtanh', 0, 20)
+
+
+def test_mel_basis_matches_reference(golden):
+	g = golden('frontend')
+	assert float((models.slaney_mel_basis(8000, 256, 64, 0.0, 4000) - g['mel']).abs().max()) < 2e-7
+	fe = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window')
+	assert (fe.win_length, fe.hop_length, fe.nfft, fe.freq_cutoff) == (160, 80, 256, 129)
+	assert float(fe.mel.bias[0]) == 2.0**-14
+
+
+def test_fold_bn_equals_conv_then_bn():
+	torch.manual_seed(0)
+	conv = torch.nn.Conv1d(6, 10, 5, padding = 2, bias = False)
+	bn = torch.nn.BatchNorm1d(10).eval()
+	bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.uniform_(0.5, 1.5); bn.bias.data.normal_()
+	x = torch.randn(2, 6, 30)
+	w, b = engine.fold_bn(conv.weight, conv.bias, bn)
+	assert torch.allclose(F.conv1d(x, w, b, padding = 2), bn(conv(x)), atol = 1e-5)
+	w2, b2 = engine.fold_bn(conv.weight, None, torch.nn.Identity())
+	assert torch.equal(w2, conv.weight) and float(b2.abs().max()) == 0
+
+
+def test_fuse_conv_bn_eval_changes_keys_like_the_reference(golden):
+	c = [c for c in golden('models')['cases'] if c['fused']][0]
+	m = models.Wav2Letter(64, [38], **c['kwargs']).eval()
+	m.load_state_dict(O.synth_state_dict(c['shapes'], seed = c['seed']), strict = False)
+	n_before = len(m.state_dict())
+	m.fuse_conv_bn_eval()
+	keys = set(m.state_dict())
+	assert not any('.bn.' in k for k in keys)
+	assert 'backbone.0.conv.0.0.bias' in keys and len(keys) < n_before
+
+
+@pytest.mark.parametrize('k,pad,F_', [(11, 5, 51), (11, 5, 50), (13, 6, 31), (3, 1, 9)])
+def test_stride2_pair_view_repacking(k, pad, F_):
+	"""The frame-pair trick: stride-2 conv == stride-1 conv over [F/2, 2C] with re-packed taps."""
+	torch.manual_seed(k)
+	C, Co, CA = 5, 7, 8
+	w = torch.randn(Co, C, k)
+	x = torch.randn(2, C, F_)
+	ref = F.conv1d(x, w, stride = 2, padding = pad)
+	wp, taps, pad_left = engine.pack_taps_stride2(w, pad, CA)
+	F_pad = F_ + F_ % 2
+	xa = torch.zeros(2, F_pad, CA)
+	xa[:, :F_, :C] = x.permute(0, 2, 1)
+	pairs = xa.view(2, F_pad // 2, 2 * CA)  # [B, P, 2CA]
+	T_out = ref.shape[-1]
+	out = torch.zeros(2, Co, T_out)
+	for t in range(T_out):
+		for j in range(taps):
+			p = t + j - pad_left
+			if 0 <= p < pairs.shape[1]:
+				out[:, :, t] += pairs[:, p] @ wp[j].T
+	assert torch.allclose(out, ref, atol = 1e-4)
+
+
+def test_precision_selection():
+	m = models.Wav2Letter(64, [38], base_width = 8)
+	assert m._active_precision() == 'fp32'
+	assert m.to(torch.bfloat16)._active_precision() == 'bf16'
+	m2, _ = models.data_parallel_and_autocast(models.Wav2Letter(64, [38], base_width = 8), opt_level = 'O2')
+	assert m2._active_precision() == 'bf16'
+
+
+def test_training_path_matches_oracle_on_cpu_modules(golden):
+	"""The module tree's own differentiable forward (ConvBn1d.forward) in eval mode equals the
+	oracle's conv stack on CPU for every golden family -- checks topology + residual wiring."""
+	for c in golden('models')['cases']:
+		if c['fused']:
+			continue
+		m = getattr(models, c['model'])(64, [c['num_classes']], dropout = 0., **c['kwargs']).eval()
+		sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
+		m.load_state_dict(sd, strict = False)
+		feats = O.masked_instance_norm(O.frontend_logmel(c['signal'], c['xlen']), c['xlen'])
+		with torch.no_grad():
+			x = feats
+			residual = []
+			for i, block in enumerate(m.backbone):
+				x = block(x, residual = residual, lengths_fraction = c['xlen'])
+				if i >= len(m.backbone) - 3:
+					residual = []
+				elif m.residual == 'dense':
+					residual = residual + [x]
+				elif m.residual:
+					residual = [x]
+			logits = m.decoder(x)[0]
+		rel = float((logits - c['logits']).norm() / c['logits'].norm())
+		assert rel < 1e-4, (c['model'], rel)
