@@ -34,7 +34,15 @@ constexpr int kStageBytes = kATileBytes + kBTileBytes;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int kNumThreads = 256;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// epilogue staging: bf16 [128 rows][32 cols] tiles (64-byte rows, 64B swizzle) for TMA stores,
+// double buffered, one pair for the hi tensor and one for the lo tensor; plus the tile's bias
+constexpr int kEpiCols = 32;
+constexpr int kEpiTileBytes = kBlockM * kEpiCols * 2;  // 8 KB
+constexpr int kOffStageOut = kStages * kStageBytes;    // 4 staging tiles
+constexpr int kOffBias = kOffStageOut + 4 * kEpiTileBytes;
+constexpr int kOffBars = kOffBias + kMaxBlockN * 4;
+constexpr int kSmemBytes = kOffBars + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 struct SrcDev {
     int a_ch_off, w_ch_off, n_chunks, taps, dil, pad_left;
@@ -43,6 +51,7 @@ struct SrcDev {
 struct alignas(64) ConvParams {
     CUtensorMap amap[CAB_MAX_CONV_SOURCES];
     CUtensorMap wmap[CAB_MAX_CONV_SOURCES];
+    CUtensorMap omap_hi, omap_lo;  // bf16 outputs, box {32 ch, 128 rows, 1}, 64B swizzle
     SrcDev src[CAB_MAX_CONV_SOURCES];
     int n_src;
     int B, T_out, C_out, block_n;
@@ -68,13 +77,65 @@ __device__ __forceinline__ float apply_act(float x, int act, float a, float b) {
     }
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+template <int ACT>
+__device__ __forceinline__ float act_t(float x, float a, float b) {
+    if (ACT == CAB_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == CAB_ACT_HARDTANH) return fminf(fmaxf(x, a), b);
+    if (ACT == CAB_ACT_LEAKY_RELU) return x > 0.f ? x : x * a;
+    return x;
+}
+
+// One 32-column chunk of the bf16 epilogue: bias + activation + mask, pack to bf16 (hi, lo),
+// write the thread's 64-byte row into the 64B-swizzled staging tile(s).
+template <int ACT, bool LO>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ sb, float a, float b,
+                                          bool keep, int row, uint8_t* st_hi, uint8_t* st_lo) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        float x0 = act_t<ACT>(__uint_as_float(v[j]) + sb[j], a, b);
+        float x1 = act_t<ACT>(__uint_as_float(v[j + 1]) + sb[j + 1], a, b);
+        if (!keep) { x0 = 0.f; x1 = 0.f; }
+        __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+        hi[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        if (LO) {
+            float2 hf = __bfloat1622float2(h);
+            lo[j >> 1] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+        }
+    }
+    // 64-byte rows, 16-byte chunk index XOR ((row >> 1) & 3)  == CU_TENSOR_MAP_SWIZZLE_64B
+    const int sw = (row >> 1) & 3;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int off = row * 64 + ((q ^ sw) << 4);
+        *reinterpret_cast<uint4*>(st_hi + off) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+        if (LO) *reinterpret_cast<uint4*>(st_lo + off) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment required by the 128B swizzle atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    float* s_bias = reinterpret_cast<float*>(smem + kOffBias);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + kAccStages;
@@ -87,6 +148,10 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         for (int s = 0; s < p.n_src; ++s) {
             tma_prefetch_desc(&p.amap[s]);
             tma_prefetch_desc(&p.wmap[s]);
+        }
+        if (p.epilogue == CAB_EPI_ACT_BF16) {
+            tma_prefetch_desc(&p.omap_hi);
+            if (p.out_lo != nullptr) tma_prefetch_desc(&p.omap_lo);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -184,6 +249,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         const int row = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t epi_chunks = 0;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int nt = tile % p.n_ntiles;
             const int mt = tile / p.n_ntiles;
@@ -192,53 +258,69 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             const int n0 = nt * block_n;
             const int t = t0 + row;
             const bool row_ok = t < p.T_out;
+            (void)row_ok;
 
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + acc * kMaxBlockN + (uint32_t(q * 32) << 16);
+            if (p.epilogue != CAB_EPI_ACT_BF16) {
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tc_fence_after();
+            }
 
             if (p.epilogue == CAB_EPI_ACT_BF16) {
                 int len = p.T_out;
                 if (p.xlen != nullptr) len = frac_len(__ldg(p.xlen + b), p.T_out);
                 const bool keep = t < len;
-                const size_t out_row = (size_t(b) * p.out_T_rows + t) * p.out_ld;
-                for (int c0 = 0; c0 < block_n; c0 += 32) {
+                const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
+                const bool has_lo = p.out_lo != nullptr;
+                // stage this tile's bias (zeros past C_out / without bias)
+                epi_bar(1);  // previous tile's readers are done with s_bias
+                for (int i = et; i < block_n; i += 128) {
+                    const int n = n0 + i;
+                    s_bias[i] = (p.bias != nullptr && n < p.C_out) ? __ldg(p.bias + n) : 0.f;
+                }
+                epi_bar(1);
+                mbar_wait(&tmem_full[acc], acc_phase);  // bias staging above overlaps the MMAs
+                tc_fence_after();
+                uint8_t* stage = smem + kOffStageOut;
+                for (int c0 = 0; c0 < block_n; c0 += kEpiCols) {
+                    if (n0 + c0 >= p.C_out) break;  // uniform
                     uint32_t v[32];
                     tmem_ld_32x32(taddr + c0, v);
                     tmem_ld_wait();
-                    const int n = n0 + c0;
-                    if (row_ok && n < p.C_out) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 32; j += 2) {
-                            float x0 = __uint_as_float(v[j]);
-                            float x1 = __uint_as_float(v[j + 1]);
-                            if (p.bias != nullptr) {
-                                x0 += __ldg(p.bias + n + j);
-                                x1 += __ldg(p.bias + n + j + 1);
-                            }
-                            x0 = apply_act(x0, p.act, p.act_a, p.act_b);
-                            x1 = apply_act(x1, p.act, p.act_a, p.act_b);
-                            if (!keep) { x0 = 0.f; x1 = 0.f; }
-                            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                            hi[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
-                            if (p.out_lo != nullptr) {
-                                float2 hf = __bfloat1622float2(h);
-                                lo[j >> 1] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
-                            }
-                        }
-                        uint4* dst = reinterpret_cast<uint4*>(p.out_hi + out_row + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        if (p.out_lo != nullptr) {
-                            uint4* dlo = reinterpret_cast<uint4*>(p.out_lo + out_row + n);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dlo[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                        }
+                    if (c0 + kEpiCols >= block_n || n0 + c0 + kEpiCols >= p.C_out) {
+                        // accumulator fully read: hand the TMEM stage back to the MMA warp early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                     }
+                    const int buf = epi_chunks & 1;
+                    uint8_t* st_hi = stage + buf * kEpiTileBytes;
+                    uint8_t* st_lo = stage + (2 + buf) * kEpiTileBytes;
+                    // the TMA store that last read this buffer was committed two chunks ago
+                    if (et == 0) bulk_wait_read<1>();
+                    epi_bar(2);
+                    const float* sb = s_bias + c0;
+#define CAB_EPI_CALL(ACT)                                                                          \
+    if (has_lo) epi_chunk<ACT, true>(v, sb, p.act_a, p.act_b, keep, row, st_hi, st_lo);            \
+    else epi_chunk<ACT, false>(v, sb, p.act_a, p.act_b, keep, row, st_hi, st_lo);
+                    switch (p.act) {
+                        case CAB_ACT_RELU: CAB_EPI_CALL(CAB_ACT_RELU) break;
+                        case CAB_ACT_HARDTANH: CAB_EPI_CALL(CAB_ACT_HARDTANH) break;
+                        case CAB_ACT_LEAKY_RELU: CAB_EPI_CALL(CAB_ACT_LEAKY_RELU) break;
+                        default: CAB_EPI_CALL(CAB_ACT_NONE) break;
+                    }
+#undef CAB_EPI_CALL
+                    fence_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
+                    epi_bar(3);
+                    if (et == 0) {
+                        tma_store_3d(&p.omap_hi, st_hi, n0 + c0, t0, b);  // rows >= T_out are clipped
+                        if (has_lo) tma_store_3d(&p.omap_lo, st_lo, n0 + c0, t0, b);
+                        bulk_commit();
+                    }
+                    ++epi_chunks;
                 }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                continue;
             } else if (p.epilogue == CAB_EPI_LOGSOFTMAX) {
                 // Single N tile holds all classes.  Three passes over TMEM (cheap) keep the
                 // register footprint small: max/argmax, sum of exp, then write.
@@ -314,6 +396,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (threadIdx.x == 128) bulk_wait_all();  // all TMA stores of this CTA have completed
     }
 
     tc_fence_before();
@@ -349,7 +432,7 @@ static EncodeTiledFn get_encode_fn() {
 // 3-D bf16 map: dims (innermost first) {d0, d1, d2}, row pitch / slab pitch in elements.
 static int encode_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                          uint64_t pitch1_elems, uint64_t pitch2_elems, uint32_t box0,
-                         uint32_t box1) {
+                         uint32_t box1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode_fn();
     CAB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[3] = {d0, d1, d2};
@@ -358,7 +441,7 @@ static int encode_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CAB_CHECK_ARG(r == CUDA_SUCCESS,
                   "cuTensorMapEncodeTiled failed (%d): base=%p dims=%llu,%llu,%llu pitch=%llu,%llu "
@@ -433,6 +516,19 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     p.logits = ep->logits;
     p.log_probs = ep->log_probs;
     p.argmax = ep->argmax;
+    if (ep->epilogue == CAB_EPI_ACT_BF16) {
+        CAB_CHECK_ARG(ep->out_lo == nullptr || (reinterpret_cast<uintptr_t>(ep->out_lo) & 15) == 0, "out_lo must be 16-byte aligned");
+        int rc = encode_map_3d(&p.omap_hi, ep->out_hi, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,
+                               (uint64_t)ep->out_ld_ch, (uint64_t)ep->out_T_rows * ep->out_ld_ch, kEpiCols, kBlockM,
+                               CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        if (ep->out_lo != nullptr) {
+            rc = encode_map_3d(&p.omap_lo, ep->out_lo, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,
+                               (uint64_t)ep->out_ld_ch, (uint64_t)ep->out_T_rows * ep->out_ld_ch, kEpiCols, kBlockM,
+                               CU_TENSOR_MAP_SWIZZLE_64B);
+            if (rc) return rc;
+        }
+    }
 
     for (int s = 0; s < n_src; ++s) {
         const cab_conv_source_t& c = srcs[s];

@@ -30,162 +30,120 @@ __device__ __forceinline__ float lse2(float a, float b) {
 }
 
 // ------------------------------------------------------------------------------------------
-// CTC forward: alpha recursion.  grid = B, block = threads (multiple of 32).
+// CTC alpha / beta recursion.  grid = B * n_roles, block = threads (multiple of 32).
+// beta is alpha on the time- and state-reversed problem (beta[t][s] = alpha'[il-1-t][S-1-s]),
+// so one body serves both directions; with both roles in one grid the two latency-bound
+// recursions of an utterance run concurrently on different SMs.
+// The emission of step t+kCtcPrefetch is requested while step t is computed, so the L2/HBM
+// latency never sits on the sequential critical path.
 // shared: float prev[2][S_max + 2]
 // ------------------------------------------------------------------------------------------
-__global__ void ctc_alpha_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
-                                 const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
-                                 const int64_t* __restrict__ tgt_len, int T, int C, int L_max, int blank,
-                                 float* __restrict__ alpha_ws, float* __restrict__ nll) {
+constexpr int kCtcPrefetch = 8;
+
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+    const float m = fmaxf(a, fmaxf(b, c));
+    if (m == -INFINITY) return -INFINITY;
+    return __logf(__expf(a - m) + __expf(b - m) + __expf(c - m)) + m;
+}
+
+__global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
+                                     const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
+                                     const int64_t* __restrict__ tgt_len, int B, int T, int L_max, int blank,
+                                     int first_role, float* __restrict__ alpha_ws, float* __restrict__ beta_ws,
+                                     float* __restrict__ nll) {
     extern __shared__ float sh[];
-    const int b = blockIdx.x;
+    const int b = blockIdx.x % B;
+    const bool rev = (first_role + blockIdx.x / B) != 0;  // role 0 = alpha, role 1 = beta
     const int S_max = 2 * L_max + 1;
     const int tl = (int)tgt_len[b];
     const int il = (int)in_len[b];
     const int S = 2 * tl + 1;
-    float* buf0 = sh;               // index s+2 (two guard cells at the front)
+    float* buf0 = sh;  // index s+2 (two guard cells at the front)
     float* buf1 = sh + (S_max + 2);
     const float* lpb = lp + (int64_t)b * sb;
-    float* aw = alpha_ws + (size_t)b * T * S_max;
+    float* ws = (rev ? beta_ws : alpha_ws) + (size_t)b * T * S_max;
 
-    int ext[kCtcMaxPer];
+    if (il <= 0 || il > T || tl > L_max || tl < 0) {
+        if (threadIdx.x == 0 && !rev && nll) nll[b] = INFINITY;
+        return;
+    }
+    // per-thread states (virtual index s runs in recursion order; sr is the real state)
+    int sr[kCtcMaxPer];
+    int64_t off[kCtcMaxPer];  // ext(s) * stride_c
     bool skip[kCtcMaxPer];
 #pragma unroll
     for (int i = 0; i < kCtcMaxPer; ++i) {
         const int s = threadIdx.x + i * blockDim.x;
-        ext[i] = blank;
+        sr[i] = rev ? S - 1 - s : s;
+        int e = blank;
         skip[i] = false;
-        if (s < S && (s & 1)) {
-            ext[i] = (int)targets[(size_t)b * L_max + (s >> 1)];
-            if (s >= 3) skip[i] = ext[i] != (int)targets[(size_t)b * L_max + (s >> 1) - 1];
+        if (s < S && (sr[i] & 1)) {
+            e = (int)targets[(size_t)b * L_max + (sr[i] >> 1)];
+            if (s >= 2) {  // the state two behind in recursion order
+                const int s2 = rev ? sr[i] + 2 : sr[i] - 2;
+                skip[i] = e != (int)targets[(size_t)b * L_max + (s2 >> 1)];
+            }
         }
+        off[i] = (int64_t)e * sc;
     }
     if (threadIdx.x < 2) { buf0[threadIdx.x] = -INFINITY; buf1[threadIdx.x] = -INFINITY; }
-    if (il <= 0 || tl > L_max) {
-        if (threadIdx.x == 0) nll[b] = INFINITY;
-        return;
-    }
-    // t = 0
+    auto tmap = [&](int t) -> int64_t { return (int64_t)(rev ? il - 1 - t : t) * st; };
+    auto wrow = [&](int t) -> size_t { return (size_t)(rev ? il - 1 - t : t) * S_max; };
+
+    // step 0
 #pragma unroll
     for (int i = 0; i < kCtcMaxPer; ++i) {
         const int s = threadIdx.x + i * blockDim.x;
         if (s < S) {
             float a = -INFINITY;
-            if (s < 2) a = lpb[(int64_t)ext[i] * sc];
+            if (s < 2) a = lpb[tmap(0) + off[i]];
             buf0[s + 2] = a;
-            aw[s] = a;
+            ws[wrow(0) + sr[i]] = a;
+        }
+    }
+    // prefetch ring: ring[i][u] holds the emission of step t with t % kCtcPrefetch == u
+    float ring[kCtcMaxPer][kCtcPrefetch];
+#pragma unroll
+    for (int u = 0; u < kCtcPrefetch; ++u) {
+        const int t = 1 + u;
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) {
+            const int s = threadIdx.x + i * blockDim.x;
+            ring[i][u] = (s < S && t < il) ? lpb[tmap(t) + off[i]] : 0.f;
         }
     }
     __syncthreads();
     float* prev = buf0;
     float* cur = buf1;
-    float lp_next[kCtcMaxPer];
+    for (int t0 = 1; t0 < il; t0 += kCtcPrefetch) {
 #pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
-        const int s = threadIdx.x + i * blockDim.x;
-        lp_next[i] = (s < S && il > 1) ? lpb[st + (int64_t)ext[i] * sc] : 0.f;
-    }
-    for (int t = 1; t < il; ++t) {
-        float lpc[kCtcMaxPer];
+        for (int u = 0; u < kCtcPrefetch; ++u) {
+            const int t = t0 + u;
+            if (t < il) {  // uniform across the block
 #pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) {
-            lpc[i] = lp_next[i];
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S && t + 1 < il) lp_next[i] = lpb[(int64_t)(t + 1) * st + (int64_t)ext[i] * sc];
-        }
-#pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S) {
-                const float a1 = prev[s + 2];
-                const float a2 = prev[s + 1];
-                const float a3 = skip[i] ? prev[s] : -INFINITY;
-                const float v = lse3(a1, a2, a3) + lpc[i];
-                cur[s + 2] = v;
-                aw[(size_t)t * S_max + s] = v;
+                for (int i = 0; i < kCtcMaxPer; ++i) {
+                    const int s = threadIdx.x + i * blockDim.x;
+                    if (s < S) {
+                        const float e = ring[i][u];
+                        const int tn = t + kCtcPrefetch;
+                        if (tn < il) ring[i][u] = lpb[tmap(tn) + off[i]];
+                        const float a1 = prev[s + 2];
+                        const float a2 = prev[s + 1];
+                        const float a3 = skip[i] ? prev[s] : -INFINITY;
+                        const float v = lse3_fast(a1, a2, a3) + e;
+                        cur[s + 2] = v;
+                        ws[wrow(t) + sr[i]] = v;
+                    }
+                }
+                __syncthreads();
+                float* tmp = prev; prev = cur; cur = tmp;
             }
         }
-        __syncthreads();
-        float* tmp = prev; prev = cur; cur = tmp;
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && !rev && nll) {
         const float l1 = prev[S - 1 + 2];
         const float l2 = S > 1 ? prev[S - 2 + 2] : -INFINITY;
         nll[b] = -lse2(l1, l2);
-    }
-}
-
-// CTC backward: beta recursion, stored to ws_beta
-__global__ void ctc_beta_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
-                                const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
-                                const int64_t* __restrict__ tgt_len, int T, int C, int L_max, int blank,
-                                float* __restrict__ beta_ws) {
-    extern __shared__ float sh[];
-    const int b = blockIdx.x;
-    const int S_max = 2 * L_max + 1;
-    const int tl = (int)tgt_len[b];
-    const int il = (int)in_len[b];
-    const int S = 2 * tl + 1;
-    float* buf0 = sh;  // index s, two guard cells at the END
-    float* buf1 = sh + (S_max + 2);
-    const float* lpb = lp + (int64_t)b * sb;
-    float* bw = beta_ws + (size_t)b * T * S_max;
-    if (il <= 0 || tl > L_max) return;
-
-    int ext[kCtcMaxPer];
-    bool skip[kCtcMaxPer];  // may jump s -> s+2
-#pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
-        const int s = threadIdx.x + i * blockDim.x;
-        ext[i] = blank;
-        skip[i] = false;
-        if (s < S && (s & 1)) {
-            ext[i] = (int)targets[(size_t)b * L_max + (s >> 1)];
-            if (s + 2 < S) skip[i] = ext[i] != (int)targets[(size_t)b * L_max + (s >> 1) + 1];
-        }
-    }
-    if (threadIdx.x < 2) { buf0[S + threadIdx.x] = -INFINITY; buf1[S + threadIdx.x] = -INFINITY; }
-#pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
-        const int s = threadIdx.x + i * blockDim.x;
-        if (s < S) {
-            float v = -INFINITY;
-            if (s >= S - 2) v = lpb[(int64_t)(il - 1) * st + (int64_t)ext[i] * sc];
-            buf0[s] = v;
-            bw[(size_t)(il - 1) * S_max + s] = v;
-        }
-    }
-    __syncthreads();
-    float* nxt = buf0;
-    float* cur = buf1;
-    float lp_next[kCtcMaxPer];
-#pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
-        const int s = threadIdx.x + i * blockDim.x;
-        lp_next[i] = (s < S && il > 1) ? lpb[(int64_t)(il - 2) * st + (int64_t)ext[i] * sc] : 0.f;
-    }
-    for (int t = il - 2; t >= 0; --t) {
-        float lpc[kCtcMaxPer];
-#pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) {
-            lpc[i] = lp_next[i];
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S && t >= 1) lp_next[i] = lpb[(int64_t)(t - 1) * st + (int64_t)ext[i] * sc];
-        }
-#pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            if (s < S) {
-                const float b1 = nxt[s];
-                const float b2 = nxt[s + 1];
-                const float b3 = skip[i] ? nxt[s + 2] : -INFINITY;
-                const float v = lse3(b1, b2, b3) + lpc[i];
-                cur[s] = v;
-                bw[(size_t)t * S_max + s] = v;
-            }
-        }
-        __syncthreads();
-        float* tmp = nxt; nxt = cur; cur = tmp;
     }
 }
 
@@ -548,13 +506,15 @@ using namespace cab;
 extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                 const int64_t* targets, const int64_t* input_lengths,
                                 const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                                float* ws_alpha, float* nll, cab_stream_t stream_) {
+                                float* ws_alpha, float* ws_beta, float* nll, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTC_COMMON_CHECKS();
     CAB_CHECK_ARG(ws_alpha && nll, "null workspace/output");
-    ctc_alpha_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                   input_lengths, target_lengths, T, C, L_max, blank,
-                                                   ws_alpha, nll);
+    // ws_beta given: run the beta recursion in the same grid (both are needed for the gradient)
+    const int roles = ws_beta ? 2 : 1;
+    ctc_recursion_kernel<<<B * roles, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                               input_lengths, target_lengths, B, T, L_max, blank, 0,
+                                                               ws_alpha, ws_beta, nll);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -563,15 +523,20 @@ extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_
 extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                 const int64_t* targets, const int64_t* input_lengths,
                                 const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                                const float* ws_alpha, float* ws_beta, const float* nll,
+                                const float* ws_alpha, float* ws_beta, int beta_ready, const float* nll,
                                 const float* grad_out, float* grad, int64_t gstride_t, int64_t gstride_b,
                                 int64_t gstride_c, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTC_COMMON_CHECKS();
     CAB_CHECK_ARG(ws_alpha && ws_beta && nll && grad_out && grad, "null workspace/output");
-    ctc_beta_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                  input_lengths, target_lengths, T, C, L_max, blank, ws_beta);
-    CAB_CHECK_LAUNCH();
+    int n_launch = 2;
+    if (!beta_ready) {
+        ctc_recursion_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                           input_lengths, target_lengths, B, T, L_max, blank, 1,
+                                                           nullptr, ws_beta, nullptr);
+        CAB_CHECK_LAUNCH();
+        ++n_launch;
+    }
     {
         const int64_t n = (int64_t)B * T * C;
         int blocks = (int)((n + 255) / 256);
@@ -588,7 +553,7 @@ extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_
                                                           gstride_c);
         CAB_CHECK_LAUNCH();
     }
-    g_launch_count.fetch_add(3, std::memory_order_relaxed);
+    g_launch_count.fetch_add(n_launch, std::memory_order_relaxed);
     return 0;
 }
 

@@ -266,13 +266,16 @@ class _CtcLoss(torch.autograd.Function):
 		T, B, C, L, targets, input_lengths, target_lengths = _ctc_args(lp, targets, input_lengths, target_lengths)
 		S = 2 * L + 1
 		alpha = torch.empty(B, T, S, dtype = torch.float32, device = lp.device)
+		# when a gradient will be wanted, alpha and beta run concurrently in one launch
+		beta = torch.empty_like(alpha) if ctx.needs_input_grad[0] else None
 		nll = torch.empty(B, dtype = torch.float32, device = lp.device)
 		st, sb, sc = _tbc_strides(lp)
 		rc = _lib.load().cab_ctc_loss_fwd(
 			_p(lp), st, sb, sc, _p(targets), _p(input_lengths), _p(target_lengths), B, T, C, L, blank, _p(alpha),
-			_p(nll), _stream()
+			_p(beta), _p(nll), _stream()
 		)
 		_lib.check(rc, 'cab_ctc_loss_fwd')
+		ctx.beta = beta
 		ctx.save_for_backward(lp, targets, input_lengths, target_lengths, alpha, nll)
 		ctx.blank = blank
 		ctx.in_dtype = log_probs.dtype
@@ -283,14 +286,16 @@ class _CtcLoss(torch.autograd.Function):
 		lp, targets, input_lengths, target_lengths, alpha, nll = ctx.saved_tensors
 		T, B, C = lp.shape
 		L = targets.shape[1]
-		beta = torch.empty_like(alpha)
+		beta_ready = ctx.beta is not None
+		beta = ctx.beta if beta_ready else torch.empty_like(alpha)
+		ctx.beta = None
 		# gradient laid out like log_probs' memory (keeps [B,C,T]-permuted views coalesced)
 		grad = torch.empty_strided(lp.shape, lp.stride(), dtype = torch.float32, device = lp.device)
 		st, sb, sc = _tbc_strides(lp)
 		go = grad_out.to(torch.float32).contiguous()
 		rc = _lib.load().cab_ctc_loss_bwd(
 			_p(lp), st, sb, sc, _p(targets), _p(input_lengths), _p(target_lengths), B, T, C, L, ctx.blank, _p(alpha),
-			_p(beta), _p(nll), _p(go), _p(grad), grad.stride(0), grad.stride(1), grad.stride(2), _stream()
+			_p(beta), int(beta_ready), _p(nll), _p(go), _p(grad), grad.stride(0), grad.stride(1), grad.stride(2), _stream()
 		)
 		_lib.check(rc, 'cab_ctc_loss_bwd')
 		return grad.to(ctx.in_dtype), None, None, None, None

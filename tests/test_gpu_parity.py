@@ -156,13 +156,26 @@ def test_ctc_loss_bench_shape_against_float64_oracle(dev):
 	y = torch.randint(0, C - 1, (B, L), generator = g)
 	ylen = torch.tensor([225, 150, 3])
 	olen = torch.tensor([753, 600, 410])
-	nll, grad = O.ctc_loss_np(lp_bct.permute(2, 0, 1).numpy(), y.numpy(), olen.numpy(), ylen.numpy(), C - 1)
-	lp = lp_bct.to(dev).requires_grad_(True)
-	loss = ctc.ctc_loss(lp.permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
-	assert torch.allclose(loss.double().cpu(), torch.from_numpy(nll), rtol = 1e-4)
-	loss.sum().backward()
-	assert rel(lp.grad.permute(2, 0, 1), torch.from_numpy(grad)) < 1e-4
-	assert float(lp.grad.sum(1).abs().max()) < 1e-3  # softmax already folded in: sums to 0 over C
+	# (a) log-probs of a model that has learnt something: the target path is likely, nll = O(100)
+	path = torch.full((B, T), C - 1)
+	for b in range(B):
+		pos = torch.linspace(0, int(olen[b]) - 1, int(ylen[b])).long()
+		path[b, pos] = y[b, :int(ylen[b])]
+	peaked = (torch.randn(B, C, T, generator = g) + 6.0 * torch.nn.functional.one_hot(path, C).permute(0, 2, 1)).log_softmax(1)
+	# (b) uniform-ish random log-probs: nll = O(3000), where fp32 alpha+beta-nll carries ~ulp(3000)=2.4e-4
+	#     of rounding noise in ANY fp32 implementation (ATen's included) -- looser bar, documented in DESIGN.md
+	for lp_cpu, tol in ((peaked, 1e-4), (lp_bct, 1e-3)):
+		nll, grad = O.ctc_loss_np(lp_cpu.permute(2, 0, 1).numpy(), y.numpy(), olen.numpy(), ylen.numpy(), C - 1)
+		lp = lp_cpu.to(dev).requires_grad_(True)
+		loss = ctc.ctc_loss(lp.permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
+		assert torch.allclose(loss.double().cpu(), torch.from_numpy(nll), rtol = 1e-4)
+		loss.sum().backward()
+		assert rel(lp.grad.permute(2, 0, 1), torch.from_numpy(grad)) < tol, tol
+		assert float(lp.grad.sum(1).abs().max()) < 2e-3  # softmax already folded in: sums to 0 over C
+	# forward-only call (no gradient requested) gives the same loss
+	with torch.no_grad():
+		loss2 = ctc.ctc_loss(lp.detach().permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
+	assert torch.equal(loss2, loss.detach())
 
 
 def test_alignment_against_golden_and_oracle(golden, dev):
