@@ -49,7 +49,7 @@ SIGNATURES = {
 	'cab_log_softmax_argmax': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 	'cab_log_softmax_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
 	'cab_ctc_loss_fwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-						c_void_p, c_void_p, c_void_p, c_void_p],
+						c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
 	'cab_ctc_loss_bwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
 						c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p],
 	'cab_ctc_alignment': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -50,7 +50,7 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
                                      const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
                                      const int64_t* __restrict__ tgt_len, int B, int T, int L_max, int blank,
                                      int first_role, float* __restrict__ alpha_ws, float* __restrict__ beta_ws,
-                                     float* __restrict__ nll) {
+                                     double* __restrict__ off_ws, int G_cap, float* __restrict__ nll) {
     extern __shared__ float sh[];
     const int b = blockIdx.x % B;
     const bool rev = (first_role + blockIdx.x / B) != 0;  // role 0 = alpha, role 1 = beta
@@ -60,16 +60,26 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
     const int S = 2 * tl + 1;
     float* buf0 = sh;  // index s+2 (two guard cells at the front)
     float* buf1 = sh + (S_max + 2);
+    float* s_red = buf1 + (S_max + 2);  // [32] per-warp maxima of the re-centring step
     const float* lpb = lp + (int64_t)b * sb;
     float* ws = (rev ? beta_ws : alpha_ws) + (size_t)b * T * S_max;
+    // Re-centring: every kCtcPrefetch steps the block maximum is subtracted from the running
+    // values and accumulated (in double) into off[g]; stored values therefore stay O(10) instead
+    // of O(nll), which keeps fp32 rounding out of alpha+beta-nll for long utterances.
+    double* off = off_ws + ((size_t)b * 2 + (rev ? 1 : 0)) * G_cap;
+    double O = 0.0;
 
     if (il <= 0 || il > T || tl > L_max || tl < 0) {
-        if (threadIdx.x == 0 && !rev && nll) nll[b] = INFINITY;
+        if (threadIdx.x == 0 && !rev) {
+            if (nll) nll[b] = INFINITY;
+            off[G_cap - 1] = -(double)INFINITY;
+        }
         return;
     }
+    if (threadIdx.x == 0) off[0] = 0.0;
     // per-thread states (virtual index s runs in recursion order; sr is the real state)
     int sr[kCtcMaxPer];
-    int64_t off[kCtcMaxPer];  // ext(s) * stride_c
+    int64_t off_c[kCtcMaxPer];  // ext(s) * stride_c
     bool skip[kCtcMaxPer];
 #pragma unroll
     for (int i = 0; i < kCtcMaxPer; ++i) {
@@ -84,7 +94,7 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
                 skip[i] = e != (int)targets[(size_t)b * L_max + (s2 >> 1)];
             }
         }
-        off[i] = (int64_t)e * sc;
+        off_c[i] = (int64_t)e * sc;
     }
     if (threadIdx.x < 2) { buf0[threadIdx.x] = -INFINITY; buf1[threadIdx.x] = -INFINITY; }
     auto tmap = [&](int t) -> int64_t { return (int64_t)(rev ? il - 1 - t : t) * st; };
@@ -96,7 +106,7 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
         const int s = threadIdx.x + i * blockDim.x;
         if (s < S) {
             float a = -INFINITY;
-            if (s < 2) a = lpb[tmap(0) + off[i]];
+            if (s < 2) a = lpb[tmap(0) + off_c[i]];
             buf0[s + 2] = a;
             ws[wrow(0) + sr[i]] = a;
         }
@@ -109,13 +119,17 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
 #pragma unroll
         for (int i = 0; i < kCtcMaxPer; ++i) {
             const int s = threadIdx.x + i * blockDim.x;
-            ring[i][u] = (s < S && t < il) ? lpb[tmap(t) + off[i]] : 0.f;
+            ring[i][u] = (s < S && t < il) ? lpb[tmap(t) + off_c[i]] : 0.f;
         }
     }
     __syncthreads();
     float* prev = buf0;
     float* cur = buf1;
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int t0 = 1; t0 < il; t0 += kCtcPrefetch) {
+        float vlast[kCtcMaxPer];
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) vlast[i] = -INFINITY;
 #pragma unroll
         for (int u = 0; u < kCtcPrefetch; ++u) {
             const int t = t0 + u;
@@ -126,24 +140,46 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
                     if (s < S) {
                         const float e = ring[i][u];
                         const int tn = t + kCtcPrefetch;
-                        if (tn < il) ring[i][u] = lpb[tmap(tn) + off[i]];
+                        if (tn < il) ring[i][u] = lpb[tmap(tn) + off_c[i]];
                         const float a1 = prev[s + 2];
                         const float a2 = prev[s + 1];
                         const float a3 = skip[i] ? prev[s] : -INFINITY;
                         const float v = lse3_fast(a1, a2, a3) + e;
                         cur[s + 2] = v;
                         ws[wrow(t) + sr[i]] = v;
+                        vlast[i] = v;
                     }
                 }
                 __syncthreads();
                 float* tmp = prev; prev = cur; cur = tmp;
             }
         }
+        // re-centre: subtract the block maximum from the live values (prev)
+        float m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kCtcMaxPer; ++i) m = fmaxf(m, vlast[i]);
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) s_red[warp] = m;
+        __syncthreads();
+        m = -INFINITY;
+        for (int w = 0; w < n_warps; ++w) m = fmaxf(m, s_red[w]);
+        if (m > -INFINITY && m < INFINITY) {
+#pragma unroll
+            for (int i = 0; i < kCtcMaxPer; ++i) {
+                const int s = threadIdx.x + i * blockDim.x;
+                if (s < S) prev[s + 2] -= m;
+            }
+            O += (double)m;
+        }
+        if (threadIdx.x == 0) off[(t0 - 1) / kCtcPrefetch + 1] = O;
+        __syncthreads();
     }
-    if (threadIdx.x == 0 && !rev && nll) {
+    if (threadIdx.x == 0 && !rev) {
         const float l1 = prev[S - 1 + 2];
         const float l2 = S > 1 ? prev[S - 2 + 2] : -INFINITY;
-        nll[b] = -lse2(l1, l2);
+        const double ll = (double)lse2(l1, l2) + O;
+        if (nll) nll[b] = (float)(-ll);
+        off[G_cap - 1] = ll;
     }
 }
 
@@ -172,7 +208,7 @@ __global__ void ctc_grad_scatter_kernel(const float* __restrict__ lp, int64_t st
                                         const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
                                         const int64_t* __restrict__ tgt_len, int T, int L_max, int blank,
                                         const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
-                                        const float* __restrict__ nll, const float* __restrict__ go,
+                                        const double* __restrict__ off_ws, int G_cap, const float* __restrict__ go,
                                         float* __restrict__ grad, int64_t gt, int64_t gb, int64_t gc) {
     const int b = blockIdx.y;
     const int S_max = 2 * L_max + 1;
@@ -182,7 +218,13 @@ __global__ void ctc_grad_scatter_kernel(const float* __restrict__ lp, int64_t st
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + warp;
     if (t >= il || tl > L_max) return;
-    const float nl = nll[b], g = go[b];
+    // alpha + beta - ll with the re-centring offsets folded in, in double: O(1) result
+    const double* offa = off_ws + (size_t)b * 2 * G_cap;
+    const double* offb = offa + G_cap;
+    const int tb = il - 1 - t;  // step index of this frame in the reversed (beta) recursion
+    const int ga = t == 0 ? 0 : (t - 1) / kCtcPrefetch, gbt = tb == 0 ? 0 : (tb - 1) / kCtcPrefetch;
+    const float nl = (float)(offa[ga] + offb[gbt] - offa[G_cap - 1]);
+    const float g = go[b];
     const float* lpt = lp + (int64_t)t * st + (int64_t)b * sb;
     float* gr = grad + (int64_t)t * gt + (int64_t)b * gb;
     const float lp_blank = lpt[(int64_t)blank * sc];
@@ -501,20 +543,23 @@ using namespace cab;
     const int S_max = 2 * L_max + 1;                                                              \
     CAB_CHECK_ARG(S_max <= kCtcMaxPer * 1024, "target too long: L_max=%d", L_max);                \
     const int threads = ctc_threads(S_max);                                                       \
-    const size_t smem = sizeof(float) * 2 * (S_max + 2);
+    const int G_cap = (T + kCtcPrefetch - 1) / kCtcPrefetch + 2;                                  \
+    (void)G_cap;                                                                                  \
+    const size_t smem = sizeof(float) * (2 * (S_max + 2) + 32);
 
 extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                 const int64_t* targets, const int64_t* input_lengths,
                                 const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                                float* ws_alpha, float* ws_beta, float* nll, cab_stream_t stream_) {
+                                float* ws_alpha, float* ws_beta, double* ws_offsets, float* nll,
+                                cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTC_COMMON_CHECKS();
-    CAB_CHECK_ARG(ws_alpha && nll, "null workspace/output");
+    CAB_CHECK_ARG(ws_alpha && ws_offsets && nll, "null workspace/output");
     // ws_beta given: run the beta recursion in the same grid (both are needed for the gradient)
     const int roles = ws_beta ? 2 : 1;
     ctc_recursion_kernel<<<B * roles, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
                                                                input_lengths, target_lengths, B, T, L_max, blank, 0,
-                                                               ws_alpha, ws_beta, nll);
+                                                               ws_alpha, ws_beta, ws_offsets, G_cap, nll);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -523,17 +568,17 @@ extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_
 extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                 const int64_t* targets, const int64_t* input_lengths,
                                 const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                                const float* ws_alpha, float* ws_beta, int beta_ready, const float* nll,
+                                const float* ws_alpha, float* ws_beta, int beta_ready, double* ws_offsets,
                                 const float* grad_out, float* grad, int64_t gstride_t, int64_t gstride_b,
                                 int64_t gstride_c, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTC_COMMON_CHECKS();
-    CAB_CHECK_ARG(ws_alpha && ws_beta && nll && grad_out && grad, "null workspace/output");
+    CAB_CHECK_ARG(ws_alpha && ws_beta && ws_offsets && grad_out && grad, "null workspace/output");
     int n_launch = 2;
     if (!beta_ready) {
         ctc_recursion_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
                                                            input_lengths, target_lengths, B, T, L_max, blank, 1,
-                                                           nullptr, ws_beta, nullptr);
+                                                           nullptr, ws_beta, ws_offsets, G_cap, nullptr);
         CAB_CHECK_LAUNCH();
         ++n_launch;
     }
@@ -549,8 +594,8 @@ extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_
         dim3 grid((T + 7) / 8, B);
         ctc_grad_scatter_kernel<<<grid, 256, 0, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
                                                           input_lengths, target_lengths, T, L_max, blank, ws_alpha,
-                                                          ws_beta, nll, grad_out, grad, gstride_t, gstride_b,
-                                                          gstride_c);
+                                                          ws_beta, ws_offsets, G_cap, grad_out, grad, gstride_t,
+                                                          gstride_b, gstride_c);
         CAB_CHECK_LAUNCH();
     }
     g_launch_count.fetch_add(n_launch, std::memory_order_relaxed);

@@ -269,21 +269,22 @@ class _CtcLoss(torch.autograd.Function):
 		# when a gradient will be wanted, alpha and beta run concurrently in one launch
 		beta = torch.empty_like(alpha) if ctx.needs_input_grad[0] else None
 		nll = torch.empty(B, dtype = torch.float32, device = lp.device)
+		offsets = torch.empty(B, 2, (T + 7) // 8 + 2, dtype = torch.float64, device = lp.device)
 		st, sb, sc = _tbc_strides(lp)
 		rc = _lib.load().cab_ctc_loss_fwd(
 			_p(lp), st, sb, sc, _p(targets), _p(input_lengths), _p(target_lengths), B, T, C, L, blank, _p(alpha),
-			_p(beta), _p(nll), _stream()
+			_p(beta), _p(offsets), _p(nll), _stream()
 		)
 		_lib.check(rc, 'cab_ctc_loss_fwd')
 		ctx.beta = beta
-		ctx.save_for_backward(lp, targets, input_lengths, target_lengths, alpha, nll)
+		ctx.save_for_backward(lp, targets, input_lengths, target_lengths, alpha, offsets)
 		ctx.blank = blank
 		ctx.in_dtype = log_probs.dtype
 		return nll
 
 	@staticmethod
 	def backward(ctx, grad_out):
-		lp, targets, input_lengths, target_lengths, alpha, nll = ctx.saved_tensors
+		lp, targets, input_lengths, target_lengths, alpha, offsets = ctx.saved_tensors
 		T, B, C = lp.shape
 		L = targets.shape[1]
 		beta_ready = ctx.beta is not None
@@ -295,7 +296,7 @@ class _CtcLoss(torch.autograd.Function):
 		go = grad_out.to(torch.float32).contiguous()
 		rc = _lib.load().cab_ctc_loss_bwd(
 			_p(lp), st, sb, sc, _p(targets), _p(input_lengths), _p(target_lengths), B, T, C, L, ctx.blank, _p(alpha),
-			_p(beta), int(beta_ready), _p(nll), _p(go), _p(grad), grad.stride(0), grad.stride(1), grad.stride(2), _stream()
+			_p(beta), int(beta_ready), _p(offsets), _p(go), _p(grad), grad.stride(0), grad.stride(1), grad.stride(2), _stream()
 		)
 		_lib.check(rc, 'cab_ctc_loss_bwd')
 		return grad.to(ctx.in_dtype), None, None, None, None

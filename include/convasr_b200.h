@@ -150,6 +150,8 @@ int cab_log_softmax_bwd(const float* log_probs, const float* grad_out, int B, in
  *   element strides so both [T,B,C] and the permuted [B,C,T] view work without a copy.
  *   targets: int64 [B, L_max] padded; input_lengths / target_lengths: int64 [B].
  *   ws_alpha / ws_beta: fp32 [B, T, 2*L_max+1] workspaces.  nll: fp32 [B].
+ *   ws_offsets: fp64 [B, 2, (T+7)/8 + 2] workspace (re-centring offsets of the recursions and the
+ *   log-likelihood; alpha/beta are stored relative to them so fp32 stays accurate for long inputs).
  *   cab_ctc_loss_fwd with a non-NULL ws_beta also runs the beta recursion, concurrently with
  *   alpha in the same grid (the caller then passes beta_ready=1 to cab_ctc_loss_bwd).
  *   The backward returns ATen's convention: (exp(lp) - occupancy) * grad_out, zero for
@@ -158,11 +160,12 @@ int cab_log_softmax_bwd(const float* log_probs, const float* grad_out, int B, in
 int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                      const int64_t* targets, const int64_t* input_lengths,
                      const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                     float* ws_alpha, float* ws_beta_or_null, float* nll, cab_stream_t stream);
+                     float* ws_alpha, float* ws_beta_or_null, double* ws_offsets, float* nll,
+                     cab_stream_t stream);
 int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                      const int64_t* targets, const int64_t* input_lengths,
                      const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                     const float* ws_alpha, float* ws_beta, int beta_ready, const float* nll,
+                     const float* ws_alpha, float* ws_beta, int beta_ready, double* ws_offsets,
                      const float* grad_out, float* grad, int64_t gstride_t, int64_t gstride_b,
                      int64_t gstride_c, cab_stream_t stream);
 
