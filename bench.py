@@ -163,6 +163,7 @@ def main():
 	ap.add_argument('--workload', default = DEFAULT_WORKLOAD, choices = sorted(WORKLOADS))
 	ap.add_argument('--no-cpu-baseline', action = 'store_true')
 	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
+	ap.add_argument('--no-cuda-graphs', action = 'store_true')
 	args = ap.parse_args()
 	model_name, C, B, seconds, precision = WORKLOADS[args.workload]
 	rank = int(os.environ.get('RANK', 0))
@@ -170,7 +171,7 @@ def main():
 	local_rank = int(os.environ.get('LOCAL_RANK', 0))
 	steps, warmup = args.steps, max(args.warmup, 3)
 	config = dict(workload = args.workload, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision,
-				step = 'frontend+instnorm+conv stack+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)', parallelism = f'utterance-sharded replicas x{world}', l2 = 'flushed between timed steps (256 MiB memset)')
+				step = 'frontend+instnorm+conv stack+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)', parallelism = f'utterance-sharded replicas x{world}', l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
 
 	if args.impl == 'reference':
 		if rank != 0:
@@ -250,6 +251,15 @@ def main():
 		torch.cuda.synchronize()
 		return sum(a.elapsed_time(b) for a, b in evs)  # ms
 
+	# one eager step counts this repo's kernel launches per step (graph replays bypass the counter)
+	step_device()
+	torch.cuda.synchronize()
+	l0 = _lib.launch_count()
+	step_device()
+	torch.cuda.synchronize()
+	launches_per_step = _lib.launch_count() - l0
+	if not args.no_cuda_graphs:
+		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
 	for _ in range(warmup):
 		nll, _ = step_device()
 	torch.cuda.synchronize()
@@ -258,12 +268,11 @@ def main():
 	if rank == 0:
 		sampler.start()
 	barrier()
-	launches0 = _lib.launch_count()
 	t_wall0 = time.time()
 	ms = timed(step_device, steps)
 	barrier()
 	t_wall1 = time.time()
-	launches = _lib.launch_count() - launches0
+	launches = launches_per_step * steps
 	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
 	# dominant kernel (conv1d_umma_kernel): per-launch CUDA events on the launching stream
@@ -278,12 +287,15 @@ def main():
 		conv_events.append((e0, e1))
 
 	ops.conv1d_fused = traced
+	model.enable_cuda_graphs(False)  # per-launch events need the eager launch path
 	n_prof = min(steps, 5)
 	for _ in range(n_prof):
 		flush.zero_()
 		step_device()
 	torch.cuda.synchronize()
 	ops.conv1d_fused = orig
+	if not args.no_cuda_graphs:
+		model.enable_cuda_graphs(True)
 	conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / n_prof
 	n_conv = len(conv_events) // n_prof
 

@@ -34,38 +34,52 @@ __device__ __forceinline__ float lse2(float a, float b) {
 // beta is alpha on the time- and state-reversed problem (beta[t][s] = alpha'[il-1-t][S-1-s]),
 // so one body serves both directions; with both roles in one grid the two latency-bound
 // recursions of an utterance run concurrently on different SMs.
-// The emission of step t+kCtcPrefetch is requested while step t is computed, so the L2/HBM
-// latency never sits on the sequential critical path.
-// shared: float prev[2][S_max + 2]
+//
+// Emissions are staged through shared memory with cp.async, G time steps per group and two
+// groups in flight: s_e[group & 1][u][s] = lp[t0 + u, ext(s)].  The copy loop is laid out so that
+// a warp reads 32 consecutive elements along the contiguous dimension of log_probs (time for the
+// model's [B, C, T] layout), i.e. coalesced 128-byte lines instead of one sector per state and
+// step; the sequential critical path only touches shared memory.
+//
+// Every kCtcRecentre steps the block maximum is subtracted from the live values and accumulated
+// in fp64 (off_ws): stored alpha/beta stay O(10) instead of O(nll), which keeps fp32 rounding
+// out of alpha + beta - nll for long utterances.
 // ------------------------------------------------------------------------------------------
-constexpr int kCtcPrefetch = 8;
+constexpr int kCtcPrefetch = 8;  // re-centring interval (also the offset-table granularity)
 
 __device__ __forceinline__ float lse3_fast(float a, float b, float c) {
     const float m = fmaxf(a, fmaxf(b, c));
     if (m == -INFINITY) return -INFINITY;
     return __logf(__expf(a - m) + __expf(b - m) + __expf(c - m)) + m;
 }
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
                                      const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
                                      const int64_t* __restrict__ tgt_len, int B, int T, int L_max, int blank,
-                                     int first_role, float* __restrict__ alpha_ws, float* __restrict__ beta_ws,
-                                     double* __restrict__ off_ws, int G_cap, float* __restrict__ nll) {
+                                     int first_role, int G, float* __restrict__ alpha_ws,
+                                     float* __restrict__ beta_ws, double* __restrict__ off_ws, int G_cap,
+                                     float* __restrict__ nll) {
     extern __shared__ float sh[];
     const int b = blockIdx.x % B;
     const bool rev = (first_role + blockIdx.x / B) != 0;  // role 0 = alpha, role 1 = beta
     const int S_max = 2 * L_max + 1;
+    const int S_pad = S_max | 1;  // odd row pitch: conflict-free transposed staging
     const int tl = (int)tgt_len[b];
     const int il = (int)in_len[b];
     const int S = 2 * tl + 1;
     float* buf0 = sh;  // index s+2 (two guard cells at the front)
     float* buf1 = sh + (S_max + 2);
-    float* s_red = buf1 + (S_max + 2);  // [32] per-warp maxima of the re-centring step
+    float* s_red = buf1 + (S_max + 2);                     // [32]
+    int* s_ext = reinterpret_cast<int*>(s_red + 32);       // [S_max] class of virtual state s
+    float* s_e = reinterpret_cast<float*>(s_ext + S_max);  // [2][G][S_pad]
     const float* lpb = lp + (int64_t)b * sb;
     float* ws = (rev ? beta_ws : alpha_ws) + (size_t)b * T * S_max;
-    // Re-centring: every kCtcPrefetch steps the block maximum is subtracted from the running
-    // values and accumulated (in double) into off[g]; stored values therefore stay O(10) instead
-    // of O(nll), which keeps fp32 rounding out of alpha+beta-nll for long utterances.
     double* off = off_ws + ((size_t)b * 2 + (rev ? 1 : 0)) * G_cap;
     double O = 0.0;
 
@@ -77,9 +91,9 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
         return;
     }
     if (threadIdx.x == 0) off[0] = 0.0;
+
     // per-thread states (virtual index s runs in recursion order; sr is the real state)
     int sr[kCtcMaxPer];
-    int64_t off_c[kCtcMaxPer];  // ext(s) * stride_c
     bool skip[kCtcMaxPer];
 #pragma unroll
     for (int i = 0; i < kCtcMaxPer; ++i) {
@@ -94,11 +108,31 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
                 skip[i] = e != (int)targets[(size_t)b * L_max + (s2 >> 1)];
             }
         }
-        off_c[i] = (int64_t)e * sc;
+        if (s < S) s_ext[s] = e;
     }
     if (threadIdx.x < 2) { buf0[threadIdx.x] = -INFINITY; buf1[threadIdx.x] = -INFINITY; }
     auto tmap = [&](int t) -> int64_t { return (int64_t)(rev ? il - 1 - t : t) * st; };
     auto wrow = [&](int t) -> size_t { return (size_t)(rev ? il - 1 - t : t) * S_max; };
+    __syncthreads();  // s_ext visible
+
+    // stage group g: virtual steps 1 + g*G + u, u in [0, G)
+    const bool time_contig = (st == 1 || st == -1);
+    auto issue = [&](int g) {
+        const int tg0 = 1 + g * G;
+        if (tg0 < il) {
+            float* dst = s_e + (size_t)(g & 1) * G * S_pad;
+            const int n = S * G;
+            for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+                int s, u;
+                if (time_contig) { u = idx % G; s = idx / G; } else { s = idx % S; u = idx / S; }
+                const int t = tg0 + u;
+                if (t < il) cp_async_4(dst + u * S_pad + s, lpb + tmap(t) + (int64_t)s_ext[s] * sc);
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0);
+    issue(1);
 
     // step 0
 #pragma unroll
@@ -106,74 +140,71 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
         const int s = threadIdx.x + i * blockDim.x;
         if (s < S) {
             float a = -INFINITY;
-            if (s < 2) a = lpb[tmap(0) + off_c[i]];
+            if (s < 2) a = lpb[tmap(0) + (int64_t)s_ext[s] * sc];
             buf0[s + 2] = a;
             ws[wrow(0) + sr[i]] = a;
         }
     }
-    // prefetch ring: ring[i][u] holds the emission of step t with t % kCtcPrefetch == u
-    float ring[kCtcMaxPer][kCtcPrefetch];
-#pragma unroll
-    for (int u = 0; u < kCtcPrefetch; ++u) {
-        const int t = 1 + u;
-#pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) {
-            const int s = threadIdx.x + i * blockDim.x;
-            ring[i][u] = (s < S && t < il) ? lpb[tmap(t) + off_c[i]] : 0.f;
-        }
-    }
-    __syncthreads();
     float* prev = buf0;
     float* cur = buf1;
     const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int t0 = 1; t0 < il; t0 += kCtcPrefetch) {
-        float vlast[kCtcMaxPer];
+    const int n_groups = (il - 1 + G - 1) / G;
+    for (int g = 0; g < n_groups; ++g) {
+        cp_async_wait<1>();  // this thread's copies of group g have landed
+        __syncthreads();     // ... and everybody else's; also orders step 0 / previous group
+        const float* se = s_e + (size_t)(g & 1) * G * S_pad;
+        for (int u0 = 0; u0 < G; u0 += kCtcPrefetch) {
+            const int t0 = 1 + g * G + u0;
+            if (t0 >= il) break;  // uniform
+            float vlast[kCtcMaxPer];
 #pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) vlast[i] = -INFINITY;
+            for (int i = 0; i < kCtcMaxPer; ++i) vlast[i] = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < kCtcPrefetch; ++u) {
-            const int t = t0 + u;
-            if (t < il) {  // uniform across the block
+            for (int u = 0; u < kCtcPrefetch; ++u) {
+                const int t = t0 + u;
+                if (t < il) {  // uniform across the block
+#pragma unroll
+                    for (int i = 0; i < kCtcMaxPer; ++i) {
+                        const int s = threadIdx.x + i * blockDim.x;
+                        if (s < S) {
+                            const float e = se[(u0 + u) * S_pad + s];
+                            const float a1 = prev[s + 2];
+                            const float a2 = prev[s + 1];
+                            const float a3 = skip[i] ? prev[s] : -INFINITY;
+                            const float v = lse3_fast(a1, a2, a3) + e;
+                            cur[s + 2] = v;
+                            ws[wrow(t) + sr[i]] = v;
+                            vlast[i] = v;
+                        }
+                    }
+                    __syncthreads();
+                    float* tmp = prev; prev = cur; cur = tmp;
+                }
+            }
+            // re-centre: subtract the block maximum from the live values (prev)
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kCtcMaxPer; ++i) m = fmaxf(m, vlast[i]);
+            m = warp_max(m);
+            if ((threadIdx.x & 31) == 0) s_red[warp] = m;
+            __syncthreads();
+            m = -INFINITY;
+            for (int w = 0; w < n_warps; ++w) m = fmaxf(m, s_red[w]);
+            if (m > -INFINITY && m < INFINITY) {
 #pragma unroll
                 for (int i = 0; i < kCtcMaxPer; ++i) {
                     const int s = threadIdx.x + i * blockDim.x;
-                    if (s < S) {
-                        const float e = ring[i][u];
-                        const int tn = t + kCtcPrefetch;
-                        if (tn < il) ring[i][u] = lpb[tmap(tn) + off_c[i]];
-                        const float a1 = prev[s + 2];
-                        const float a2 = prev[s + 1];
-                        const float a3 = skip[i] ? prev[s] : -INFINITY;
-                        const float v = lse3_fast(a1, a2, a3) + e;
-                        cur[s + 2] = v;
-                        ws[wrow(t) + sr[i]] = v;
-                        vlast[i] = v;
-                    }
+                    if (s < S) prev[s + 2] -= m;
                 }
-                __syncthreads();
-                float* tmp = prev; prev = cur; cur = tmp;
+                O += (double)m;
             }
+            if (threadIdx.x == 0) off[(t0 - 1) / kCtcPrefetch + 1] = O;
+            __syncthreads();
         }
-        // re-centre: subtract the block maximum from the live values (prev)
-        float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kCtcMaxPer; ++i) m = fmaxf(m, vlast[i]);
-        m = warp_max(m);
-        if ((threadIdx.x & 31) == 0) s_red[warp] = m;
-        __syncthreads();
-        m = -INFINITY;
-        for (int w = 0; w < n_warps; ++w) m = fmaxf(m, s_red[w]);
-        if (m > -INFINITY && m < INFINITY) {
-#pragma unroll
-            for (int i = 0; i < kCtcMaxPer; ++i) {
-                const int s = threadIdx.x + i * blockDim.x;
-                if (s < S) prev[s + 2] -= m;
-            }
-            O += (double)m;
-        }
-        if (threadIdx.x == 0) off[(t0 - 1) / kCtcPrefetch + 1] = O;
-        __syncthreads();
+        issue(g + 2);  // refill the buffer everybody has just finished reading
     }
+    cp_async_wait<0>();
+    __syncthreads();
     if (threadIdx.x == 0 && !rev) {
         const float l1 = prev[S - 1 + 2];
         const float l2 = S > 1 ? prev[S - 2 + 2] : -INFINITY;
@@ -532,6 +563,25 @@ static int ctc_threads(int S_max) {
     return th;
 }
 
+// shared memory of ctc_recursion_kernel for a staging depth of G steps; picks the deepest that fits
+static int ctc_rec_config(int S_max, int* G_out, size_t* smem_out) {
+    const int S_pad = S_max | 1;
+    for (int G = 32; G >= kCtcPrefetch; G >>= 1) {
+        const size_t bytes = sizeof(float) * (2 * (size_t)(S_max + 2) + 32 + (size_t)S_max + 2 * (size_t)G * S_pad);
+        if (bytes <= 200 * 1024) {
+            *G_out = G;
+            *smem_out = bytes;
+            static size_t attr_set = 0;
+            if (bytes > attr_set) {
+                if (cudaFuncSetAttribute(ctc_recursion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+                attr_set = bytes;
+            }
+            return 0;
+        }
+    }
+    return -1;
+}
+
 }  // namespace cab
 
 using namespace cab;
@@ -545,7 +595,8 @@ using namespace cab;
     const int threads = ctc_threads(S_max);                                                       \
     const int G_cap = (T + kCtcPrefetch - 1) / kCtcPrefetch + 2;                                  \
     (void)G_cap;                                                                                  \
-    const size_t smem = sizeof(float) * (2 * (S_max + 2) + 32);
+    const size_t smem = sizeof(float) * (2 * (S_max + 2) + 32);                                   \
+    (void)smem;
 
 extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                 const int64_t* targets, const int64_t* input_lengths,
@@ -557,9 +608,12 @@ extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_
     CAB_CHECK_ARG(ws_alpha && ws_offsets && nll, "null workspace/output");
     // ws_beta given: run the beta recursion in the same grid (both are needed for the gradient)
     const int roles = ws_beta ? 2 : 1;
-    ctc_recursion_kernel<<<B * roles, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                               input_lengths, target_lengths, B, T, L_max, blank, 0,
-                                                               ws_alpha, ws_beta, ws_offsets, G_cap, nll);
+    int G = 0;
+    size_t rec_smem = 0;
+    CAB_CHECK_ARG(ctc_rec_config(S_max, &G, &rec_smem) == 0, "target too long for the staged recursion: L_max=%d", L_max);
+    ctc_recursion_kernel<<<B * roles, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                                   input_lengths, target_lengths, B, T, L_max, blank,
+                                                                   0, G, ws_alpha, ws_beta, ws_offsets, G_cap, nll);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -576,9 +630,12 @@ extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_
     CAB_CHECK_ARG(ws_alpha && ws_beta && ws_offsets && grad_out && grad, "null workspace/output");
     int n_launch = 2;
     if (!beta_ready) {
-        ctc_recursion_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                           input_lengths, target_lengths, B, T, L_max, blank, 1,
-                                                           nullptr, ws_beta, ws_offsets, G_cap, nullptr);
+        int G = 0;
+        size_t rec_smem = 0;
+        CAB_CHECK_ARG(ctc_rec_config(S_max, &G, &rec_smem) == 0, "target too long for the staged recursion: L_max=%d", L_max);
+        ctc_recursion_kernel<<<B, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
+                                                               input_lengths, target_lengths, B, T, L_max, blank, 1, G,
+                                                               nullptr, ws_beta, ws_offsets, G_cap, nullptr);
         CAB_CHECK_LAUNCH();
         ++n_launch;
     }

@@ -340,7 +340,11 @@ extern "C" int cab_frontend_logmel(const void* signal, int signal_is_int16, cons
                   sizeof(float) * (kFrontendWarps * 2 * nfp + n_mels * (kFramesPerCta + 1));
     dim3 grid((F + kFramesPerCta - 1) / kFramesPerCta, B);
     auto launch = [&](auto kern) -> int {
-        CAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t smem_set = 0;  // one static per kernel instantiation (generic lambda)
+        if (smem > smem_set) {
+            CAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set = smem;
+        }
         kern<<<grid, kFrontendWarps * 32, smem, stream>>>(p);
         CAB_CHECK_LAUNCH();
         return 0;

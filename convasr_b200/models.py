@@ -98,10 +98,11 @@ class LogFilterBankFrontend(nn.Module):
 		self._tables = None
 
 	def _device_tables(self, device):
-		sig = (self.mel.weight.data_ptr(), self.mel.weight._version, self.window.data_ptr(), str(device))
+		sig = (self.mel.weight.data_ptr(), self.mel.weight._version, self.mel.bias.data_ptr(), self.mel.bias._version, self.window.data_ptr(), str(device))
 		if self._tables is None or self._tables[0] != sig:
 			mel = self.mel.weight.detach().squeeze(-1).to(device = device, dtype = torch.float32).contiguous()
-			self._tables = (sig, mel, ops.make_mel_band(mel), ops.make_twiddle(self.nfft, device), self.window.detach().to(device = device, dtype = torch.float32).contiguous())
+			log_eps = float(self.mel.bias[0])  # one D2H read when the tables are (re)built, never per call
+			self._tables = (sig, mel, ops.make_mel_band(mel), ops.make_twiddle(self.nfft, device), self.window.detach().to(device = device, dtype = torch.float32).contiguous(), log_eps)
 		return self._tables[1:]
 
 	def forward(self, signal, mask = None, xlen = None, **kwargs):
@@ -115,10 +116,10 @@ class LogFilterBankFrontend(nn.Module):
 			# recover exact lengths from the prefix mask; n/T rounds so that ceil(fp32(n/T)*T) == n for n <= 2^23
 			n = mask.reshape(mask.shape[0], -1).sum(dim = -1).to(torch.float32)
 			xlen = (n - 0.5) / T
-		mel, band, twiddle, window = self._device_tables(signal.device)
+		mel, band, twiddle, window, log_eps = self._device_tables(signal.device)
 		return ops.frontend_logmel(
 			signal, xlen, window, mel, band, twiddle, self.hop_length, self.nfft, preemphasis = self.preemphasis,
-			log_eps = float(self.mel.bias[0]), normalize_signal = self.normalize_signal,
+			log_eps = log_eps, normalize_signal = self.normalize_signal,
 			denom_multiplier = self.debug_short_long_records_normalize_signal_multiplier
 		)
 
@@ -356,6 +357,9 @@ class JasperNet(nn.Module):
 		self.check_time_dim_padded = check_time_dim_padded
 		self.precision = precision  # None = follow the parameter dtype; 'bf16' | 'fp32'
 		self._plan = None
+		self._graphs_enabled = os.environ.get('CONVASR_B200_CUDA_GRAPHS', '0') == '1'
+		self._graphs_max = 4
+		self._graphs = {}
 
 	# -- precision tier -------------------------------------------------------------------
 	def set_precision(self, precision):
@@ -391,11 +395,15 @@ class JasperNet(nn.Module):
 		if self.frontend is not None:
 			assert (not self.check_time_dim_padded) or (x.shape[-1] % (32 / 2) == 0), 'Shape of input signal is not divisible by 16 '
 			x = x.squeeze(1) if x.ndim == 3 else x
-			x = self.frontend(x, xlen = xlen)
-		assert (not self.check_time_dim_padded) or (x.shape[-1] % 32 == 0), 'Shape of features after frontend is not divisible by 32'
-		assert x.ndim == 3
+			n_frames = x.shape[-1] // self.frontend.hop_length + 1
+		else:
+			assert x.ndim == 3
+			n_frames = x.shape[-1]
+		assert (not self.check_time_dim_padded) or (n_frames % 32 == 0), 'Shape of features after frontend is not divisible by 32'
 
 		if self.training:
+			if self.frontend is not None:
+				x = self.frontend(x, xlen = xlen)
 			logits = self._forward_training(x, xlen)
 			log_probs = [ops.log_softmax_dim1(l) for l in logits]
 		else:
@@ -410,7 +418,63 @@ class JasperNet(nn.Module):
 			aux = dict(loss = sum(loss) if not self.bpe_only else sum(loss[1:]))
 		return self.dict(logits = logits, log_probs = log_probs, olen = olen, **aux)
 
-	def _forward_native(self, feats, xlen):
+	# -- CUDA graphs ------------------------------------------------------------------------
+	def enable_cuda_graphs(self, enabled = True, max_cached = 4):
+		"""Eval-mode forward as one CUDA-graph replay per (input shape, dtype, mask on/off): removes the
+		host launch gaps between the ~25 short kernels of a step.  Inputs are copied into static buffers
+		and outputs are cloned out, so semantics equal the eager path.  Opt-in because every distinct
+		input shape costs one capture and one private memory pool."""
+		self._graphs_enabled = bool(enabled)
+		self._graphs_max = max_cached
+		self._graphs = {}
+		return self
+
+	def _graphed_raw(self, x, xlen):
+		plan = self._get_plan()
+		key = (tuple(x.shape), x.dtype, xlen is not None, id(plan), x.device.index)
+		entry = self._graphs.get(key)
+		if entry is None:
+			if len(self._graphs) >= self._graphs_max:
+				self._graphs.pop(next(iter(self._graphs)))
+			static_x = x.clone()
+			static_xlen = xlen.clone() if xlen is not None else None
+			side = torch.cuda.Stream(device = x.device)
+			side.wait_stream(torch.cuda.current_stream())
+			with torch.cuda.stream(side):
+				for _ in range(2):
+					self._raw_to_outputs(static_x, static_xlen)
+			torch.cuda.current_stream().wait_stream(side)
+			graph = torch.cuda.CUDAGraph()
+			with torch.cuda.graph(graph):
+				outs = self._raw_to_outputs(static_x, static_xlen)
+			entry = (graph, static_x, static_xlen, outs)
+			self._graphs[key] = entry
+		graph, static_x, static_xlen, outs = entry
+		static_x.copy_(x, non_blocking = True)
+		if xlen is not None:
+			static_xlen.copy_(xlen, non_blocking = True)
+		graph.replay()
+		return [(lg.clone(), lp.clone(), am.clone()) for lg, lp, am in outs]
+
+	def _raw_to_outputs(self, x, xlen):
+		"""raw input (signal or features) -> per head (logits, log_probs, argmax); kernels only"""
+		if self.frontend is not None:
+			x = self.frontend(x, xlen = xlen)
+		return self._features_to_outputs(x, xlen)
+
+	def _forward_native(self, x, xlen):
+		if getattr(self, '_graphs_enabled', False) and not torch.cuda.is_current_stream_capturing():
+			outs = self._graphed_raw(x, xlen)
+		else:
+			outs = self._raw_to_outputs(x, xlen)
+		logits, log_probs = [], []
+		for lg, lp, am in outs:
+			lp._convasr_argmax = am  # lets GreedyCTCGenerator skip its own argmax pass
+			logits.append(lg)
+			log_probs.append(lp)
+		return tuple(logits), log_probs
+
+	def _features_to_outputs(self, feats, xlen):
 		plan = self._get_plan()
 		B, C, Fr = feats.shape
 		stride = self.backbone[0].conv[0][0].stride[0]
@@ -421,13 +485,7 @@ class JasperNet(nn.Module):
 			raise NotImplementedError('convasr_b200: instance norm with running stats / affine parameters is not built')
 		norm_xlen = xlen if (nf is not None and nf.temporal_mask) else None
 		hi, lo, _ = ops.instnorm_pack(feats, norm_xlen, nf.eps if nf is not None else -1.0, F_pad = F_pad, C_pad = C_pad, want_lo = plan.fp32_tier, normalize = nf is not None)
-		outs = plan.run(engine._Act(hi, lo, Fr, C), xlen)
-		logits, log_probs = [], []
-		for lg, lp, am in outs:
-			lp._convasr_argmax = am  # lets GreedyCTCGenerator skip its own argmax pass
-			logits.append(lg)
-			log_probs.append(lp)
-		return tuple(logits), log_probs
+		return plan.run(engine._Act(hi, lo, Fr, C), xlen)
 
 	def _forward_training(self, feats, xlen):
 		# differentiable ATen path (see module docstring); same op order as models.py:296-315
