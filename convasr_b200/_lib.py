@@ -63,7 +63,7 @@ INTROSPECTION = {'cab_abi_version': c_int, 'cab_last_error': ctypes.c_char_p, 'c
 
 
 def lib_path():
-	return _build.LIB_PATH
+	return os.environ.get('CONVASR_B200_LIB') or _build.LIB_PATH
 
 
 def load():

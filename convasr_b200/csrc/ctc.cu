@@ -12,6 +12,7 @@
 #include "../../include/convasr_b200.h"
 #include <atomic>
 #include <float.h>
+#include <cstdlib>
 
 namespace cab {
 extern std::atomic<int64_t> g_launch_count;
@@ -59,6 +60,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int PER>
 __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
                                      const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
                                      const int64_t* __restrict__ tgt_len, int B, int T, int L_max, int blank,
@@ -93,40 +95,51 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
     if (threadIdx.x == 0) off[0] = 0.0;
 
     // per-thread states (virtual index s runs in recursion order; sr is the real state)
-    int sr[kCtcMaxPer];
-    bool skip[kCtcMaxPer];
+    int sr[PER];
+    bool skip[PER], live[PER];
 #pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int s = threadIdx.x + i * blockDim.x;
+        live[i] = s < S;
         sr[i] = rev ? S - 1 - s : s;
         int e = blank;
         skip[i] = false;
-        if (s < S && (sr[i] & 1)) {
+        if (live[i] && (sr[i] & 1)) {
             e = (int)targets[(size_t)b * L_max + (sr[i] >> 1)];
             if (s >= 2) {  // the state two behind in recursion order
                 const int s2 = rev ? sr[i] + 2 : sr[i] - 2;
                 skip[i] = e != (int)targets[(size_t)b * L_max + (s2 >> 1)];
             }
         }
-        if (s < S) s_ext[s] = e;
+        if (live[i]) s_ext[s] = e;
     }
     if (threadIdx.x < 2) { buf0[threadIdx.x] = -INFINITY; buf1[threadIdx.x] = -INFINITY; }
-    auto tmap = [&](int t) -> int64_t { return (int64_t)(rev ? il - 1 - t : t) * st; };
-    auto wrow = [&](int t) -> size_t { return (size_t)(rev ? il - 1 - t : t) * S_max; };
+    const int64_t st_v = rev ? -st : st;                               // stride of one virtual step
+    const float* lp0 = lpb + (int64_t)(rev ? il - 1 : 0) * st;         // virtual step 0
+    const int64_t ws_v = rev ? -(int64_t)S_max : (int64_t)S_max;
+    float* wsp = ws + (size_t)(rev ? il - 1 : 0) * S_max;              // row of virtual step 0
     __syncthreads();  // s_ext visible
 
-    // stage group g: virtual steps 1 + g*G + u, u in [0, G)
+    // stage group g: virtual steps 1 + g*G + u, u in [0, G).  A warp copies, for one state at a
+    // time, 32 consecutive steps (time-contiguous layouts) or, for one step at a time, 32
+    // consecutive states (class-contiguous layouts): coalesced either way, no div/mod.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const bool time_contig = (st == 1 || st == -1);
     auto issue = [&](int g) {
         const int tg0 = 1 + g * G;
         if (tg0 < il) {
             float* dst = s_e + (size_t)(g & 1) * G * S_pad;
-            const int n = S * G;
-            for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-                int s, u;
-                if (time_contig) { u = idx % G; s = idx / G; } else { s = idx % S; u = idx / S; }
-                const int t = tg0 + u;
-                if (t < il) cp_async_4(dst + u * S_pad + s, lpb + tmap(t) + (int64_t)s_ext[s] * sc);
+            const int n_u = min(G, il - tg0);
+            if (time_contig) {
+                for (int s = warp; s < S; s += n_warps) {
+                    const float* src = lp0 + (int64_t)s_ext[s] * sc + (int64_t)tg0 * st_v;
+                    for (int u = lane; u < n_u; u += 32) cp_async_4(dst + u * S_pad + s, src + (int64_t)u * st_v);
+                }
+            } else {
+                for (int u = warp; u < n_u; u += n_warps) {
+                    const float* src = lp0 + (int64_t)(tg0 + u) * st_v;
+                    for (int s = lane; s < S; s += 32) cp_async_4(dst + u * S_pad + s, src + (int64_t)s_ext[s] * sc);
+                }
             }
         }
         cp_async_commit();
@@ -136,65 +149,66 @@ __global__ void ctc_recursion_kernel(const float* __restrict__ lp, int64_t st, i
 
     // step 0
 #pragma unroll
-    for (int i = 0; i < kCtcMaxPer; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int s = threadIdx.x + i * blockDim.x;
-        if (s < S) {
+        if (live[i]) {
             float a = -INFINITY;
-            if (s < 2) a = lpb[tmap(0) + (int64_t)s_ext[s] * sc];
+            if (s < 2) a = lp0[(int64_t)s_ext[s] * sc];
             buf0[s + 2] = a;
-            ws[wrow(0) + sr[i]] = a;
+            wsp[sr[i]] = a;
         }
     }
     float* prev = buf0;
     float* cur = buf1;
-    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int n_groups = (il - 1 + G - 1) / G;
+    int t = 1;
     for (int g = 0; g < n_groups; ++g) {
         cp_async_wait<1>();  // this thread's copies of group g have landed
         __syncthreads();     // ... and everybody else's; also orders step 0 / previous group
-        const float* se = s_e + (size_t)(g & 1) * G * S_pad;
-        for (int u0 = 0; u0 < G; u0 += kCtcPrefetch) {
-            const int t0 = 1 + g * G + u0;
-            if (t0 >= il) break;  // uniform
-            float vlast[kCtcMaxPer];
+        const float* se = s_e + (size_t)(g & 1) * G * S_pad + threadIdx.x;
+        const int g_end = min(il, 1 + (g + 1) * G);
+        while (t < g_end) {
+            const int t0 = t;
+            const int n_sub = min(kCtcPrefetch, g_end - t);
+            float vlast[PER];
 #pragma unroll
-            for (int i = 0; i < kCtcMaxPer; ++i) vlast[i] = -INFINITY;
+            for (int i = 0; i < PER; ++i) vlast[i] = -INFINITY;
+            for (int u = 0; u < n_sub; ++u, ++t) {
+                wsp += ws_v;
 #pragma unroll
-            for (int u = 0; u < kCtcPrefetch; ++u) {
-                const int t = t0 + u;
-                if (t < il) {  // uniform across the block
-#pragma unroll
-                    for (int i = 0; i < kCtcMaxPer; ++i) {
+                for (int i = 0; i < PER; ++i) {
+                    if (live[i]) {
                         const int s = threadIdx.x + i * blockDim.x;
-                        if (s < S) {
-                            const float e = se[(u0 + u) * S_pad + s];
-                            const float a1 = prev[s + 2];
-                            const float a2 = prev[s + 1];
-                            const float a3 = skip[i] ? prev[s] : -INFINITY;
-                            const float v = lse3_fast(a1, a2, a3) + e;
-                            cur[s + 2] = v;
-                            ws[wrow(t) + sr[i]] = v;
-                            vlast[i] = v;
-                        }
+                        const float e = se[i * blockDim.x];
+                        const float a1 = prev[s + 2];
+                        const float a2 = prev[s + 1];
+                        const float a3 = skip[i] ? prev[s] : -INFINITY;
+                        const float v = lse3_fast(a1, a2, a3) + e;
+                        cur[s + 2] = v;
+#ifndef CAB_EXPERIMENT_CTC_NO_STORE
+                        wsp[sr[i]] = v;
+#endif
+                        vlast[i] = v;
                     }
-                    __syncthreads();
-                    float* tmp = prev; prev = cur; cur = tmp;
                 }
+                se += S_pad;
+                __syncthreads();
+                float* tmp = prev; prev = cur; cur = tmp;
             }
             // re-centre: subtract the block maximum from the live values (prev)
-            float m = -INFINITY;
+            float m = vlast[0];
 #pragma unroll
-            for (int i = 0; i < kCtcMaxPer; ++i) m = fmaxf(m, vlast[i]);
+            for (int i = 1; i < PER; ++i) m = fmaxf(m, vlast[i]);
             m = warp_max(m);
-            if ((threadIdx.x & 31) == 0) s_red[warp] = m;
+            if (lane == 0) s_red[warp] = m;
             __syncthreads();
-            m = -INFINITY;
-            for (int w = 0; w < n_warps; ++w) m = fmaxf(m, s_red[w]);
+            m = s_red[lane < n_warps ? lane : 0];
+            m = warp_max(m);
             if (m > -INFINITY && m < INFINITY) {
 #pragma unroll
-                for (int i = 0; i < kCtcMaxPer; ++i) {
+                for (int i = 0; i < PER; ++i) {
                     const int s = threadIdx.x + i * blockDim.x;
-                    if (s < S) prev[s + 2] -= m;
+                    if (live[i]) prev[s + 2] -= m;
                 }
                 O += (double)m;
             }
@@ -555,10 +569,16 @@ entropy_kernel(const float* __restrict__ lp, const int64_t* __restrict__ lengths
 }
 
 static int ctc_threads(int S_max) {
-    int th = ((S_max + kCtcMaxPer - 1) / kCtcMaxPer + 31) / 32 * 32;
-    // prefer one state per thread while that stays within a 1024-thread block
-    int one = (S_max + 31) / 32 * 32;
-    if (one <= 1024) th = one;
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("CONVASR_B200_CTC_THREADS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0 && S_max <= kCtcMaxPer * forced) return forced;
+    // measured on B200 (S = 339, t = 753): 128 threads 609 us, 192: 422, 256: 375, 384: 267 --
+    // the per-state lse chain is latency bound, so one state per thread wins while it fits
+    int th = (S_max + 31) / 32 * 32;
+    if (th > 1024) th = ((S_max + kCtcMaxPer - 1) / kCtcMaxPer + 31) / 32 * 32;
     if (th < 32) th = 32;
     return th;
 }
@@ -573,7 +593,9 @@ static int ctc_rec_config(int S_max, int* G_out, size_t* smem_out) {
             *smem_out = bytes;
             static size_t attr_set = 0;
             if (bytes > attr_set) {
-                if (cudaFuncSetAttribute(ctc_recursion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(ctc_recursion_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(ctc_recursion_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
+                if (cudaFuncSetAttribute(ctc_recursion_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return -1;
                 attr_set = bytes;
             }
             return 0;
@@ -585,6 +607,18 @@ static int ctc_rec_config(int S_max, int* G_out, size_t* smem_out) {
 }  // namespace cab
 
 using namespace cab;
+
+
+#define CAB_LAUNCH_CTC_REC(grid, first_role, A, Bw, NLL)                                                        \
+    do {                                                                                                        \
+        const int per_ = (S_max + threads - 1) / threads;                                                       \
+        if (per_ <= 1)                                                                                          \
+            ctc_recursion_kernel<1><<<grid, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets, input_lengths, target_lengths, B, T, L_max, blank, first_role, G, A, Bw, ws_offsets, G_cap, NLL); \
+        else if (per_ <= 2)                                                                                     \
+            ctc_recursion_kernel<2><<<grid, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets, input_lengths, target_lengths, B, T, L_max, blank, first_role, G, A, Bw, ws_offsets, G_cap, NLL); \
+        else                                                                                                    \
+            ctc_recursion_kernel<4><<<grid, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets, input_lengths, target_lengths, B, T, L_max, blank, first_role, G, A, Bw, ws_offsets, G_cap, NLL); \
+    } while (0)
 
 #define CTC_COMMON_CHECKS()                                                                       \
     CAB_CHECK_ARG(log_probs && targets && input_lengths && target_lengths, "null pointer argument"); \
@@ -611,9 +645,7 @@ extern "C" int cab_ctc_loss_fwd(const float* log_probs, int64_t stride_t, int64_
     int G = 0;
     size_t rec_smem = 0;
     CAB_CHECK_ARG(ctc_rec_config(S_max, &G, &rec_smem) == 0, "target too long for the staged recursion: L_max=%d", L_max);
-    ctc_recursion_kernel<<<B * roles, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                                   input_lengths, target_lengths, B, T, L_max, blank,
-                                                                   0, G, ws_alpha, ws_beta, ws_offsets, G_cap, nll);
+    CAB_LAUNCH_CTC_REC(B * roles, 0, ws_alpha, ws_beta, nll);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -633,9 +665,7 @@ extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_
         int G = 0;
         size_t rec_smem = 0;
         CAB_CHECK_ARG(ctc_rec_config(S_max, &G, &rec_smem) == 0, "target too long for the staged recursion: L_max=%d", L_max);
-        ctc_recursion_kernel<<<B, threads, rec_smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                               input_lengths, target_lengths, B, T, L_max, blank, 1, G,
-                                                               nullptr, ws_beta, ws_offsets, G_cap, nullptr);
+        CAB_LAUNCH_CTC_REC(B, 1, (float*)nullptr, ws_beta, (float*)nullptr);
         CAB_CHECK_LAUNCH();
         ++n_launch;
     }
