@@ -703,6 +703,7 @@ def distributed_data_parallel_and_autocast(model, local_rank, optimizer = None, 
 		model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
 	if opt_level not in (None, '', 'O0'):
 		master_module(model).set_precision('bf16')
-	model = nn.parallel.DistributedDataParallel(model, device_ids = [local_rank], output_device = local_rank)
+	on_cuda = next(model.parameters()).is_cuda
+	model = nn.parallel.DistributedDataParallel(model, device_ids = [local_rank], output_device = local_rank) if on_cuda else nn.parallel.DistributedDataParallel(model)
 	model.train(training)
 	return model, optimizer

@@ -1,0 +1,83 @@
+"""N > 1 host logic on CPU: world_size 2, gloo backend, 127.0.0.1 rendezvous."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from convasr_b200 import parallel
+
+
+def _free_port():
+	s = socket.socket()
+	s.bind(('127.0.0.1', 0))
+	port = s.getsockname()[1]
+	s.close()
+	return port
+
+
+def test_shard_bounds_partition():
+	for n in (0, 1, 7, 8, 8192, 8191):
+		for world in (1, 2, 4, 8):
+			ranges = [parallel.shard_bounds(n, r, world) for r in range(world)]
+			assert ranges[0][0] == 0 and ranges[-1][1] == n
+			assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+			sizes = [hi - lo for lo, hi in ranges]
+			assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_by_length_balances_audio():
+	g = torch.Generator().manual_seed(0)
+	lengths = (torch.rand(1001, generator = g) * 0.5 + 0.5).tolist()
+	shards = parallel.shard_by_length(lengths, 8)
+	assert sorted(i for s in shards for i in s) == list(range(1001))
+	audio = [sum(lengths[i] for i in s) for s in shards]
+	assert (max(audio) - min(audio)) / max(audio) < 0.02
+	for s in shards:  # sorted by length inside a shard: little padding per micro-batch
+		assert all(lengths[a] >= lengths[b] for a, b in zip(s, s[1:]))
+
+
+def _worker(rank, world, port, tmp):
+	os.environ.update(RANK = str(rank), WORLD_SIZE = str(world), LOCAL_RANK = str(rank), MASTER_ADDR = '127.0.0.1', MASTER_PORT = str(port))
+	r, w, lr = parallel.init_from_env(device = 'cpu')
+	assert (r, w) == (rank, world) and dist.get_backend() == 'gloo'
+	# (1) utterance sharding + ordered gather of variable-length host results
+	n = 11
+	lo, hi = parallel.shard_bounds(n, rank, world)
+	local = [[i] * (i % 4 + 1) for i in range(lo, hi)]
+	full = parallel.gather_in_order(local, list(range(lo, hi)))
+	assert full == [[i] * (i % 4 + 1) for i in range(n)]
+	# (2) timing reduction used by bench.py: max over ranks
+	assert parallel.max_over_ranks(1.0 + rank, device = 'cpu') == float(world)
+	assert parallel.sum_over_ranks(1.0, device = 'cpu') == float(world)
+	# (3) DDP gradient all-reduce through the drop-in wrapper (models.py:755-765) on the module tree's
+	#     differentiable path: after backward every rank holds the mean of the per-rank gradients
+	from convasr_b200 import models
+	torch.manual_seed(0)
+	block = models.ConvBn1d(num_channels = (4, 6), kernel_size = 3, repeat = 2, nonlinearity = ('hardtanh', 0, 20))
+	ref_block = models.ConvBn1d(num_channels = (4, 6), kernel_size = 3, repeat = 2, nonlinearity = ('hardtanh', 0, 20))
+	ref_block.load_state_dict(block.state_dict())
+	ddp, _ = models.distributed_data_parallel_and_autocast(block, rank)
+	xs = [torch.randn(3, 4, 20, generator = torch.Generator().manual_seed(10 + k)) for k in range(world)]
+	ddp(xs[rank], lengths_fraction = torch.tensor([1.0, 0.5, 0.8])).pow(2).mean().backward()
+	expect = None
+	for k in range(world):
+		ref_block.zero_grad()
+		ref_block.train()
+		ref_block(xs[k], lengths_fraction = torch.tensor([1.0, 0.5, 0.8])).pow(2).mean().backward()
+		g = [p.grad.clone() for p in ref_block.parameters()]
+		expect = g if expect is None else [a + b for a, b in zip(expect, g)]
+		# undo the running-stat update so every replica starts from the same BN state
+		ref_block.load_state_dict(block.state_dict(), strict = False)
+	for p, e in zip(models.master_module(ddp).parameters(), expect):
+		assert torch.allclose(p.grad, e / world, atol = 1e-5)
+	dist.barrier()
+	dist.destroy_process_group()
+	open(os.path.join(tmp, f'ok{rank}'), 'w').write('ok')
+
+
+def test_world_size_2_gloo(tmp_path):
+	port = _free_port()
+	mp.spawn(_worker, args = (2, port, str(tmp_path)), nprocs = 2, join = True)
+	assert sorted(os.listdir(tmp_path)) == ['ok0', 'ok1']
