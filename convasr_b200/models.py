@@ -404,8 +404,12 @@ class JasperNet(nn.Module):
 		if self.training:
 			if self.frontend is not None:
 				x = self.frontend(x, xlen = xlen)
-			logits = self._forward_training(x, xlen)
-			log_probs = [ops.log_softmax_dim1(l) for l in logits]
+			from . import training
+			if getattr(self, 'native_training', True) and training.supported(self):
+				logits, log_probs = training.forward_training(self, x, xlen)  # conv/BN forward + backward on this repo's kernels
+			else:
+				logits = self._forward_training(x, xlen)
+				log_probs = [ops.log_softmax_dim1(l) for l in logits]
 		else:
 			logits, log_probs = self._forward_native(x, xlen)
 		olen = [compute_output_lengths(l, xlen) for l in logits]

@@ -148,6 +148,21 @@ def conv1d_fused(
 	_lib.check(rc, 'cab_conv1d_fused')
 
 
+def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0):
+	"""out[tap, m, n] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dilation - pad_left, n]  (fp32 [taps, M, N_ld])"""
+	_need_cuda(a, bx)
+	assert a.dtype == BF16 and bx.dtype == BF16 and a.is_contiguous() and bx.is_contiguous()
+	B = a.shape[0]
+	out_ld = (N_total + 3) // 4 * 4
+	out = torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
+	rc = _lib.load().cab_conv1d_wgrad(
+		_p(a), a_T, a.shape[1], a.shape[2], M_total, _p(bx), b_T, bx.shape[1], bx.shape[2], N_total, B, taps, dilation, pad_left,
+		_p(out), out_ld, n_splits, _stream()
+	)
+	_lib.check(rc, 'cab_conv1d_wgrad')
+	return out  # [taps, M_total, ld >= N_total]; columns past N_total are padding
+
+
 def grouped_conv1d_relu(act, T, C_in, wgt, bias, groups, pad_left, ld_out = None, act_lo = None, want_lo = False):
 	_need_cuda(act, act_lo, wgt, bias)
 	B, T_rows, ld_in = act.shape

@@ -125,6 +125,47 @@ typedef struct {
 int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
                      const cab_conv_epilogue_t* epilogue_host, cab_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training: Conv1d weight gradient (autograd's wgrad behind loss.backward(), train.py:770-774)
+ *   out[tap][m][n] = sum_{b,t} a[b, t, m] * bx[b, t + tap*dilation - pad_left, n]
+ *   a: bf16 [B, a_T_rows, a_ld] (gradient w.r.t. the conv output), bx: bf16 [B, b_T_rows, b_ld]
+ *   (conv input) -- or swapped by the caller, whichever side should be the 128-row M side.
+ *   out: fp32 [taps, M_total, out_ld].  n_splits = 0 picks a batch split for >= 4 waves;
+ *   with n_splits > 1 partial sums are reduced in L2 (the call zeroes `out` first).
+ * ------------------------------------------------------------------------------------- */
+int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total, const void* bx,
+                     int b_T, int b_T_rows, int b_ld, int N_total, int B, int taps, int dilation,
+                     int pad_left, float* out, int out_ld, int n_splits, cab_stream_t stream);
+
+/* Training-mode BatchNorm1d + activation + temporal mask around the conv GEMMs
+ * (nn.BatchNorm1d(momentum, eps) inside ConvBn1d.forward, models.py:112-113,127-139):
+ *   cab_bn_batch_stats : biased batch statistics over all B*T rows of y (bf16 [B,T,ld]); writes
+ *                        out_ss = [scale, shift, mean, invstd] (fp32 [4][C]) and updates the running
+ *                        statistics (unbiased running_var) when the pointers are non-NULL.
+ *   cab_bn_act_mask_fwd: out = act(y*scale + shift) * (t < ceil(frac*T))
+ *   cab_bn_act_mask_bwd: given grad_out w.r.t. `out`: sums = [dbeta, dgamma] (fp32 [2][C]) and
+ *                        grad_y = scale * (dz - mean(dz) - xhat * mean(dz*xhat)),
+ *                        dz = grad_out * act'(z) * mask  (hardtanh: a < z < b strictly). */
+int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta,
+                       float eps, float momentum, float* running_mean, float* running_var,
+                       float* ws_sums, float* out_ss, cab_stream_t stream);
+int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a,
+                        float act_b, const float* xlen_frac, void* out, cab_stream_t stream);
+int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld,
+                        int act, float act_a, float act_b, const float* xlen_frac, float* sums,
+                        void* grad_y, cab_stream_t stream);
+/* fp32 [Co,Ci,K] -> bf16 tap-major [K,Co,ci_ld] (forward operand) and/or [K,Ci,co_ld] with flipped
+ * taps (dgrad operand); and the inverse for a packed fp32 gradient ([K,Co,ld] or, transposed,
+ * [K,Ci,ld]) into the parameter layout. */
+int cab_pack_weight(const float* w, int Co, int Ci, int K, void* fwd, int ci_ld, void* dgrad, int co_ld,
+                    cab_stream_t stream);
+int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad,
+                     int accumulate, cab_stream_t stream);
+/* fp32 [B,C,T] (gradient w.r.t. the logits) -> bf16 channels-last [B,T,ld]; class_sums (fp32 [C],
+ * optional) receives the sums over (b,t) = the decoder bias gradient. */
+int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, float* class_sums,
+                   cab_stream_t stream);
+
 /* grouped Conv1d + bias + ReLU of the separable blocks (models.py:50-64): bf16 channels-last
  * in [B, T_rows, ld_in] / out [B, out_T_rows, ld_out] (channels C_out..ld_out-1 are zeroed),
  * weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1.

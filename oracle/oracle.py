@@ -167,10 +167,14 @@ def _activation(y, act):
 	raise ValueError(act)
 
 
-def _bn_eval(y, sd, prefix, eps = 1e-5):
-	"""nn.BatchNorm1d in eval mode (models.py:112-113); absent keys = already fused (Identity)."""
+def _bn_eval(y, sd, prefix, eps = 1e-5, training = False):
+	"""nn.BatchNorm1d (models.py:112-113): eval mode uses the running statistics; training mode the
+	biased batch statistics over all B*t positions (padded frames included -- the mask comes after the
+	activation, models.py:135-138).  Absent keys = already fused (Identity)."""
 	if prefix + '.running_mean' not in sd:
 		return y
+	if training:
+		return F.batch_norm(y, None, None, sd[prefix + '.weight'], sd[prefix + '.bias'], True, 0.1, eps)
 	g, b = sd[prefix + '.weight'], sd[prefix + '.bias']
 	m, v = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
 	return (y - m[None, :, None]) / torch.sqrt(v[None, :, None] + eps) * g[None, :, None] + b[None, :, None]
@@ -183,7 +187,7 @@ def _count(sd, fmt):
 	return n
 
 
-def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32):
+def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False):
 	"""JasperNet.forward models.py:303-317 (backbone, decoder, log_softmax) in eval mode.
 
 	x: normalised features [B, C, F].  Returns (logits list, log_probs list, olen list)."""
@@ -206,14 +210,14 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 				y = F.conv1d(y.relu(), sd[p + '.2.weight'], sd.get(p + '.2.bias'))
 			else:
 				y = F.conv1d(x, w, sd.get(p + '.0.bias'), stride = stride, padding = pad, dilation = dil)
-			y = _bn_eval(y, sd, f'backbone.{i}.bn.{j}')
+			y = _bn_eval(y, sd, f'backbone.{i}.bn.{j}', training = training)
 			if j == reps - 1:  # residuals join on the last repeat only (models.py:129-133)
 				assert n_res == len(res) or not residual
 				for r, rx in enumerate(res[:n_res] if residual else []):
 					pr = f'backbone.{i}.conv_residual.{r}'
 					if pr + '.weight' in sd:
 						ry = F.conv1d(rx, sd[pr + '.weight'], sd.get(pr + '.bias'))
-						ry = _bn_eval(ry, sd, f'backbone.{i}.bn_residual.{r}')
+						ry = _bn_eval(ry, sd, f'backbone.{i}.bn_residual.{r}', training = training)
 					else:  # 'flat' residual: Identity (models.py:117,121)
 						ry = rx
 					y = y + ry

@@ -233,11 +233,36 @@ def probe_ctc():
 	return ok
 
 
+def probe_wgrad():
+	ok = True
+	g = torch.Generator().manual_seed(0)
+	for (B, T_in, Ci, Co, k, dil, pad, splits) in [(2, 200, 64, 128, 1, 1, 0, 1), (3, 333, 256, 256, 11, 1, 5, 0), (2, 751, 768, 896, 29, 2, 29, 0), (4, 300, 128, 384, 3, 1, 1, 3), (2, 150, 1024, 38, 1, 1, 0, 0)]:
+		x = torch.randn(B, Ci, T_in, generator = g).to(dev).to(torch.bfloat16)
+		w = torch.zeros(Co, Ci, k, device = dev, requires_grad = True)
+		y = F.conv1d(x.float(), w, None, padding = pad, dilation = dil)
+		dy = torch.randn(y.shape, generator = g).to(dev).to(torch.bfloat16)
+		y.backward(dy.float())
+		ref = w.grad  # [Co, Ci, k]
+		T_out = y.shape[-1]
+		co_ld, ci_ld = (Co + 63) // 64 * 64, (Ci + 63) // 64 * 64
+		a = torch.zeros(B, T_out, co_ld, dtype = torch.bfloat16, device = dev); a[:, :, :Co] = dy.permute(0, 2, 1)
+		bx = torch.zeros(B, T_in, ci_ld, dtype = torch.bfloat16, device = dev); bx[:, :, :Ci] = x.permute(0, 2, 1)
+		if Co >= Ci or Co >= 128:
+			out = ops.conv1d_wgrad(a, T_out, Co, bx, T_in, Ci, k, dil, pad, n_splits = splits)
+			got = out[:, :, :Ci].permute(1, 2, 0)
+		else:  # swapped: wide side on M; shift applies to the B operand (here dy) with the opposite sign
+			out = ops.conv1d_wgrad(bx, T_in, Ci, a, T_out, Co, k, dil, -pad + 0, n_splits = splits) if k == 1 else None
+			got = out[:, :, :Co].permute(2, 1, 0)
+		torch.cuda.synchronize()
+		ok &= report(f'wgrad B{B} T{T_in} {Ci}->{Co} k{k} d{dil} splits={splits}', got, ref, 2e-3)
+	return ok
+
+
 if __name__ == '__main__':
 	what = sys.argv[1] if len(sys.argv) > 1 else 'all'
 	print('device', torch.cuda.get_device_name(0), 'lib', _lib.lib_path(), flush = True)
 	res = {}
-	for name, fn in [('conv', probe_conv), ('frontend', probe_frontend), ('ctc', probe_ctc)]:
+	for name, fn in [('conv', probe_conv), ('frontend', probe_frontend), ('ctc', probe_ctc), ('wgrad', probe_wgrad)]:
 		if what in (name, 'all'):
 			try:
 				res[name] = fn()
