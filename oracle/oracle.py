@@ -187,12 +187,21 @@ def _count(sd, fmt):
 	return n
 
 
-def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False):
+def _round_bf16(t):
+	"""bf16 rounding with a straight-through gradient: emulates bf16 storage of a tensor"""
+	return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False, round_bf16 = False):
 	"""JasperNet.forward models.py:303-317 (backbone, decoder, log_softmax) in eval mode.
 
 	x: normalised features [B, C, F].  Returns (logits list, log_probs list, olen list)."""
 	sd = {k: v.to(dtype) if v.is_floating_point() else v for k, v in sd.items()}
 	x = x.to(dtype)
+	# round_bf16: the reference under bf16 mixed precision (apex O2 / autocast): conv operands and conv
+	# outputs live in bf16, BatchNorm arithmetic and accumulation in fp32
+	rb = _round_bf16 if round_bf16 else (lambda t: t)
+	x = rb(x)
 	n_blocks = _count(sd, 'backbone.{}.')
 	res = []
 	for i in range(n_blocks):
@@ -209,7 +218,7 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 				y = F.conv1d(x, w, sd.get(p + '.0.bias'), stride = stride, padding = pad, dilation = dil, groups = groups)
 				y = F.conv1d(y.relu(), sd[p + '.2.weight'], sd.get(p + '.2.bias'))
 			else:
-				y = F.conv1d(x, w, sd.get(p + '.0.bias'), stride = stride, padding = pad, dilation = dil)
+				y = rb(F.conv1d(x, rb(w), sd.get(p + '.0.bias'), stride = stride, padding = pad, dilation = dil))
 			y = _bn_eval(y, sd, f'backbone.{i}.bn.{j}', training = training)
 			if j == reps - 1:  # residuals join on the last repeat only (models.py:129-133)
 				assert n_res == len(res) or not residual
@@ -224,6 +233,7 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 			x = _activation(y, act)
 			if mask and xlen is not None:  # models.py:136-138
 				x = x * temporal_mask(x.shape[-1], output_lengths(x.shape[-1], xlen))
+			x = rb(x)
 		# residual bookkeeping, models.py:306-313
 		if i >= n_blocks - num_epilogue - 1:
 			res = []
@@ -233,7 +243,7 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 			res = [x]
 		else:
 			res = []
-	logits = [F.conv1d(x, sd['decoder.0.weight'], sd['decoder.0.bias'])]  # models.py:26
+	logits = [F.conv1d(x, rb(sd['decoder.0.weight']), sd['decoder.0.bias'])]  # models.py:26
 	log_probs = [F.log_softmax(l, dim = 1).to(torch.float32) for l in logits]  # :316
 	olen = [output_lengths(l.shape[-1], xlen) if xlen is not None else torch.full((len(l), ), l.shape[-1], dtype = torch.long) for l in logits]  # :317
 	return logits, log_probs, olen
