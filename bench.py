@@ -2,18 +2,23 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
 
-Workload (BASELINE.json configs[1] shape): Wav2Letter-char (66.5 M params, 38 classes), batch
-80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16 tier.  One step = one pass of the
-hot path over one batch: log-mel frontend -> instance norm -> 19 fused conv launches -> decoder +
-log_softmax + argmax -> CTC loss (alpha) -> CTC gradient w.r.t. the logits (beta + scatter).
-The conv-stack backward (dgrad/wgrad) is NOT part of the step (not native yet).
+Default workload = BASELINE.json configs[1]: Wav2Letter-char (66.5 M params, 38 classes) TRAINING
+STEP, batch 80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16.  One step = log-mel
+frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + mask layers -> decoder
++ log_softmax -> CTC loss -> backward through everything (CTC gradient, log_softmax, decoder, BN,
+dgrad and wgrad of every conv) -> SGD(momentum) update.  Everything except the optimizer update
+(torch.optim.SGD, section 8f "next" #3) runs on this repo's kernels.  N > 1: DistributedDataParallel
+gradient all-reduce over NCCL.
+
+Secondary workload (reported under "also", selectable with --workload): the inference path of the
+same shape -- eval-mode forward with folded BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
 
 value  = whole-job audio-seconds / second with the PCM already resident in HBM (CUDA events).
-e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM -> H2D,
-         model(x, xlen, y, ylen), D2H of the per-utterance loss and the greedy ids.
-N > 1  = utterance-sharded replicas (weak scaling, no data-path collective); time = max over ranks.
---impl reference = the CPU oracle port of the reference path (torch CPU ops, all host threads)
-         on a bounded sample of the same workload.
+e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM + targets
+         -> H2D, the step, D2H of the per-utterance loss (and the greedy ids for inference).
+N > 1  = per-GPU batch fixed (weak scaling); time = max over ranks.
+--impl reference = the CPU oracle port of the reference path (torch CPU ops, all host threads) on a
+         bounded sample of the same workload.
 """
 import argparse
 import json
@@ -30,12 +35,18 @@ if ROOT not in sys.path:
 import torch
 
 WORKLOADS = {
-	# name: (model, num_classes, batch, seconds, precision)
-	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16'),
-	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32'),
-	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16'),
+	# name: (model, num_classes, batch, seconds, precision, kind)
+	'wav2letter_char_train_step_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'train'),
+	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer'),
+	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer'),
+	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer'),
 }
-DEFAULT_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'
+DEFAULT_WORKLOAD = 'wav2letter_char_train_step_B80x15s_bf16'
+SECONDARY_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'
+STEP_DESC = {
+	'train': 'frontend+instnorm+18x(conv, batch-stat BN, hardtanh, mask)+decoder/log_softmax+CTC loss+full backward (CTC grad, BN bwd, dgrad, wgrad)+SGD update',
+	'infer': 'frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)',
+}
 SAMPLE_RATE = 8000
 
 
@@ -128,8 +139,18 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path (oracle/ is the checker AND the CPU baseline)
 # --------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C):
+def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind):
 	from oracle import oracle as O
+	if kind == 'train':
+		leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
+		logits, log_probs, olen = O.model_forward(leaf, sig, xlen, model = model_name, training = True)
+		loss = O.ctc_loss_torch(log_probs[0].permute(2, 0, 1), y[:, 0], olen[0], ylen[:, 0], C - 1).mean()
+		loss.backward()  # backward through the whole stack, as train.py:770-774
+		with torch.no_grad():
+			for k, v in leaf.items():
+				if v.is_floating_point() and v.grad is not None:
+					sd[k] = sd[k] - 1e-6 * v.grad  # plain SGD update
+		return loss
 	logits, log_probs, olen = O.model_forward(sd, sig, xlen, model = model_name)
 	lp = log_probs[0].permute(2, 0, 1).detach().requires_grad_(True)
 	loss = O.ctc_loss_torch(lp, y[:, 0], olen[0], ylen[:, 0], C - 1)
@@ -137,102 +158,98 @@ def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C):
 	return loss
 
 
-def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup):
+def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup, kind):
 	from oracle import oracle as O
 	torch.set_num_threads(os.cpu_count())
 	shapes = {k: s for k, s in model_shapes(model_name, C).items() if not k.startswith('frontend.')}
 	sd = O.synth_state_dict(shapes, seed = 0)
 	sig, xlen, y, ylen = synth_batch(sample_B, seconds, C, seed = 0)
-	with torch.no_grad():
-		pass
 	for _ in range(warmup):
-		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C)
+		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind)
 	t0 = time.perf_counter()
 	for _ in range(steps):
-		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C)
+		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind)
 	dt = time.perf_counter() - t0
 	return sample_B * seconds * steps / dt, dt / steps
 
 
-def main():
-	ap = argparse.ArgumentParser()
-	ap.add_argument('--gpus', type = int, default = 1)
-	ap.add_argument('--steps', type = int, default = 50)
-	ap.add_argument('--warmup', type = int, default = 5)
-	ap.add_argument('--impl', default = 'native', choices = ['native', 'reference'])
-	ap.add_argument('--workload', default = DEFAULT_WORKLOAD, choices = sorted(WORKLOADS))
-	ap.add_argument('--no-cpu-baseline', action = 'store_true')
-	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
-	ap.add_argument('--no-cuda-graphs', action = 'store_true')
-	args = ap.parse_args()
-	model_name, C, B, seconds, precision = WORKLOADS[args.workload]
-	rank = int(os.environ.get('RANK', 0))
-	world = int(os.environ.get('WORLD_SIZE', 1))
-	local_rank = int(os.environ.get('LOCAL_RANK', 0))
-	steps, warmup = args.steps, max(args.warmup, 3)
-	config = dict(workload = args.workload, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision,
-				step = 'frontend+instnorm+conv stack+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)', parallelism = f'utterance-sharded replicas x{world}', l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
-
-	if args.impl == 'reference':
-		if rank != 0:
-			return
-		sB = args.cpu_sample_batch
-		n_steps = max(1, min(steps, 3))
-		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1)
-		line = dict(
-			impl = 'reference', metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = args.gpus, steps = n_steps, warmup = 1, ms_per_step = sec * 1e3,
-			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config,
-			cpu_baseline = dict(value = value, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, {n_steps} steps (oracle port: torch {torch.__version__} CPU ops)'),
-			e2e = dict(value = value, unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0), gpu_launches = 0
-		)
-		print(json.dumps(line))
-		return
-
-	# ------------------------------------------------------------------ native arm
-	assert torch.cuda.is_available(), 'bench.py --impl native needs a CUDA device'
-	torch.cuda.set_device(local_rank)
-	dev = torch.device('cuda', local_rank)
-	if world > 1:
-		import torch.distributed as dist
-		dist.init_process_group('nccl', device_id = dev)
-	from convasr_b200 import _lib, engine, models, ops
+def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline, full):
+	"""one workload on this rank's GPU; `full` adds roofline / e2e / clocks (primary line)"""
+	from convasr_b200 import _lib, models, ops
 	from oracle import oracle as O  # only for the seeded synthetic weights + the cpu_baseline leg
-
+	model_name, C, B, seconds, precision, kind = WORKLOADS[name]
+	config = dict(workload = name, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
+				step = STEP_DESC[kind], parallelism = (f'DDP x{world} (NCCL gradient all-reduce)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
+				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = kind == 'infer' and not args.no_cuda_graphs)
 	cpu_baseline = None
-	if rank == 0 and world == 1 and not args.no_cpu_baseline:
-		v, sec = run_cpu_baseline(model_name, C, seconds, args.cpu_sample_batch, 3, 1)
-		cpu_baseline = dict(value = v, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{args.cpu_sample_batch} x {seconds:g} s utterances per step, 3 steps after 1 warm-up ({sec:.2f} s/step; oracle port: torch {torch.__version__} CPU ops)')
+	if with_cpu_baseline:
+		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
+		v, sec = run_cpu_baseline(model_name, C, seconds, sB, 3, 1, kind)
+		cpu_baseline = dict(value = v, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, 3 steps after 1 warm-up ({sec:.2f} s/step; oracle port: torch {torch.__version__} CPU ops, {kind} step)')
 
 	frontend = models.LogFilterBankFrontend(64, SAMPLE_RATE, .02, .01, 'hann_window')
 	model = getattr(models, model_name)(64, [C], frontend = frontend, dropout = 0., check_time_dim_padded = False)
 	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
 	model.load_state_dict(O.synth_state_dict(shapes, seed = 0), strict = False)
-	model = model.to(dev).eval().set_precision(precision)
+	model = model.to(dev)
 	sig, xlen, y, ylen = synth_batch(B, seconds, C, seed = 1000 + rank)
 	sig_pin, xlen_pin, y_pin, ylen_pin = [t.pin_memory() for t in (sig, xlen, y, ylen)]
 	sig_d, xlen_d, y_d, ylen_d = [t.to(dev) for t in (sig, xlen, y, ylen)]
 	flush = torch.empty(256 << 20, dtype = torch.uint8, device = dev)
-	F = sig.shape[1] // 80 + 1
-	flops, t_out = conv_flops_per_step(model, B, F)
+	Fr = sig.shape[1] // 80 + 1
+	flops_fwd, t_out = conv_flops_per_step(model, B, Fr)
+	first = model.backbone[0].conv[0][0]
+	flops_first = 2 * B * ((Fr + 2 * first.padding[0] - first.kernel_size[0]) // first.stride[0] + 1) * first.out_channels * first.in_channels * first.kernel_size[0]
 
-	def step_device():
-		# grad w.r.t. the log-probs/logits only: CTC alpha -> beta -> gradient scatter
-		with torch.no_grad():
-			out = model(sig_d, xlen_d)
-		lp = out['log_probs'][0].requires_grad_(True)
-		nll = ops.ctc_loss(lp.permute(2, 0, 1), y_d[:, 0], out['olen'][0], ylen_d[:, 0], blank = C - 1)
-		nll.sum().backward()
-		return nll, lp
+	if kind == 'train':
+		from convasr_b200 import training
+		model.train()
+		assert training.supported(model), 'native training path does not cover this topology'
+		net = model
+		if world > 1:
+			net, _ = models.distributed_data_parallel_and_autocast(model, local_rank)
+		optimizer = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr = 1e-6, momentum = 0.9)
+		flops = 3 * flops_fwd - flops_first  # forward + dgrad (all but the first layer) + wgrad
 
-	def step_e2e():
-		s = sig_pin.to(dev, non_blocking = True)
-		xl = xlen_pin.to(dev, non_blocking = True)
-		yy = y_pin.to(dev, non_blocking = True)
-		yl = ylen_pin.to(dev, non_blocking = True)
-		out = model(s, xl, y = yy, ylen = yl)
-		loss_h = out['loss'].cpu()
-		ids_h = out['log_probs'][0]._convasr_argmax.cpu()
-		return loss_h, ids_h
+		def run(s, xl, yy, yl):
+			optimizer.zero_grad(set_to_none = True)
+			out = net(s, xl, y = yy, ylen = yl)
+			loss = (out['loss'] * yl[:, 0]).mean()  # train.py:754-755
+			loss.backward()
+			optimizer.step()
+			return out['loss']
+
+		def step_device():
+			return run(sig_d, xlen_d, y_d, ylen_d)
+
+		def step_e2e():
+			per_utt = run(*[t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)])
+			return per_utt.detach().cpu()
+
+		d2h = B * 4
+		traced_names = ['conv1d_fused', 'conv1d_wgrad']
+		kernel_label = 'conv1d_umma_kernel (forward + dgrad) + wgrad_umma_kernel'
+	else:
+		model.eval().set_precision(precision)
+		flops = flops_fwd
+
+		def step_device():
+			# grad w.r.t. the log-probs/logits only: CTC alpha || beta -> gradient scatter
+			with torch.no_grad():
+				out = model(sig_d, xlen_d)
+			lp = out['log_probs'][0].requires_grad_(True)
+			nll = ops.ctc_loss(lp.permute(2, 0, 1), y_d[:, 0], out['olen'][0], ylen_d[:, 0], blank = C - 1)
+			nll.sum().backward()
+			return nll
+
+		def step_e2e():
+			s, xl, yy, yl = [t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)]
+			out = model(s, xl, y = yy, ylen = yl)
+			return out['loss'].cpu(), out['log_probs'][0]._convasr_argmax.cpu()
+
+		d2h = B * 4 + B * t_out * 4
+		traced_names = ['conv1d_fused']
+		kernel_label = 'conv1d_umma_kernel'
 
 	def barrier():
 		if world > 1:
@@ -258,83 +275,140 @@ def main():
 	step_device()
 	torch.cuda.synchronize()
 	launches_per_step = _lib.launch_count() - l0
-	if not args.no_cuda_graphs:
+	if config['cuda_graphs']:
 		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
 	for _ in range(warmup):
-		nll, _ = step_device()
+		nll = step_device()
 	torch.cuda.synchronize()
 	assert bool(torch.isfinite(nll).all()), 'synthetic targets must admit an alignment'
 	sampler = ClockSampler(local_rank)
-	if rank == 0:
+	if rank == 0 and full:
 		sampler.start()
 	barrier()
 	t_wall0 = time.time()
 	ms = timed(step_device, steps)
 	barrier()
 	t_wall1 = time.time()
-	launches = launches_per_step * steps
-	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 and full else None
+	result = dict(ms = ms, ms_e2e = None)
+	roofline = None
+	if full:
+		# dominant (tensor-pipe) kernels: per-launch CUDA events on the launching stream
+		events = []
+		originals = {n: getattr(ops, n) for n in traced_names}
 
-	# dominant kernel (conv1d_umma_kernel): per-launch CUDA events on the launching stream
-	conv_events = []
-	orig = ops.conv1d_fused
+		def make_traced(fn):
+			def traced(*a, **k):
+				e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+				e0.record()
+				r = fn(*a, **k)
+				e1.record()
+				events.append((e0, e1))
+				return r
+			return traced
 
-	def traced(*a, **k):
-		e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
-		e0.record()
-		orig(*a, **k)
-		e1.record()
-		conv_events.append((e0, e1))
+		for n_, fn in originals.items():
+			setattr(ops, n_, make_traced(fn))
+		model.enable_cuda_graphs(False)  # per-launch events need the eager launch path
+		n_prof = min(steps, 5)
+		for _ in range(n_prof):
+			flush.zero_()
+			step_device()
+		torch.cuda.synchronize()
+		for n_, fn in originals.items():
+			setattr(ops, n_, fn)
+		if config['cuda_graphs']:
+			model.enable_cuda_graphs(True)
+		kern_ms = sum(a.elapsed_time(b) for a, b in events) / n_prof
+		n_kern = len(events) // n_prof
+		# end to end through the public API with host buffers
+		for _ in range(3):
+			step_e2e()
+		barrier()
+		result['ms_e2e'] = timed(step_e2e, steps)
+		barrier()
+		peaks = measured_peaks()
+		peak = peaks['bf16_tflops_sustained'] if peaks else 1590.0
+		achieved = flops / (kern_ms / 1e3) / 1e12
+		roofline = dict(
+			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
+			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
+			peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = None, launches_per_step = n_kern, kernel_ms_per_step = kern_ms,
+			algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1, share_of_step = kern_ms / (ms / steps)
+		)
+	result.update(config = config, cpu_baseline = cpu_baseline, clocks = clocks, roofline = roofline, launches = launches_per_step * steps, B = B, seconds = seconds, precision = precision,
+					h2d = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen)), d2h = d2h)
+	del model, flush
+	torch.cuda.empty_cache()
+	return result
 
-	ops.conv1d_fused = traced
-	model.enable_cuda_graphs(False)  # per-launch events need the eager launch path
-	n_prof = min(steps, 5)
-	for _ in range(n_prof):
-		flush.zero_()
-		step_device()
-	torch.cuda.synchronize()
-	ops.conv1d_fused = orig
-	if not args.no_cuda_graphs:
-		model.enable_cuda_graphs(True)
-	conv_ms = sum(a.elapsed_time(b) for a, b in conv_events) / n_prof
-	n_conv = len(conv_events) // n_prof
 
-	# end to end through the public API with host buffers
-	for _ in range(3):
-		step_e2e()
-	barrier()
-	ms_e2e = timed(step_e2e, steps)
-	barrier()
+def main():
+	ap = argparse.ArgumentParser()
+	ap.add_argument('--gpus', type = int, default = 1)
+	ap.add_argument('--steps', type = int, default = 30)
+	ap.add_argument('--warmup', type = int, default = 5)
+	ap.add_argument('--impl', default = 'native', choices = ['native', 'reference'])
+	ap.add_argument('--workload', default = DEFAULT_WORKLOAD, choices = sorted(WORKLOADS))
+	ap.add_argument('--no-cpu-baseline', action = 'store_true')
+	ap.add_argument('--no-secondary', action = 'store_true')
+	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
+	ap.add_argument('--no-cuda-graphs', action = 'store_true')
+	args = ap.parse_args()
+	model_name, C, B, seconds, precision, kind = WORKLOADS[args.workload]
+	rank = int(os.environ.get('RANK', 0))
+	world = int(os.environ.get('WORLD_SIZE', 1))
+	local_rank = int(os.environ.get('LOCAL_RANK', 0))
+	steps, warmup = args.steps, max(args.warmup, 3)
 
-	if world > 1:
-		t = torch.tensor([ms, ms_e2e], device = dev, dtype = torch.float64)
-		torch.distributed.all_reduce(t, op = torch.distributed.ReduceOp.MAX)
-		ms, ms_e2e = t.tolist()
-	if rank != 0:
-		if world > 1:
-			torch.distributed.destroy_process_group()
+	if args.impl == 'reference':
+		if rank != 0:
+			return
+		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
+		n_steps = max(1, min(steps, 3))
+		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1, kind)
+		config = dict(workload = args.workload, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = 'fp32', kind = kind, step = STEP_DESC[kind])
+		line = dict(
+			impl = 'reference', metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = args.gpus, steps = n_steps, warmup = 1, ms_per_step = sec * 1e3,
+			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config,
+			cpu_baseline = dict(value = value, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, {n_steps} steps (oracle port: torch {torch.__version__} CPU ops, {kind} step)'),
+			e2e = dict(value = value, unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0), gpu_launches = 0
+		)
+		print(json.dumps(line))
 		return
 
-	audio_s = B * seconds * world
-	value = audio_s * steps / (ms / 1e3)
-	e2e_value = audio_s * steps / (ms_e2e / 1e3)
-	peaks = measured_peaks()
-	peak = peaks['bf16_tflops_sustained'] if peaks else 1590.0
-	achieved = flops / (conv_ms / 1e3) / 1e12
-	passes = 3 if precision == 'fp32' else 1
-	roofline = dict(
-		bound = 'tensor', kernel = 'conv1d_umma_kernel', achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
-		peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
-		peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = None, launches_per_step = n_conv, kernel_ms_per_step = conv_ms,
-		algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = passes, share_of_step = conv_ms / (ms / steps)
-	)
-	line = dict(
-		metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = world, steps = steps, warmup = warmup, ms_per_step = ms / steps, higher_is_better = True,
-		scaling = 'weak', vs_baseline = None, dtype = 'bf16' if precision == 'bf16' else 'bf16x3 (split-bf16, fp32 accumulate)', data = 'synthetic', config = config,
-		e2e = dict(value = e2e_value, unit = 'audio-s/s', ms_per_step = ms_e2e / steps, h2d_bytes_per_step = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen)), d2h_bytes_per_step = B * 4 + B * t_out * 4),
-		gpu_launches = launches, roofline = roofline, cpu_baseline = cpu_baseline, clocks = clocks
-	)
-	print(json.dumps(line))
+	# ------------------------------------------------------------------ native arm
+	assert torch.cuda.is_available(), 'bench.py --impl native needs a CUDA device'
+	torch.cuda.set_device(local_rank)
+	dev = torch.device('cuda', local_rank)
+	if world > 1:
+		import torch.distributed as dist
+		dist.init_process_group('nccl', device_id = dev)
+
+	def reduce_max(vals):
+		if world == 1:
+			return vals
+		t = torch.tensor(vals, device = dev, dtype = torch.float64)
+		torch.distributed.all_reduce(t, op = torch.distributed.ReduceOp.MAX)
+		return t.tolist()
+
+	r = measure(args.workload, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = rank == 0 and world == 1 and not args.no_cpu_baseline, full = True)
+	ms, ms_e2e = reduce_max([r['ms'], r['ms_e2e']])
+	also = None
+	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD:
+		r2 = measure(SECONDARY_WORKLOAD, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
+		ms2, = reduce_max([r2['ms']])
+		also = {SECONDARY_WORKLOAD: dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'])}
+	if rank == 0:
+		audio_s = r['B'] * r['seconds'] * world
+		line = dict(
+			metric = 'audio_seconds_per_second', value = audio_s * steps / (ms / 1e3), unit = 'audio-s/s', n_gpus = world, steps = steps, warmup = warmup, ms_per_step = ms / steps,
+			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'bf16' if r['precision'] == 'bf16' else 'bf16x3 (split-bf16, fp32 accumulate)', data = 'synthetic',
+			config = r['config'],
+			e2e = dict(value = audio_s * steps / (ms_e2e / 1e3), unit = 'audio-s/s', ms_per_step = ms_e2e / steps, h2d_bytes_per_step = r['h2d'], d2h_bytes_per_step = r['d2h']),
+			gpu_launches = r['launches'], roofline = r['roofline'], cpu_baseline = r['cpu_baseline'], clocks = r['clocks'], also = also
+		)
+		print(json.dumps(line))
 	if world > 1:
 		torch.distributed.destroy_process_group()
 
