@@ -32,36 +32,70 @@ __device__ __forceinline__ float act_grad(float z, int act, float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------
-// per-channel sum / sum of squares of a bf16 [R, ld] matrix (R = B*t rows).
-// block (64, 4): x = channel pair, y = row lane; grid (ceil(C/128), row blocks)
+// Row-walker layout shared by the four activation-sized kernels: a thread owns ONE 16-byte channel
+// vector (8 bf16 channels) and walks down the rows, so the per-channel coefficients live in
+// registers and a warp touches 512 contiguous bytes per row.
+//   block (32, 8): x = channel vector, y = row lane;  grid (ceil(ld/8/32), ceil(R/kRowsPerBlock))
 // ---------------------------------------------------------------------------------------
 constexpr int kRowsPerBlock = 256;
+constexpr int kRowLanes = 8;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        f[2 * j] = t.x;
+        f[2 * j + 1] = t.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// reduce 2 x 8 per-thread partials over the row lanes, then one atomic per channel and statistic
+__device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8], int c0, int C, float* __restrict__ out) {
+    __shared__ float sm[kRowLanes][32][17];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sm[threadIdx.y][threadIdx.x][e] = s[e];
+        sm[threadIdx.y][threadIdx.x][8 + e] = q[e];
+    }
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float a = s[e], b = q[e];
+            for (int y = 1; y < kRowLanes; ++y) {
+                a += sm[y][threadIdx.x][e];
+                b += sm[y][threadIdx.x][8 + e];
+            }
+            if (c0 + e < C) {
+                atomicAdd(out + c0 + e, a);
+                atomicAdd(out + C + c0 + e, b);
+            }
+        }
+    }
+}
+
+// per-channel sum / sum of squares of a bf16 [R, ld] matrix (R = B*t rows)
 __global__ void __launch_bounds__(256)
 colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float* __restrict__ out) {
-    const int c = (blockIdx.x * 64 + threadIdx.x) * 2;
-    const int r0 = blockIdx.y * kRowsPerBlock;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    if (c < C) {
-        const int r1 = min(R, r0 + kRowsPerBlock);
-        for (int r = r0 + threadIdx.y; r < r1; r += 4) {
-            const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)r * ld + c));
-            s0 += v.x; s1 += v.y;
-            q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+    if (c0 < ld) {
+        const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+        for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(x + (size_t)r * ld + c0), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
         }
     }
-    __shared__ float sm[4][64][4];
-    sm[threadIdx.y][threadIdx.x][0] = s0; sm[threadIdx.y][threadIdx.x][1] = s1;
-    sm[threadIdx.y][threadIdx.x][2] = q0; sm[threadIdx.y][threadIdx.x][3] = q1;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-        for (int y = 1; y < 4; ++y) {
-            s0 += sm[y][threadIdx.x][0]; s1 += sm[y][threadIdx.x][1];
-            q0 += sm[y][threadIdx.x][2]; q1 += sm[y][threadIdx.x][3];
-        }
-        atomicAdd(out + c, s0);
-        atomicAdd(out + C + c, q0);
-        if (c + 1 < C) { atomicAdd(out + c + 1, s1); atomicAdd(out + C + c + 1, q1); }
-    }
+    reduce_rows_and_add(s, q, c0, C, out);
 }
 
 // mean / invstd / fused scale+shift, running statistics update (momentum, unbiased running_var)
@@ -83,31 +117,35 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float
     if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (n / fmaxf(n - 1.f, 1.f));
 }
 
-// out = act(y * scale + shift) * (t < len_b); 8 channels per thread
+// out = act(y * scale + shift) * (t < len_b)
 __global__ void __launch_bounds__(256)
 bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int B, int T, int C, int ld,
                        int act, float a, float bb, const float* __restrict__ xlen, __nv_bfloat16* __restrict__ out) {
-    const int vec_per_row = ld / 8;
-    const size_t n = (size_t)B * T * vec_per_row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vec_per_row);
-        const size_t row = i / vec_per_row;
-        const int t = (int)(row % T), b = (int)(row / T);
-        const int c0 = cv * 8;
-        bool keep = true;
-        if (xlen != nullptr) keep = t < frac_len(__ldg(xlen + b), T);
-        uint4 v = *reinterpret_cast<const uint4*>(y + row * ld + c0);
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    if (c0 >= ld) return;
+    float sc[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-            const int c = c0 + 2 * j;
-            float z0 = 0.f, z1 = 0.f;
-            if (keep && c < C) z0 = act_fwd(fmaf(f.x, __ldg(ss + c), __ldg(ss + C + c)), act, a, bb);
-            if (keep && c + 1 < C) z1 = act_fwd(fmaf(f.y, __ldg(ss + c + 1), __ldg(ss + C + c + 1)), act, a, bb);
-            w[j] = pack_bf16x2(z0, z1);
+    for (int e = 0; e < 8; ++e) {
+        const bool ok = c0 + e < C;
+        sc[e] = ok ? ss[c0 + e] : 0.f;
+        sh[e] = ok ? ss[C + c0 + e] : 0.f;
+    }
+    const int R = B * T;
+    const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+        const int b = r / T, t = r - b * T;
+        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
+        float f[8];
+        if (keep) {
+            unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (c0 + e < C) ? act_fwd(fmaf(f[e], sc[e], sh[e]), act, a, bb) : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
         }
-        *reinterpret_cast<uint4*>(out + row * ld + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(out + (size_t)r * ld + c0) = pack8(f);
     }
 }
 
@@ -116,82 +154,80 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g,
                          const float* __restrict__ ss, int B, int T, int C, int ld, int act, float a, float bb,
                          const float* __restrict__ xlen, float* __restrict__ out) {
-    const int c = (blockIdx.x * 64 + threadIdx.x) * 2;
-    const int R = B * T;
-    const int r0 = blockIdx.y * kRowsPerBlock;
-    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    if (c < C) {
-        const float sc0 = ss[c], sh0 = ss[C + c], m0 = ss[2 * C + c], i0 = ss[3 * C + c];
-        const bool has1 = c + 1 < C;
-        const float sc1 = has1 ? ss[c + 1] : 0.f, sh1 = has1 ? ss[C + c + 1] : 0.f, m1 = has1 ? ss[2 * C + c + 1] : 0.f, i1 = has1 ? ss[3 * C + c + 1] : 0.f;
-        const int r1 = min(R, r0 + kRowsPerBlock);
-        for (int r = r0 + threadIdx.y; r < r1; r += 4) {
-            const int t = r % T, b = r / T;
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+    if (c0 < ld) {
+        float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const bool ok = c0 + e < C;
+            sc[e] = ok ? ss[c0 + e] : 0.f;
+            sh[e] = ok ? ss[C + c0 + e] : 0.f;
+            mu[e] = ok ? ss[2 * C + c0 + e] : 0.f;
+            is[e] = ok ? ss[3 * C + c0 + e] : 0.f;
+        }
+        const int R = B * T;
+        const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+        for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+            const int b = r / T, t = r - b * T;
             if (xlen != nullptr && t >= frac_len(__ldg(xlen + b), T)) continue;
-            const float2 yv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(y + (size_t)r * ld + c));
-            const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(g + (size_t)r * ld + c));
-            const float dz0 = gv.x * act_grad(fmaf(yv.x, sc0, sh0), act, a, bb);
-            s0 += dz0; q0 = fmaf(dz0, (yv.x - m0) * i0, q0);
-            if (has1) {
-                const float dz1 = gv.y * act_grad(fmaf(yv.y, sc1, sh1), act, a, bb);
-                s1 += dz1; q1 = fmaf(dz1, (yv.y - m1) * i1, q1);
+            float yf[8], gf[8];
+            unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), yf);
+            unpack8(*reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0), gf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
+                s[e] += dz;
+                q[e] = fmaf(dz, (yf[e] - mu[e]) * is[e], q[e]);
             }
         }
     }
-    __shared__ float sm[4][64][4];
-    sm[threadIdx.y][threadIdx.x][0] = s0; sm[threadIdx.y][threadIdx.x][1] = s1;
-    sm[threadIdx.y][threadIdx.x][2] = q0; sm[threadIdx.y][threadIdx.x][3] = q1;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-        for (int yy = 1; yy < 4; ++yy) {
-            s0 += sm[yy][threadIdx.x][0]; s1 += sm[yy][threadIdx.x][1];
-            q0 += sm[yy][threadIdx.x][2]; q1 += sm[yy][threadIdx.x][3];
-        }
-        atomicAdd(out + c, s0);
-        atomicAdd(out + C + c, q0);
-        if (c + 1 < C) { atomicAdd(out + c + 1, s1); atomicAdd(out + C + c + 1, q1); }
-    }
+    reduce_rows_and_add(s, q, c0, C, out);
 }
 
-// backward pass 2: dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n)
+// backward pass 2: dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n) = scale*dz + k0 + k1*y
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g,
                         const float* __restrict__ ss, const float* __restrict__ sums, float inv_n, int B, int T, int C,
                         int ld, int act, float a, float bb, const float* __restrict__ xlen,
                         __nv_bfloat16* __restrict__ dy) {
-    const int vec_per_row = ld / 8;
-    const size_t n = (size_t)B * T * vec_per_row;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % vec_per_row);
-        const size_t row = i / vec_per_row;
-        const int t = (int)(row % T), b = (int)(row / T);
-        const int c0 = cv * 8;
-        bool keep = true;
-        if (xlen != nullptr) keep = t < frac_len(__ldg(xlen + b), T);
-        const uint4 yv4 = *reinterpret_cast<const uint4*>(y + row * ld + c0);
-        const uint4 gv4 = *reinterpret_cast<const uint4*>(g + row * ld + c0);
-        const uint32_t yw[4] = {yv4.x, yv4.y, yv4.z, yv4.w};
-        const uint32_t gw[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
-        uint32_t ow[4];
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    if (c0 >= ld) return;
+    float sc[8], sh[8], k0[8], k1[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[j]));
-            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]));
-            float o[2] = {0.f, 0.f};
-            const float yy[2] = {yf.x, yf.y}, gg[2] = {gf.x, gf.y};
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        const bool ok = c < C;
+        sc[e] = ok ? ss[c] : 0.f;
+        sh[e] = ok ? ss[C + c] : 0.f;
+        const float mean = ok ? ss[2 * C + c] : 0.f, istd = ok ? ss[3 * C + c] : 0.f;
+        const float m1 = ok ? sums[c] * inv_n : 0.f, m2 = ok ? sums[C + c] * inv_n : 0.f;
+        k1[e] = -sc[e] * m2 * istd;          // coefficient of y
+        k0[e] = -sc[e] * m1 - k1[e] * mean;  // constant term
+    }
+    const int R = B * T;
+    const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+        const int b = r / T, t = r - b * T;
+        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
+        float yf[8], gf[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), yf);
+        if (keep) {
+            unpack8(*reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0), gf);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int c = c0 + 2 * j + e;
-                if (c < C) {
-                    const float sc = __ldg(ss + c), sh = __ldg(ss + C + c), mean = __ldg(ss + 2 * C + c), istd = __ldg(ss + 3 * C + c);
-                    const float dz = keep ? gg[e] * act_grad(fmaf(yy[e], sc, sh), act, a, bb) : 0.f;
-                    const float xhat = (yy[e] - mean) * istd;
-                    o[e] = sc * (dz - __ldg(sums + c) * inv_n - xhat * __ldg(sums + C + c) * inv_n);
-                }
+            for (int e = 0; e < 8; ++e) {
+                const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
+                o[e] = fmaf(sc[e], dz, fmaf(k1[e], yf[e], k0[e]));
             }
-            ow[j] = pack_bf16x2(o[0], o[1]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fmaf(k1[e], yf[e], k0[e]);
         }
-        *reinterpret_cast<uint4*>(dy + row * ld + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(dy + (size_t)r * ld + c0) = pack8(o);
     }
 }
 
@@ -199,16 +235,28 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
 // weight packing: fp32 [Co, Ci, K] -> bf16 tap-major [K, Co, ci_ld] (forward operand) and/or
 // bf16 [K, Ci, co_ld] with flipped taps (dgrad operand); inverse for the gradient.
 // ---------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int K, __nv_bfloat16* __restrict__ fwd,
-                                   int ci_ld, __nv_bfloat16* __restrict__ dgr, int co_ld) {
-    const size_t n = (size_t)Co * Ci * K;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const int ci = (int)((i / K) % Ci);
-        const int co = (int)(i / ((size_t)K * Ci));
-        const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
-        if (fwd) fwd[((size_t)k * Co + co) * ci_ld + ci] = v;
-        if (dgr) dgr[((size_t)(K - 1 - k) * Ci + ci) * co_ld + co] = v;
+// block = (32, 8): a 32 (co) x 32 (ci) tile for all K taps; reads run along (ci, k) of one co row,
+// writes run along ci (forward operand) or co (dgrad operand)
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int K, __nv_bfloat16* __restrict__ fwd,
+                   int ci_ld, __nv_bfloat16* __restrict__ dgr, int co_ld) {
+    extern __shared__ float tile[];  // [32 co][32 ci * K + 1]
+    const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int run = 32 * K, pitch = run + 1;
+    const int ci_n = min(32, Ci - ci0), co_n = min(32, Co - co0);
+    for (int co = threadIdx.y; co < co_n; co += 8) {
+        const float* src = w + ((size_t)(co0 + co) * Ci + ci0) * K;
+        for (int i = threadIdx.x; i < ci_n * K; i += 32) tile[co * pitch + i] = src[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < 32 * 32 * K; i += 256) {
+        // forward operand: ci fastest
+        int ci = i % 32, co = (i / 32) % 32, k = i / 1024;
+        if (fwd && ci < ci_n && co < co_n) fwd[((size_t)k * Co + co0 + co) * ci_ld + ci0 + ci] = __float2bfloat16_rn(tile[co * pitch + ci * K + k]);
+        // dgrad operand: co fastest, taps flipped
+        co = i % 32; ci = (i / 32) % 32;
+        if (dgr && ci < ci_n && co < co_n) dgr[((size_t)(K - 1 - k) * Ci + ci0 + ci) * co_ld + co0 + co] = __float2bfloat16_rn(tile[co * pitch + ci * K + k]);
     }
 }
 // packed gradient fp32 [K, M, ld] -> fp32 [Co, Ci, K]; transposed = packed is [K, Ci, Co]
@@ -259,10 +307,10 @@ extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, co
                                   float* out_ss /*[4][C]*/, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && ws_sums && out_ss, "null pointer argument");
-    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C && C % 2 == 0, "bad channel layout C=%d ld=%d", C, ld);
+    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout C=%d ld=%d", C, ld);
     CAB_CHECK_CUDA(cudaMemsetAsync(ws_sums, 0, sizeof(float) * 2 * C, stream));
     const int R = B * T;
-    dim3 grid((C + 127) / 128, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(64, 4);
+    dim3 grid((ld / 8 + 31) / 32, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
     colstats_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), R, C, ld, ws_sums);
     CAB_CHECK_LAUNCH();
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_sums, C, (float)R, gamma, beta, eps, momentum, running_mean, running_var, out_ss);
@@ -276,8 +324,8 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && ss && out, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
-    const size_t n = (size_t)B * T * (ld / 8);
-    bn_act_mask_fwd_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out));
+    dim3 grid((ld / 8 + 31) / 32, (B * T + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
+    bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out));
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -288,14 +336,13 @@ extern "C" int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const fl
                                    void* grad_y, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
-    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C && C % 2 == 0, "bad channel layout");
+    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
     CAB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
     const int R = B * T;
-    dim3 grid((C + 127) / 128, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(64, 4);
+    dim3 grid((ld / 8 + 31) / 32, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
     bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums);
     CAB_CHECK_LAUNCH();
-    const size_t n = (size_t)B * T * (ld / 8);
-    bn_act_bwd_apply_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y));
+    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y));
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return 0;
@@ -305,8 +352,15 @@ extern "C" int cab_pack_weight(const float* w, int Co, int Ci, int K, void* fwd,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(w && (fwd || dgrad), "null pointer argument");
     CAB_CHECK_ARG((!fwd || ci_ld >= Ci) && (!dgrad || co_ld >= Co), "bad pitch");
-    const size_t n = (size_t)Co * Ci * K;
-    pack_weight_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(w, Co, Ci, K, static_cast<__nv_bfloat16*>(fwd), ci_ld, static_cast<__nv_bfloat16*>(dgrad), co_ld);
+    const size_t smem = sizeof(float) * 32 * (32 * K + 1);
+    CAB_CHECK_ARG(smem <= 160 * 1024, "kernel size K=%d too large for the packing tile", K);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CAB_CHECK_CUDA(cudaFuncSetAttribute(pack_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((Ci + 31) / 32, (Co + 31) / 32), block(32, 8);
+    pack_weight_kernel<<<grid, block, smem, stream>>>(w, Co, Ci, K, static_cast<__nv_bfloat16*>(fwd), ci_ld, static_cast<__nv_bfloat16*>(dgrad), co_ld);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

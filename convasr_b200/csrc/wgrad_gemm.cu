@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int block_n = p.block_n;
-    const int n_batoms = block_n / kAtom;
+    const int n_batoms = (block_n + kAtom - 1) / kAtom;  // 64-channel TMA boxes covering the N tile
     const uint32_t stage_tx = kATileBytes + n_batoms * kSubTile;
 
     // item -> (tap, mt, nt, split); splits are the fastest index so neighbours share operands' L2 lines
@@ -256,7 +256,7 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
                                 float* out, int out_ld, int n_splits, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(a && bx && out, "null pointer argument");
-    CAB_CHECK_ARG(B > 0 && a_T > 0 && b_T > 0 && taps > 0 && dilation > 0, "bad shape");
+    CAB_CHECK_ARG(B > 0 && a_T > 0 && b_T > 0 && taps > 0 && dilation != 0, "bad shape");
     CAB_CHECK_ARG(a_ld % 8 == 0 && b_ld % 8 == 0 && a_ld >= M_total && b_ld >= N_total, "bad channel pitch");
     CAB_CHECK_ARG(out_ld % 4 == 0 && out_ld >= N_total, "out_ld=%d must be a multiple of 4 and >= N_total", out_ld);
     CAB_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(bx) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "pointers must be 16-byte aligned");
@@ -269,7 +269,7 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
     p.M_total = M_total; p.N_total = N_total;
     const int n_nt = (N_total + wg::kMaxBlockN - 1) / wg::kMaxBlockN;
     int bn = (N_total + n_nt - 1) / n_nt;
-    bn = (bn + wg::kAtom - 1) / wg::kAtom * wg::kAtom;
+    bn = (bn + 31) / 32 * 32;  // UMMA N granularity (16) x2 so the epilogue reads 32-column chunks
     p.block_n = bn;
     p.n_mtiles = (M_total + wg::kBlockM - 1) / wg::kBlockM;
     p.n_ntiles = (N_total + bn - 1) / bn;
@@ -285,10 +285,19 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
     CAB_CHECK_ARG(attr_err == cudaSuccess && num_sms > 0, "wgrad kernel setup failed: %s", cudaGetErrorString(attr_err));
     const int tiles = taps * p.n_mtiles * p.n_ntiles;
     if (n_splits <= 0) {
-        // enough items for >= ~4 waves of the persistent grid, never more splits than utterances
-        n_splits = (4 * num_sms + tiles - 1) / tiles;
-        if (n_splits > B) n_splits = B;
-        if (n_splits < 1) n_splits = 1;
+        // All items cost the same and every persistent CTA takes ceil(items / #SMs) of them, so pick
+        // the batch split that wastes the least of the last wave (ties: fewer splits = less L2
+        // reduction traffic); never more splits than utterances, at least ~2 waves when possible.
+        double best = -1.0;
+        n_splits = 1;
+        const int max_splits = B < 24 ? B : 24;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const long long items = (long long)tiles * sp;
+            const long long waves = (items + num_sms - 1) / num_sms;
+            double eff = (double)items / (double)(waves * num_sms);
+            if (items < 2LL * num_sms) eff *= 0.9;  // too few items to hide the pipeline fill
+            if (eff > best + 0.02) { best = eff; n_splits = sp; }
+        }
     }
     CAB_CHECK_ARG(n_splits <= B, "n_splits=%d > B=%d", n_splits, B);
     p.n_splits = n_splits;

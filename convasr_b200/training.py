@@ -189,13 +189,29 @@ class NativeStack(torch.autograd.Function):
 				packed = ops.conv1d_wgrad(dy, T_out, L.C_out, xv, xv.shape[1], 2 * L.ci_alloc, taps, 1, pad_left)
 				grads[L.conv.weight] = _unpack_stride2(packed, L)
 			else:
-				packed = ops.conv1d_wgrad(dy, T_out, L.C_out, x, x_T, L.C_in, L.k, L.dil, L.pad)
-				grads[L.conv.weight] = _unpack(packed, L.k, L.C_out, L.C_in, transposed = False)
+				grads[L.conv.weight] = _wgrad(dy, T_out, L.C_out, x, x_T, L.C_in, L.k, L.dil, L.pad)
 			if li > 0:
 				gx = torch.empty(B, x_T, L.ci_alloc, dtype = BF16, device = dev)
 				# dx[j] = sum_k' W'[k'] dy[j + k'*d - (d*(K-1) - pad)], W' = flipped, transposed weights
 				ops.conv1d_fused([ops.Source(dy, w_dgr, L.co_alloc, L.k, L.dil, L.dil * (L.k - 1) - L.pad, T_in = T_out)], B, x_T, L.ci_alloc, out_hi = gx)
 		return (None, None, None) + tuple(grads.get(p) for p in holder['params'])
+
+
+def _padded_work(M, N):
+	n_nt = (N + 255) // 256
+	bn = ((N + n_nt - 1) // n_nt + 31) // 32 * 32
+	return ((M + 127) // 128 * 128) * n_nt * bn
+
+
+def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad):
+	"""dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * x[b, t + tap*dil - pad, ci].  Either tensor can sit on the
+	128-row M side of the GEMM; pick the orientation with less tile padding (e.g. 640 -> 768 wastes 20 %
+	one way and nothing the other way).  Swapping sides negates the frame shift."""
+	if _padded_work(C_out, C_in) <= _padded_work(C_in, C_out):
+		packed = ops.conv1d_wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad)
+		return _unpack(packed, k, C_out, C_in, transposed = False)
+	packed = ops.conv1d_wgrad(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad)
+	return _unpack(packed, k, C_out, C_in, transposed = True)
 
 
 def _unpack(packed, K, Co, Ci, transposed):
