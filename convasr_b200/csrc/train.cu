@@ -88,11 +88,21 @@ colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
     if (c0 < ld) {
         const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-        for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
-            float f[8];
-            unpack8(*reinterpret_cast<const uint4*>(x + (size_t)r * ld + c0), f);
+        // 4 independent 16-byte loads in flight per thread (the loop is latency bound otherwise)
+        for (int r = r0 + threadIdx.y; r < r1; r += 4 * kRowLanes) {
+            uint4 v[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + u * kRowLanes;
+                v[u] = rr < r1 ? *reinterpret_cast<const uint4*>(x + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8(v[u], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+            }
         }
     }
     reduce_rows_and_add(s, q, c0, C, out);
@@ -133,19 +143,26 @@ bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restr
     }
     const int R = B * T;
     const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
-        const int b = r / T, t = r - b * T;
-        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
-        float f[8];
-        if (keep) {
-            unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), f);
+    for (int r = r0 + threadIdx.y; r < r1; r += 4 * kRowLanes) {
+        uint4 v[4];
+        bool keep[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = (c0 + e < C) ? act_fwd(fmaf(f[e], sc[e], sh[e]), act, a, bb) : 0.f;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + u * kRowLanes;
+            const int b = rr / T, t = rr - b * T;
+            keep[u] = rr < r1 && (xlen == nullptr || t < frac_len(__ldg(xlen + b), T));
+            v[u] = keep[u] ? *reinterpret_cast<const uint4*>(y + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
         }
-        *reinterpret_cast<uint4*>(out + (size_t)r * ld + c0) = pack8(f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int rr = r + u * kRowLanes;
+            if (rr >= r1) break;
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (keep[u] && c0 + e < C) ? act_fwd(fmaf(f[e], sc[e], sh[e]), act, a, bb) : 0.f;
+            *reinterpret_cast<uint4*>(out + (size_t)rr * ld + c0) = pack8(f);
+        }
     }
 }
 
@@ -171,17 +188,29 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
         }
         const int R = B * T;
         const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-        for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
-            const int b = r / T, t = r - b * T;
-            if (xlen != nullptr && t >= frac_len(__ldg(xlen + b), T)) continue;
-            float yf[8], gf[8];
-            unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), yf);
-            unpack8(*reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0), gf);
+        for (int r = r0 + threadIdx.y; r < r1; r += 2 * kRowLanes) {
+            uint4 yv[2], gv[2];
+            bool on[2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
-                s[e] += dz;
-                q[e] = fmaf(dz, (yf[e] - mu[e]) * is[e], q[e]);
+            for (int u = 0; u < 2; ++u) {
+                const int rr = r + u * kRowLanes;
+                const int b = rr / T, t = rr - b * T;
+                on[u] = rr < r1 && (xlen == nullptr || t < frac_len(__ldg(xlen + b), T));
+                yv[u] = on[u] ? *reinterpret_cast<const uint4*>(y + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
+                gv[u] = on[u] ? *reinterpret_cast<const uint4*>(g + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue;
+                float yf[8], gf[8];
+                unpack8(yv[u], yf);
+                unpack8(gv[u], gf);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
+                    s[e] += dz;
+                    q[e] = fmaf(dz, (yf[e] - mu[e]) * is[e], q[e]);
+                }
             }
         }
     }
@@ -211,23 +240,31 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
     }
     const int R = B * T;
     const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
-        const int b = r / T, t = r - b * T;
-        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
-        float yf[8], gf[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + (size_t)r * ld + c0), yf);
-        if (keep) {
-            unpack8(*reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0), gf);
+    for (int r = r0 + threadIdx.y; r < r1; r += 2 * kRowLanes) {
+        uint4 yv[2], gv[2];
+        bool keep[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + u * kRowLanes;
+            const int b = rr / T, t = rr - b * T;
+            keep[u] = rr < r1 && (xlen == nullptr || t < frac_len(__ldg(xlen + b), T));
+            yv[u] = rr < r1 ? *reinterpret_cast<const uint4*>(y + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
+            gv[u] = keep[u] ? *reinterpret_cast<const uint4*>(g + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rr = r + u * kRowLanes;
+            if (rr >= r1) break;
+            float yf[8], gf[8], o[8];
+            unpack8(yv[u], yf);
+            unpack8(gv[u], gf);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
+                const float dz = keep[u] ? gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb) : 0.f;
                 o[e] = fmaf(sc[e], dz, fmaf(k1[e], yf[e], k0[e]));
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = fmaf(k1[e], yf[e], k0[e]);
+            *reinterpret_cast<uint4*>(dy + (size_t)rr * ld + c0) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(dy + (size_t)r * ld + c0) = pack8(o);
     }
 }
 

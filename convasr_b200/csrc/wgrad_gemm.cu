@@ -96,13 +96,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
     const int n_batoms = (block_n + kAtom - 1) / kAtom;  // 64-channel TMA boxes covering the N tile
     const uint32_t stage_tx = kATileBytes + n_batoms * kSubTile;
 
-    // item -> (tap, mt, nt, split); splits are the fastest index so neighbours share operands' L2 lines
+    // item -> (split, mt, nt, tap), tap fastest and the batch split SLOWEST: the ~148 items in flight
+    // then all stream the same slab of utterances in the same order (it stays L2 resident; with the
+    // split as the fastest index every CTA walked a different slab and the operands -- 184 MB for a
+    // 768-channel layer -- were re-fetched from HBM: 2.5 GB of DRAM reads per launch, ncu r01)
     auto decode = [&](int item, int& tap, int& mt, int& nt, int& b0, int& b1) {
-        const int split = item % p.n_splits;
-        int r = item / p.n_splits;
-        nt = r % p.n_ntiles; r /= p.n_ntiles;
-        mt = r % p.n_mtiles;
-        tap = r / p.n_mtiles;
+        const int tiles = p.taps * p.n_mtiles * p.n_ntiles;
+        const int split = item / tiles;
+        int r = item - split * tiles;
+        tap = r % p.taps; r /= p.taps;
+        nt = r % p.n_ntiles;
+        mt = r / p.n_ntiles;
         b0 = (int)((long long)p.B * split / p.n_splits);
         b1 = (int)((long long)p.B * (split + 1) / p.n_splits);
     };
@@ -123,10 +127,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
                         uint8_t* a_dst = smem + stage * kStageBytes;
                         uint8_t* b_dst = a_dst + kATileBytes;
                         mbar_expect_tx(&full_bar[stage], stage_tx);
-                        tma_load_3d(a_dst, &p.amap, &full_bar[stage], m0, t0, b);
-                        tma_load_3d(a_dst + kSubTile, &p.amap, &full_bar[stage], m0 + kAtom, t0, b);
-                        for (int i = 0; i < n_batoms; ++i)
-                            tma_load_3d(b_dst + i * kSubTile, &p.bmap, &full_bar[stage], n0 + i * kAtom, t0 + shift, b);
+                        // one 4-D box per operand: {64 ch, 64 frames, atoms, 1} lands as [atom][frame][64 ch]
+                        tma_load_4d(a_dst, &p.amap, &full_bar[stage], 0, t0, m0 / kAtom, b);
+                        tma_load_4d(b_dst, &p.bmap, &full_bar[stage], 0, t0 + shift, n0 / kAtom, b);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -233,14 +236,17 @@ static EncodeTiledFn encode_fn() {
     });
     return fn;
 }
-static int encode_cl(CUtensorMap* map, const void* base, int ld, int T, int T_rows, int B) {
+// channels-last [B, T_rows, ld] viewed as 4-D {64 ch, T frames, ld/64 atoms, B}: a box of `atoms`
+// 64-channel atoms lands in shared memory atom-major, i.e. as the 8 KB sub-tiles UMMA wants
+static int encode_cl(CUtensorMap* map, const void* base, int ld, int T, int T_rows, int B, int atoms) {
     EncodeTiledFn enc = encode_fn();
     CAB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T_rows * ld * 2};
-    cuuint32_t box[3] = {kAtom, kBlockK, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CAB_CHECK_ARG(ld % kAtom == 0, "wgrad operands need a channel pitch that is a multiple of 64 (got %d)", ld);
+    cuuint64_t dims[4] = {(cuuint64_t)kAtom, (cuuint64_t)T, (cuuint64_t)(ld / kAtom), (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)kAtom * 2, (cuuint64_t)T_rows * ld * 2};
+    cuuint32_t box[4] = {kAtom, kBlockK, (cuuint32_t)atoms, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CAB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for wgrad operand ld=%d T=%d B=%d", (int)r, ld, T, B);
@@ -257,20 +263,20 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(a && bx && out, "null pointer argument");
     CAB_CHECK_ARG(B > 0 && a_T > 0 && b_T > 0 && taps > 0 && dilation != 0, "bad shape");
-    CAB_CHECK_ARG(a_ld % 8 == 0 && b_ld % 8 == 0 && a_ld >= M_total && b_ld >= N_total, "bad channel pitch");
+    CAB_CHECK_ARG(a_ld % 64 == 0 && b_ld % 64 == 0 && a_ld >= M_total && b_ld >= N_total, "bad channel pitch (multiples of 64 required)");
     CAB_CHECK_ARG(out_ld % 4 == 0 && out_ld >= N_total, "out_ld=%d must be a multiple of 4 and >= N_total", out_ld);
     CAB_CHECK_ARG((reinterpret_cast<uintptr_t>(a) & 15) == 0 && (reinterpret_cast<uintptr_t>(bx) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "pointers must be 16-byte aligned");
     static thread_local wg::Params p;
-    int rc = wg::encode_cl(&p.amap, a, a_ld, a_T, a_T_rows, B);
-    if (rc) return rc;
-    rc = wg::encode_cl(&p.bmap, bx, b_ld, b_T, b_T_rows, B);
-    if (rc) return rc;
     p.B = B; p.T_a = a_T; p.taps = taps; p.dil = dilation; p.pad_left = pad_left;
     p.M_total = M_total; p.N_total = N_total;
     const int n_nt = (N_total + wg::kMaxBlockN - 1) / wg::kMaxBlockN;
     int bn = (N_total + n_nt - 1) / n_nt;
-    bn = (bn + 31) / 32 * 32;  // UMMA N granularity (16) x2 so the epilogue reads 32-column chunks
+    bn = (bn + wg::kAtom - 1) / wg::kAtom * wg::kAtom;  // whole 64-channel atoms (one TMA box per operand)
     p.block_n = bn;
+    int rc = wg::encode_cl(&p.amap, a, a_ld, a_T, a_T_rows, B, 2);
+    if (rc) return rc;
+    rc = wg::encode_cl(&p.bmap, bx, b_ld, b_T, b_T_rows, B, bn / wg::kAtom);
+    if (rc) return rc;
     p.n_mtiles = (M_total + wg::kBlockM - 1) / wg::kBlockM;
     p.n_ntiles = (N_total + bn - 1) / bn;
     static int num_sms = 0;

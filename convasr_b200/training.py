@@ -199,7 +199,7 @@ class NativeStack(torch.autograd.Function):
 
 def _padded_work(M, N):
 	n_nt = (N + 255) // 256
-	bn = ((N + n_nt - 1) // n_nt + 31) // 32 * 32
+	bn = ((N + n_nt - 1) // n_nt + 63) // 64 * 64
 	return ((M + 127) // 128 * 128) * n_nt * bn
 
 
