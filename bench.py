@@ -180,7 +180,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	model_name, C, B, seconds, precision, kind = WORKLOADS[name]
 	config = dict(workload = name, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
 				step = STEP_DESC[kind], parallelism = (f'DDP x{world} (NCCL gradient all-reduce)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
-				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = kind == 'infer' and not args.no_cuda_graphs)
+				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = (kind == 'infer' or world == 1) and not args.no_cuda_graphs)
 	cpu_baseline = None
 	if with_cpu_baseline:
 		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
@@ -211,7 +211,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		optimizer = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr = 1e-6, momentum = 0.9)
 		flops = 3 * flops_fwd - flops_first  # forward + dgrad (all but the first layer) + wgrad
 
-		def run(s, xl, yy, yl):
+		def run_eager(s, xl, yy, yl):
 			optimizer.zero_grad(set_to_none = True)
 			out = net(s, xl, y = yy, ylen = yl)
 			loss = (out['loss'] * yl[:, 0]).mean()  # train.py:754-755
@@ -219,11 +219,13 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			optimizer.step()
 			return out['loss']
 
+		run = [run_eager]  # swapped for the CUDA-graph replay after the eager launch count (single GPU only)
+
 		def step_device():
-			return run(sig_d, xlen_d, y_d, ylen_d)
+			return run[0](sig_d, xlen_d, y_d, ylen_d)
 
 		def step_e2e():
-			per_utt = run(*[t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)])
+			per_utt = run[0](*[t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)])
 			return per_utt.detach().cpu()
 
 		d2h = B * 4
@@ -275,8 +277,10 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	step_device()
 	torch.cuda.synchronize()
 	launches_per_step = _lib.launch_count() - l0
-	if config['cuda_graphs']:
+	if config['cuda_graphs'] and kind == 'infer':
 		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
+	if config['cuda_graphs'] and kind == 'train':
+		run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d)  # whole step = one replay
 	for _ in range(warmup):
 		nll = step_device()
 	torch.cuda.synchronize()
@@ -310,6 +314,9 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		for n_, fn in originals.items():
 			setattr(ops, n_, make_traced(fn))
 		model.enable_cuda_graphs(False)  # per-launch events need the eager launch path
+		graphed = run[0] if kind == 'train' else None
+		if kind == 'train':
+			run[0] = run_eager
 		n_prof = min(steps, 5)
 		for _ in range(n_prof):
 			flush.zero_()
@@ -317,8 +324,10 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		torch.cuda.synchronize()
 		for n_, fn in originals.items():
 			setattr(ops, n_, fn)
-		if config['cuda_graphs']:
+		if config['cuda_graphs'] and kind == 'infer':
 			model.enable_cuda_graphs(True)
+		if kind == 'train':
+			run[0] = graphed
 		kern_ms = sum(a.elapsed_time(b) for a, b in events) / n_prof
 		n_kern = len(events) // n_prof
 		# end to end through the public API with host buffers

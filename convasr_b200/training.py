@@ -254,3 +254,39 @@ def forward_training(model, feats_f32, xlen):
 	logits, log_probs, argmax = NativeStack.apply(holder, hi, xlen, *params)
 	log_probs._convasr_argmax = argmax
 	return (logits, ), [log_probs]
+
+
+class GraphedTrainStep:
+	"""One whole training step -- zero_grad, forward, CTC loss, backward, optimizer.step -- captured
+	once into a CUDA graph and replayed: ~190 kernel launches per step stop paying host launch
+	latency and inter-kernel gaps.  Inputs are copied into static buffers; the per-utterance loss of
+	the step is returned (a clone).  Shapes are fixed at construction; single process only (under
+	DistributedDataParallel use the eager step, whose all-reduce overlaps the backward)."""
+
+	def __init__(self, model, optimizer, x, xlen, y, ylen, warmup = 3):
+		self.model, self.optimizer = model, optimizer
+		self.static = [t.clone() for t in (x, xlen, y, ylen)]
+		side = torch.cuda.Stream(device = x.device)
+		side.wait_stream(torch.cuda.current_stream())
+		with torch.cuda.stream(side):
+			for _ in range(warmup):
+				self._step()
+		torch.cuda.current_stream().wait_stream(side)
+		self.graph = torch.cuda.CUDAGraph()
+		with torch.cuda.graph(self.graph):
+			self.loss = self._step()
+
+	def _step(self):
+		sx, sxlen, sy, sylen = self.static
+		self.optimizer.zero_grad(set_to_none = True)
+		out = self.model(sx, sxlen, y = sy, ylen = sylen)
+		loss = (out['loss'] * sylen[:, 0]).mean()  # train.py:754-755
+		loss.backward()
+		self.optimizer.step()
+		return out['loss'].detach()
+
+	def __call__(self, x, xlen, y, ylen):
+		for dst, src in zip(self.static, (x, xlen, y, ylen)):
+			dst.copy_(src, non_blocking = True)
+		self.graph.replay()
+		return self.loss.clone()
