@@ -29,7 +29,7 @@ class ConvEpilogue(ctypes.Structure):
 		('B', c_i32), ('T_out', c_i32), ('C_out', c_i32), ('block_n', c_i32), ('epilogue', c_i32), ('act', c_i32),
 		('act_a', c_float), ('act_b', c_float), ('bias', c_void_p), ('xlen_frac', c_void_p), ('out_hi', c_void_p),
 		('out_lo', c_void_p), ('out_T_rows', c_i32), ('out_ld_ch', c_i32), ('logits', c_void_p),
-		('log_probs', c_void_p), ('argmax', c_void_p)
+		('log_probs', c_void_p), ('argmax', c_void_p), ('stats', c_void_p)
 	]
 
 
@@ -48,6 +48,7 @@ SIGNATURES = {
 						c_void_p, c_int, c_int, c_void_p],
 	'cab_bn_batch_stats': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_void_p],
+	'cab_bn_finalize': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
 	'cab_bn_act_mask_fwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
 	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
 							c_void_p, c_void_p, c_void_p],

@@ -66,6 +66,7 @@ struct alignas(64) ConvParams {
     float* logits;
     float* log_probs;
     int* argmax;
+    float* stats;  // [2][C_out] per-channel sum / sum of squares of the bf16 outputs, or null
 };
 
 __device__ __forceinline__ float apply_act(float x, int act, float a, float b) {
@@ -102,6 +103,24 @@ __device__ __forceinline__ float act_t(float x, float a, float b) {
 
 // One 32-column chunk of the bf16 epilogue: bias + activation + mask, pack to bf16 (hi, lo),
 // write the thread's 64-byte row into the 64B-swizzled staging tile(s).
+// Per-column sums over the 32 rows a warp holds (one row per lane, 32 columns per lane): butterfly
+// reduce-scatter -- after the 5 exchange steps lane l holds the warp total of column l.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+    for (int step = 0; step < 5; ++step) {
+        const int half = 16 >> step;  // values kept per lane after this step
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            // keep columns [0, half) if lower lane-half, [half, 2*half) if upper; send the other half
+            const float mine = upper ? x[j + half] : x[j];
+            const float send = upper ? x[j] : x[j + half];
+            x[j] = mine + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return x[0];
+}
+
 template <int ACT, bool LO>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ sb, float a, float b,
                                           bool keep, int row, uint8_t* st_hi, uint8_t* st_lo) {
@@ -258,7 +277,6 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             const int n0 = nt * block_n;
             const int t = t0 + row;
             const bool row_ok = t < p.T_out;
-            (void)row_ok;
 
             const uint32_t taddr = tmem_base + acc * kMaxBlockN + (uint32_t(q * 32) << 16);
             if (p.epilogue != CAB_EPI_ACT_BF16) {
@@ -310,6 +328,32 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                         default: CAB_EPI_CALL(CAB_ACT_NONE) break;
                     }
 #undef CAB_EPI_CALL
+                    if (p.stats != nullptr) {
+                        // BatchNorm batch statistics of what was just stored (bf16-rounded), valid rows only
+                        float xs[32], xq[32];
+                        const uint4* mine = reinterpret_cast<const uint4*>(st_hi + row * 64);
+                        const int sw = (row >> 1) & 3;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const uint4 w4 = mine[qd ^ sw];
+                            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                                const float f0 = row_ok ? f.x : 0.f, f1 = row_ok ? f.y : 0.f;
+                                xs[qd * 8 + 2 * j] = f0; xs[qd * 8 + 2 * j + 1] = f1;
+                                xq[qd * 8 + 2 * j] = f0 * f0; xq[qd * 8 + 2 * j + 1] = f1 * f1;
+                            }
+                        }
+                        const float cs = warp_colsum32(xs, lane);
+                        const float cq = warp_colsum32(xq, lane);
+                        // lane l now owns column bit-reversed?  no: the butterfly keeps column index == lane
+                        const int col = n0 + c0 + lane;
+                        if (col < p.C_out) {
+                            atomicAdd(p.stats + col, cs);
+                            atomicAdd(p.stats + p.C_out + col, cq);
+                        }
+                    }
                     fence_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
                     epi_bar(3);
                     if (et == 0) {
@@ -516,6 +560,8 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     p.logits = ep->logits;
     p.log_probs = ep->log_probs;
     p.argmax = ep->argmax;
+    p.stats = ep->epilogue == CAB_EPI_ACT_BF16 ? ep->stats : nullptr;
+    if (p.stats != nullptr) CAB_CHECK_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * ep->C_out, stream));
     if (ep->epilogue == CAB_EPI_ACT_BF16) {
         CAB_CHECK_ARG(ep->out_lo == nullptr || (reinterpret_cast<uintptr_t>(ep->out_lo) & 15) == 0, "out_lo must be 16-byte aligned");
         int rc = encode_map_3d(&p.omap_hi, ep->out_hi, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,

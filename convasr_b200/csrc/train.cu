@@ -356,6 +356,16 @@ extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, co
     return 0;
 }
 
+extern "C" int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* out_ss, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(sums && out_ss && n_rows > 0 && C > 0, "bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, (float)n_rows, gamma, beta, eps, momentum, running_mean, running_var, out_ss);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
                                    const float* xlen_frac, void* out, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -127,7 +127,7 @@ class Source:
 
 def conv1d_fused(
 	sources, B, T_out, C_out, bias = None, act = _lib.ACT_NONE, act_a = 0.0, act_b = 0.0, xlen = None, out_hi = None,
-	out_lo = None, logits = None, log_probs = None, argmax = None, epilogue = _lib.EPI_ACT_BF16, block_n = 0
+	out_lo = None, logits = None, log_probs = None, argmax = None, epilogue = _lib.EPI_ACT_BF16, block_n = 0, stats = None
 ):
 	_need_cuda(*(s.act for s in sources), bias, xlen, out_hi, out_lo, logits, log_probs, argmax)
 	n = len(sources)
@@ -144,6 +144,7 @@ def conv1d_fused(
 	ep.logits = None if logits is None else logits.data_ptr()
 	ep.log_probs = None if log_probs is None else log_probs.data_ptr()
 	ep.argmax = None if argmax is None else argmax.data_ptr()
+	ep.stats = None if stats is None else stats.data_ptr()
 	rc = _lib.load().cab_conv1d_fused(arr, n, ctypes.byref(ep), _stream())
 	_lib.check(rc, 'cab_conv1d_fused')
 

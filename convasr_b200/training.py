@@ -22,6 +22,7 @@ import torch.nn as nn
 from . import _lib, engine, ops
 
 BF16 = torch.bfloat16
+_SEPARATE_BN_STATS = __import__('os').environ.get('CONVASR_B200_SEPARATE_BN_STATS', '0') == '1'
 
 
 def supported(model):
@@ -77,16 +78,18 @@ def _pack(w, ci_ld, co_ld, want_dgrad):
 	return fwd, dgr
 
 
-def _bn_stats(y, T, layer):
+def _bn_finalize(sums, n_rows, layer):
+	"""sums: fp32 [2, co_alloc] accumulated by the conv epilogue -> [scale, shift, mean, invstd] + running stats"""
 	bn = layer.bn
-	B = y.shape[0]
-	ws = torch.empty(2, layer.C_out, dtype = torch.float32, device = y.device)
-	ss = torch.empty(4, layer.C_out, dtype = torch.float32, device = y.device)
-	rc = _lib.load().cab_bn_batch_stats(
-		ops._p(y), B, T, layer.C_out, y.shape[2], ops._p(bn.weight), ops._p(bn.bias), float(bn.eps), float(bn.momentum),
-		ops._p(bn.running_mean), ops._p(bn.running_var), ops._p(ws), ops._p(ss), ops._stream()
+	ss = torch.empty(4, layer.C_out, dtype = torch.float32, device = sums.device)
+	# the epilogue indexes the statistics with the padded channel count; BatchNorm sees the real channels
+	if sums.shape[1] != layer.C_out:
+		sums = sums[:, :layer.C_out].contiguous()
+	rc = _lib.load().cab_bn_finalize(
+		ops._p(sums), n_rows, layer.C_out, ops._p(bn.weight), ops._p(bn.bias), float(bn.eps), float(bn.momentum),
+		ops._p(bn.running_mean), ops._p(bn.running_var), ops._p(ss), ops._stream()
 	)
-	_lib.check(rc, 'cab_bn_batch_stats')
+	_lib.check(rc, 'cab_bn_finalize')
 	return ss
 
 
@@ -118,8 +121,15 @@ class NativeStack(torch.autograd.Function):
 				T_out = x_T + 2 * L.pad - L.dil * (L.k - 1)
 				geom = ('plain', L.k, L.pad)
 			y = torch.empty(B, T_out, L.co_alloc, dtype = BF16, device = x.device)
-			ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y)
-			ss = _bn_stats(y, T_out, L)
+			if _SEPARATE_BN_STATS:  # A/B switch: statistics as a separate pass over y
+				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y)
+				ws = torch.empty(2, L.C_out, dtype = torch.float32, device = x.device)
+				ss = torch.empty(4, L.C_out, dtype = torch.float32, device = x.device)
+				_lib.check(lib.cab_bn_batch_stats(ops._p(y), B, T_out, L.C_out, L.co_alloc, ops._p(L.bn.weight), ops._p(L.bn.bias), float(L.bn.eps), float(L.bn.momentum), ops._p(L.bn.running_mean), ops._p(L.bn.running_var), ops._p(ws), ops._p(ss), ops._stream()), 'cab_bn_batch_stats')
+			else:
+				sums = torch.empty(2, L.co_alloc, dtype = torch.float32, device = x.device)
+				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y, stats = sums)  # batch statistics in the epilogue
+				ss = _bn_finalize(sums, B * T_out, L)
 			out = torch.empty_like(y)
 			code, a, b = L.act
 			rc = lib.cab_bn_act_mask_fwd(ops._p(y), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(out), ops._stream())

@@ -120,6 +120,9 @@ typedef struct {
     float* logits;           /* LOGSOFTMAX / LOGITS_F32: fp32 [B, C_out, T_out] or NULL */
     float* log_probs;        /* LOGSOFTMAX: fp32 [B, C_out, T_out] or NULL */
     int32_t* argmax;         /* LOGSOFTMAX: int32 [B, T_out] or NULL (ties -> lowest id) */
+    float* stats;            /* ACT_BF16: NULL, or fp32 [2][C_out]: the call zeroes it and the epilogue
+                                accumulates per-channel sum / sum of squares of the (bf16-rounded) outputs
+                                over all B*T_out rows -- BatchNorm batch statistics for training */
 } cab_conv_epilogue_t;
 
 int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
@@ -149,6 +152,10 @@ int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total
 int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var,
                        float* ws_sums, float* out_ss, cab_stream_t stream);
+/* same as cab_bn_batch_stats but from sums the conv epilogue already accumulated (cab_conv_epilogue_t.stats) */
+int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* out_ss,
+                    cab_stream_t stream);
 int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a,
                         float act_b, const float* xlen_frac, void* out, cab_stream_t stream);
 int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld,

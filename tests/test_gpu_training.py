@@ -213,9 +213,10 @@ def test_graphed_train_step_equals_eager_step():
 		m, sd = _model(dev, dict(base_width = 32, num_blocks = 1))
 		opt = torch.optim.SGD(m.parameters(), lr = 1e-3, momentum = 0.9)
 		if graphed:
-			step = training.GraphedTrainStep(m, opt, sig, xlen, y, ylen, warmup = 0)
-			m.load_state_dict(sd, strict = False)  # capture ran one step on the weights: restart from the same point
-			opt.state.clear()
+			step = training.GraphedTrainStep(m, opt, sig, xlen, y, ylen, warmup = 2)
+			m.load_state_dict(sd, strict = False)  # warm-up + capture stepped the weights: restart from the same point
+			for st in opt.state.values():  # the graph holds these buffers: reset their contents, keep the tensors
+				st['momentum_buffer'].zero_()
 			out = [step(sig, xlen, y, ylen) for _ in range(3)]
 		else:
 			out = []
