@@ -6,8 +6,9 @@ Default workload = BASELINE.json configs[1]: Wav2Letter-char (66.5 M params, 38 
 STEP, batch 80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16.  One step = log-mel
 frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + mask layers -> decoder
 + log_softmax -> CTC loss -> backward through everything (CTC gradient, log_softmax, decoder, BN,
-dgrad and wgrad of every conv) -> SGD(momentum) update.  Everything except the optimizer update
-(torch.optim.SGD, section 8f "next" #3) runs on this repo's kernels.  N > 1: DistributedDataParallel
+dgrad and wgrad of every conv) -> clip_grad_norm_ + SGD(momentum, weight decay) update.  Everything except
+the gradient clipping / optimizer update (torch.nn.utils + torch.optim.SGD, the reference's train.py defaults;
+section 8f "next" #3) runs on this repo's kernels.  N > 1: DistributedDataParallel
 gradient all-reduce over NCCL.
 
 Secondary workload (reported under "also", selectable with --workload): the inference path of the
@@ -43,8 +44,13 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = 'wav2letter_char_train_step_B80x15s_bf16'
 SECONDARY_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'
+# mean DRAM bytes per launch of the tensor-pipe kernels, from the committed ncu --set full captures
+NCU_DRAM_BYTES_PER_LAUNCH = {
+	'wav2letter_char_train_step_B80x15s_bf16': 131.2e6,  # profiles/r01_train_step_tensor_kernels_ncu_full.csv (56 launches)
+	'wav2letter_char_fwd_ctc_B80x15s_bf16': 105.0e6,  # profiles/r01_step_kernels_ncu_full.csv (conv1d_umma_kernel launches)
+}
 STEP_DESC = {
-	'train': 'frontend+instnorm+18x(conv, batch-stat BN, hardtanh, mask)+decoder/log_softmax+CTC loss+full backward (CTC grad, BN bwd, dgrad, wgrad)+SGD update',
+	'train': 'frontend+instnorm+18x(conv, batch-stat BN, hardtanh, mask)+decoder/log_softmax+CTC loss+full backward (CTC grad, BN bwd, dgrad, wgrad)+clip_grad_norm+SGD(momentum,wd) update',
 	'infer': 'frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)',
 }
 SAMPLE_RATE = 8000
@@ -208,7 +214,9 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		net = model
 		if world > 1:
 			net, _ = models.distributed_data_parallel_and_autocast(model, local_rank)
-		optimizer = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr = 1e-6, momentum = 0.9)
+		# train.py defaults: SGD(momentum 0.9, weight_decay 1e-3) after clip_grad_norm_(max_norm 100) (train.py:657-662,776-779)
+		train_params = [p for p in model.parameters() if p.requires_grad]
+		optimizer = torch.optim.SGD(train_params, lr = 1e-6, momentum = 0.9, weight_decay = 1e-3)
 		flops = 3 * flops_fwd - flops_first  # forward + dgrad (all but the first layer) + wgrad
 
 		def run_eager(s, xl, yy, yl):
@@ -216,6 +224,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			out = net(s, xl, y = yy, ylen = yl)
 			loss = (out['loss'] * yl[:, 0]).mean()  # train.py:754-755
 			loss.backward()
+			torch.nn.utils.clip_grad_norm_(train_params, 100.0, error_if_nonfinite = False)
 			optimizer.step()
 			return out['loss']
 
@@ -280,7 +289,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	if config['cuda_graphs'] and kind == 'infer':
 		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
 	if config['cuda_graphs'] and kind == 'train':
-		run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d)  # whole step = one replay
+		run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d, max_grad_norm = 100.0)  # whole step = one replay
 	for _ in range(warmup):
 		nll = step_device()
 	torch.cuda.synchronize()
@@ -342,7 +351,8 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		roofline = dict(
 			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
 			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
-			peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = None, launches_per_step = n_kern, kernel_ms_per_step = kern_ms,
+			peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name), traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed',
+			launches_per_step = n_kern, kernel_ms_per_step = kern_ms,
 			algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1, share_of_step = kern_ms / (ms / steps)
 		)
 	result.update(config = config, cpu_baseline = cpu_baseline, clocks = clocks, roofline = roofline, launches = launches_per_step * steps, B = B, seconds = seconds, precision = precision,

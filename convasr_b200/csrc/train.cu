@@ -31,6 +31,18 @@ __device__ __forceinline__ float act_grad(float z, int act, float a, float b) {
     }
 }
 
+// Dropout keep-decision: counter-based, recomputed identically in the backward pass (no mask is
+// stored).  seed comes from DEVICE memory so that CUDA-graph replays draw fresh masks; the stream
+// is this repo's own (F.dropout's Philox stream is not reproducible across implementations anyway,
+// parity runs use dropout = 0).
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long idx, float p) {
+    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ULL;  // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f) >= p;  // 24 uniform bits
+}
+
 // ---------------------------------------------------------------------------------------
 // Row-walker layout shared by the four activation-sized kernels: a thread owns ONE 16-byte channel
 // vector (8 bf16 channels) and walks down the rows, so the per-channel coefficients live in
@@ -130,7 +142,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float
 // out = act(y * scale + shift) * (t < len_b)
 __global__ void __launch_bounds__(256)
 bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int B, int T, int C, int ld,
-                       int act, float a, float bb, const float* __restrict__ xlen, __nv_bfloat16* __restrict__ out) {
+                       int act, float a, float bb, const float* __restrict__ xlen, __nv_bfloat16* __restrict__ out,
+                       float drop_p, const long long* __restrict__ seed_ptr, unsigned long long salt) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     if (c0 >= ld) return;
@@ -161,6 +174,12 @@ bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restr
             unpack8(v[u], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = (keep[u] && c0 + e < C) ? act_fwd(fmaf(f[e], sc[e], sh[e]), act, a, bb) : 0.f;
+            if (drop_p > 0.f) {
+                const unsigned long long seed = (unsigned long long)seed_ptr[0] + salt * 0xD1B54A32D192ED03ULL;
+                const float inv_keep = 1.f / (1.f - drop_p);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, drop_p) ? f[e] * inv_keep : 0.f;
+            }
             *reinterpret_cast<uint4*>(out + (size_t)rr * ld + c0) = pack8(f);
         }
     }
@@ -170,7 +189,8 @@ bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restr
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g,
                          const float* __restrict__ ss, int B, int T, int C, int ld, int act, float a, float bb,
-                         const float* __restrict__ xlen, float* __restrict__ out) {
+                         const float* __restrict__ xlen, float* __restrict__ out, float drop_p,
+                         const long long* __restrict__ seed_ptr, unsigned long long salt) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     float s[8], q[8];
@@ -205,6 +225,13 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
                 float yf[8], gf[8];
                 unpack8(yv[u], yf);
                 unpack8(gv[u], gf);
+                if (drop_p > 0.f) {
+                    const unsigned long long seed = (unsigned long long)seed_ptr[0] + salt * 0xD1B54A32D192ED03ULL;
+                    const float inv_keep = 1.f / (1.f - drop_p);
+                    const int rr = r + u * kRowLanes;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gf[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, drop_p) ? gf[e] * inv_keep : 0.f;
+                }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
@@ -222,7 +249,8 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g,
                         const float* __restrict__ ss, const float* __restrict__ sums, float inv_n, int B, int T, int C,
                         int ld, int act, float a, float bb, const float* __restrict__ xlen,
-                        __nv_bfloat16* __restrict__ dy) {
+                        __nv_bfloat16* __restrict__ dy, float drop_p, const long long* __restrict__ seed_ptr,
+                        unsigned long long salt) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     if (c0 >= ld) return;
@@ -258,6 +286,12 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
             float yf[8], gf[8], o[8];
             unpack8(yv[u], yf);
             unpack8(gv[u], gf);
+            if (drop_p > 0.f) {
+                const unsigned long long seed = (unsigned long long)seed_ptr[0] + salt * 0xD1B54A32D192ED03ULL;
+                const float inv_keep = 1.f / (1.f - drop_p);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gf[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, drop_p) ? gf[e] * inv_keep : 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float dz = keep[u] ? gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb) : 0.f;
@@ -367,12 +401,14 @@ extern "C" int cab_bn_finalize(const float* sums, int n_rows, int C, const float
 }
 
 extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
-                                   const float* xlen_frac, void* out, cab_stream_t stream_) {
+                                   const float* xlen_frac, void* out, float dropout_p, const int64_t* seed, int64_t salt,
+                                   cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && ss && out, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
+    CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
     dim3 grid((ld / 8 + 31) / 32, (B * T + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
-    bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out));
+    bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -380,16 +416,16 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T,
 
 extern "C" int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld, int act,
                                    float act_a, float act_b, const float* xlen_frac, float* sums /*[2][C]: dbeta, dgamma*/,
-                                   void* grad_y, cab_stream_t stream_) {
+                                   void* grad_y, float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
     CAB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
     const int R = B * T;
     dim3 grid((ld / 8 + 31) / 32, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
-    bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums);
+    bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
     CAB_CHECK_LAUNCH();
-    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y));
+    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return 0;

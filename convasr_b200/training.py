@@ -13,8 +13,9 @@ What `model.train(); loss.backward()` does in the reference through autograd + c
 
 Activations are bf16 channels-last, parameters stay fp32 masters (bf16 operand copies are re-packed
 every step by cab_pack_weight), all gradients are fp32.  Supported topologies: dense (non-separable)
-blocks without residual branches and without dropout -- the Wav2Letter family with dropout=0;
-anything else keeps using the ATen path in models.JasperNet._forward_training.
+blocks without residual branches -- the Wav2Letter family, with or without dropout (dropout masks come
+from a counter-based generator of this repo, not from torch's Philox stream); anything else keeps using
+the ATen path in models.JasperNet._forward_training.
 """
 import torch
 import torch.nn as nn
@@ -32,7 +33,7 @@ def supported(model):
 	if model.decoder[0].out_channels > 256:
 		return False
 	for i, block in enumerate(model.backbone):
-		if len(block.conv_residual) > 0 or block.activation.dropout > 0 or block.activation.invertible:
+		if len(block.conv_residual) > 0 or block.activation.invertible:
 			return False
 		if block.activation.nonlinearity[0] not in ('relu', 'hardtanh', 'leaky_relu'):
 			return False
@@ -50,8 +51,8 @@ def supported(model):
 class _Layer:
 	"""static description of one conv + BN + activation repeat"""
 
-	def __init__(self, conv, bn, act, mask):
-		self.conv, self.bn = conv, bn
+	def __init__(self, conv, bn, act, mask, dropout):
+		self.conv, self.bn, self.dropout = conv, bn, float(dropout)
 		self.k, self.stride, self.dil, self.pad = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
 		self.C_in, self.C_out = conv.in_channels, conv.out_channels
 		self.ci_alloc, self.co_alloc = engine._ceil_to(self.C_in, 64), engine._ceil_to(self.C_out, 64)
@@ -63,7 +64,7 @@ def _layers(model):
 	out = []
 	for block in model.backbone:
 		for seq, bn in zip(block.conv, block.bn):
-			out.append(_Layer(seq[0], bn, block.activation.nonlinearity, bool(block.temporal_mask)))
+			out.append(_Layer(seq[0], bn, block.activation.nonlinearity, bool(block.temporal_mask), block.activation.dropout))
 	return out
 
 
@@ -132,7 +133,7 @@ class NativeStack(torch.autograd.Function):
 				ss = _bn_finalize(sums, B * T_out, L)
 			out = torch.empty_like(y)
 			code, a, b = L.act
-			rc = lib.cab_bn_act_mask_fwd(ops._p(y), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(out), ops._stream())
+			rc = lib.cab_bn_act_mask_fwd(ops._p(y), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(out), L.dropout, ops._p(holder['seed']), li, ops._stream())
 			_lib.check(rc, 'cab_bn_act_mask_fwd')
 			saved.append((x, x_T, y, T_out, ss, w_dgr, geom))
 			x, x_T = out, T_out
@@ -145,6 +146,8 @@ class NativeStack(torch.autograd.Function):
 		argmax = torch.empty(B, x_T, dtype = torch.int32, device = x.device)
 		ops.conv1d_fused([ops.Source(x, w_dec, w_dec.shape[2], 1, 1, 0, T_in = x_T)], B, x_T, C, bias = dec.bias.detach() if dec.bias is not None else None, logits = logits, log_probs = log_probs, argmax = argmax, epilogue = _lib.EPI_LOGSOFTMAX)
 		ctx.holder, ctx.saved, ctx.xlen = holder, saved, xlen
+		ctx.seed = holder['seed'].clone()  # the value this forward used (the live counter advances every step)
+		holder['seed'].add_(len(layers) + 1)
 		ctx.x_last, ctx.T_last, ctx.w_dec_dgr = x, x_T, w_dec_dgr
 		ctx.save_for_backward(log_probs)
 		ctx.mark_non_differentiable(argmax)
@@ -189,7 +192,7 @@ class NativeStack(torch.autograd.Function):
 			code, a, b = L.act
 			sums = torch.empty(2, L.C_out, dtype = torch.float32, device = dev)
 			dy = torch.empty_like(y)
-			rc = lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(gx), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(sums), ops._p(dy), ops._stream())
+			rc = lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(gx), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(sums), ops._p(dy), L.dropout, ops._p(ctx.seed), li, ops._stream())
 			_lib.check(rc, 'cab_bn_act_mask_bwd')
 			grads[L.bn.bias] = sums[0]
 			grads[L.bn.weight] = sums[1]
@@ -260,7 +263,11 @@ def forward_training(model, feats_f32, xlen):
 		params += [L.conv.weight, L.bn.weight, L.bn.bias]
 	dec = model.decoder[0]
 	params += [dec.weight] + ([dec.bias] if dec.bias is not None else [])
-	holder = dict(model = model, layers = layers, params = params, n_frames = Fr)
+	seed = getattr(model, '_dropout_seed', None)
+	if seed is None or seed.device != hi.device:
+		# device-resident dropout counter, initialised from torch's seed so torch.manual_seed controls it
+		seed = model._dropout_seed = torch.full((1, ), torch.initial_seed() & 0x7FFFFFFFFFFF, dtype = torch.int64, device = hi.device)
+	holder = dict(model = model, layers = layers, params = params, n_frames = Fr, seed = seed)
 	logits, log_probs, argmax = NativeStack.apply(holder, hi, xlen, *params)
 	log_probs._convasr_argmax = argmax
 	return (logits, ), [log_probs]
@@ -273,8 +280,9 @@ class GraphedTrainStep:
 	the step is returned (a clone).  Shapes are fixed at construction; single process only (under
 	DistributedDataParallel use the eager step, whose all-reduce overlaps the backward)."""
 
-	def __init__(self, model, optimizer, x, xlen, y, ylen, warmup = 3):
-		self.model, self.optimizer = model, optimizer
+	def __init__(self, model, optimizer, x, xlen, y, ylen, warmup = 3, max_grad_norm = None):
+		self.model, self.optimizer, self.max_grad_norm = model, optimizer, max_grad_norm
+		self.params = [p for g in optimizer.param_groups for p in g['params']]
 		self.static = [t.clone() for t in (x, xlen, y, ylen)]
 		side = torch.cuda.Stream(device = x.device)
 		side.wait_stream(torch.cuda.current_stream())
@@ -292,6 +300,8 @@ class GraphedTrainStep:
 		out = self.model(sx, sxlen, y = sy, ylen = sylen)
 		loss = (out['loss'] * sylen[:, 0]).mean()  # train.py:754-755
 		loss.backward()
+		if self.max_grad_norm is not None:  # train.py:776-779
+			torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, error_if_nonfinite = False)
 		self.optimizer.step()
 		return out['loss'].detach()
 

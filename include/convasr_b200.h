@@ -148,7 +148,10 @@ int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total
  *   cab_bn_act_mask_fwd: out = act(y*scale + shift) * (t < ceil(frac*T))
  *   cab_bn_act_mask_bwd: given grad_out w.r.t. `out`: sums = [dbeta, dgamma] (fp32 [2][C]) and
  *                        grad_y = scale * (dz - mean(dz) - xhat * mean(dz*xhat)),
- *                        dz = grad_out * act'(z) * mask  (hardtanh: a < z < b strictly). */
+ *                        dz = grad_out * act'(z) * mask  (hardtanh: a < z < b strictly).
+ *   dropout_p > 0 applies F.dropout after the activation (ResidualActivation.forward, models.py:357-371):
+ *   out *= keep / (1 - p) with a counter-based keep decision from (*seed, salt, element index) that
+ *   the backward recomputes; *seed lives in device memory so CUDA-graph replays draw new masks. */
 int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var,
                        float* ws_sums, float* out_ss, cab_stream_t stream);
@@ -157,10 +160,12 @@ int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, co
                     float momentum, float* running_mean, float* running_var, float* out_ss,
                     cab_stream_t stream);
 int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a,
-                        float act_b, const float* xlen_frac, void* out, cab_stream_t stream);
+                        float act_b, const float* xlen_frac, void* out, float dropout_p,
+                        const int64_t* seed, int64_t salt, cab_stream_t stream);
 int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld,
                         int act, float act_a, float act_b, const float* xlen_frac, float* sums,
-                        void* grad_y, cab_stream_t stream);
+                        void* grad_y, float dropout_p, const int64_t* seed, int64_t salt,
+                        cab_stream_t stream);
 /* fp32 [Co,Ci,K] -> bf16 tap-major [K,Co,ci_ld] (forward operand) and/or [K,Ci,co_ld] with flipped
  * taps (dgrad operand); and the inverse for a packed fp32 gradient ([K,Co,ld] or, transposed,
  * [K,Ci,ld]) into the parameter layout. */

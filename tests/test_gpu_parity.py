@@ -268,3 +268,47 @@ def test_training_step_runs_and_matches_oracle_loss(golden, dev):
 	loss.backward()
 	grads = [p.grad for p in m.parameters() if p.requires_grad]
 	assert all(g is not None and torch.isfinite(g).all() for g in grads)
+
+
+def test_feature_input_and_no_lengths_paths(dev):
+	"""model(x[B,64,F]) without a frontend (features computed elsewhere, datasets.py:269-277) and
+	xlen=None (no masks anywhere, full-length olen) -- models.py:282-326."""
+	from convasr_b200 import models
+	m = models.Wav2Letter(64, [38], base_width = 32, dropout = 0., check_time_dim_padded = False)
+	shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+	sd = O.synth_state_dict(shapes, seed = 9)
+	m.load_state_dict(sd)
+	m = m.to(dev).eval()
+	g = torch.Generator().manual_seed(6)
+	sig = (torch.randn(2, 9600, generator = g) * 1000).round().to(torch.int16)
+	feats = O.frontend_logmel(sig, None)  # [2, 64, 121], un-normalised
+	ref_logits, ref_lp, ref_olen = O.conv_stack_forward(sd, O.masked_instance_norm(feats, None), None, **O.MODEL_CONFIGS['Wav2Letter'])
+	for precision, tol in (('fp32', 1e-3), ('bf16', 2e-2)):
+		m.set_precision(precision)
+		with torch.no_grad():
+			out = m(feats.to(dev))
+		assert out['logits'][0].shape == ref_logits[0].shape
+		assert out['olen'][0].tolist() == [ref_logits[0].shape[-1]] * 2 == ref_olen[0].tolist()
+		assert rel(out['logits'][0], ref_logits[0]) < tol, precision
+	# lengths given, features in: masks applied from the fractions
+	xlen = torch.tensor([1.0, 0.52])
+	ref2, _, olen2 = O.conv_stack_forward(sd, O.masked_instance_norm(feats, xlen), xlen, **O.MODEL_CONFIGS['Wav2Letter'])
+	m.set_precision('fp32')
+	with torch.no_grad():
+		out2 = m(feats.to(dev), xlen.to(dev))
+	assert torch.equal(out2['olen'][0].cpu(), olen2[0]) and rel(out2['logits'][0], ref2[0]) < 1e-3
+
+
+def test_cuda_graph_forward_equals_eager(golden, dev):
+	c = golden('models')['cases'][0]
+	m = _build(c, dev, 'bf16')
+	sig, xlen = c['signal'].to(dev), c['xlen'].to(dev)
+	with torch.no_grad():
+		eager = m(sig, xlen)
+		m.enable_cuda_graphs(True)
+		g1 = m(sig, xlen)
+		g2 = m(sig.clone(), xlen.clone())  # replay with fresh input tensors
+		other = m(sig.roll(1, 0), xlen.roll(1, 0))
+	assert torch.equal(eager['logits'][0], g1['logits'][0]) and torch.equal(g1['logits'][0], g2['logits'][0])
+	assert torch.equal(other['logits'][0], eager['logits'][0].roll(1, 0))
+	assert torch.equal(g1['log_probs'][0]._convasr_argmax, eager['log_probs'][0]._convasr_argmax)

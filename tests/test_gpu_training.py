@@ -59,14 +59,70 @@ def test_bn_act_mask_forward_backward_kernels():
 		_lib.check(lib.cab_bn_batch_stats(ops._p(yd), B, T, C, C, ops._p(gamma_d), ops._p(beta_d), 1e-5, 0.1, ops._p(rm_d), ops._p(rv_d), ops._p(ws), ops._p(ss), ops._stream()), 'stats')
 		out = torch.empty_like(yd)
 		xl = xlen.to(dev)
-		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), ops._stream()), 'fwd')
+		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), 0.0, None, 0, ops._stream()), 'fwd')
 		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd)
-		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), ops._stream()), 'bwd')
+		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._stream()), 'bwd')
 		torch.cuda.synchronize()
 		assert rel(out.float().permute(0, 2, 1), o) < 4e-3, act_name  # bf16 output rounding
 		assert torch.allclose(rm_d.cpu(), rm_ref, atol = 1e-5) and torch.allclose(rv_d.cpu(), rv_ref, rtol = 1e-4, atol = 1e-5)
 		assert rel(sums[0], br.grad) < 1e-4 and rel(sums[1], gr.grad) < 1e-4, act_name
 		assert rel(dy.float().permute(0, 2, 1), yr.grad) < 4e-3, act_name
+
+
+def test_dropout_in_bn_act_kernels():
+	"""F.dropout after the activation (models.py:357-371): keep/(1-p) scaling, rate ~ p, and a backward
+	that uses exactly the forward's mask (recomputed from the counter, not stored)."""
+	from convasr_b200 import _lib, ops
+	dev = torch.device('cuda:0')
+	lib = _lib.load()
+	g = torch.Generator().manual_seed(5)
+	B, C, T, p = 4, 128, 200, 0.2
+	y = (torch.randn(B, C, T, generator = g) * 2).to(BF16).float()
+	go = torch.randn(B, C, T, generator = g).to(BF16).float()
+	gamma, beta = torch.rand(C, generator = g) + 0.5, torch.randn(C, generator = g) * 0.1
+	yd, go_d, gamma_d, beta_d = cl(y).to(dev), cl(go).to(dev), gamma.to(dev), beta.to(dev)
+	ws = torch.empty(2, C, device = dev); ss = torch.empty(4, C, device = dev)
+	_lib.check(lib.cab_bn_batch_stats(ops._p(yd), B, T, C, C, ops._p(gamma_d), ops._p(beta_d), 1e-5, 0.1, None, None, ops._p(ws), ops._p(ss), ops._stream()), 'stats')
+	seed = torch.tensor([1234], dtype = torch.int64, device = dev)
+	outs = []
+	for salt in (3, 3, 4):
+		out = torch.empty_like(yd)
+		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(out), p, ops._p(seed), salt, ops._stream()), 'fwd')
+		outs.append(out.float().permute(0, 2, 1).cpu())
+	assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])  # deterministic in (seed, salt)
+	# reference without dropout
+	yr = y.clone().requires_grad_(True)
+	z = F.batch_norm(yr, None, None, gamma, beta, True, 0.1, 1e-5).relu()
+	pos = z > 1e-3
+	kept = outs[0][pos] != 0
+	rate = 1.0 - float(kept.float().mean())
+	assert abs(rate - p) < 0.01, rate
+	assert torch.allclose(outs[0][pos][kept], (z[pos][kept] / (1 - p)).detach(), rtol = 1e-2, atol = 1e-2)
+	# backward against autograd with the recovered mask
+	mask = torch.where(pos, (outs[0] != 0).float(), torch.ones_like(z)) / (1 - p)  # where z ~ 0 the mask is irrelevant
+	(z * mask).backward(go)
+	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd)
+	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), p, ops._p(seed), 3, ops._stream()), 'bwd')
+	torch.cuda.synchronize()
+	assert rel(dy.float().permute(0, 2, 1), yr.grad) < 2e-2
+
+
+def test_training_step_with_dropout_runs_natively():
+	from convasr_b200 import training
+	dev = torch.device('cuda:0')
+	C = 38
+	from convasr_b200 import models
+	m = models.Wav2Letter(64, [C], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0.2, check_time_dim_padded = False, base_width = 32).to(dev).train()
+	assert training.supported(m) and m.backbone[1].activation.dropout == 0.2
+	sig, xlen, y, ylen = [t.to(dev) for t in _batch(C)]
+	losses = []
+	for _ in range(2):
+		m.zero_grad()
+		out = m(sig, xlen, y = y, ylen = ylen)
+		(out['loss'] * ylen[:, 0]).mean().backward()
+		losses.append(out['loss'].detach().clone())
+		assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters() if p.requires_grad)
+	assert not torch.equal(losses[0], losses[1])  # a fresh dropout mask every step
 
 
 def test_wgrad_and_dgrad_kernels_against_cpu_autograd():

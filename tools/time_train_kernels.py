@@ -24,8 +24,8 @@ for C in (256, 512, 768, 1024):
 	xlen = (torch.rand(B, device = dev) * 0.5 + 0.5)
 	mb = y.numel() * 2 / 1e6
 	t1 = timeit(lambda: lib.cab_bn_batch_stats(ops._p(y), B, T, C, C, ops._p(gamma), ops._p(beta), 1e-5, 0.1, ops._p(rm), ops._p(rv), ops._p(ws), ops._p(ss), ops._stream()))
-	t2 = timeit(lambda: lib.cab_bn_act_mask_fwd(ops._p(y), ops._p(ss), B, T, C, C, 2, 0.0, 20.0, ops._p(xlen), ops._p(out), ops._stream()))
-	t3 = timeit(lambda: lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(g), ops._p(ss), B, T, C, C, 2, 0.0, 20.0, ops._p(xlen), ops._p(sums), ops._p(dy), ops._stream()))
+	t2 = timeit(lambda: lib.cab_bn_act_mask_fwd(ops._p(y), ops._p(ss), B, T, C, C, 2, 0.0, 20.0, ops._p(xlen), ops._p(out), 0.0, None, 0, ops._stream()))
+	t3 = timeit(lambda: lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(g), ops._p(ss), B, T, C, C, 2, 0.0, 20.0, ops._p(xlen), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._stream()))
 	w = torch.randn(C, C, 11, device = dev)
 	t4 = timeit(lambda: training._pack(w, C, C, True))
 	print(f'C={C:5d} act {mb:6.1f} MB | stats {t1:7.1f} us ({mb/t1*1e-3:.2f} TB/s) | fwd {t2:7.1f} us ({2*mb/t2*1e-3:.2f} TB/s) | bwd(reduce+apply) {t3:7.1f} us ({5*mb/t3*1e-3:.2f} TB/s) | pack k11 {t4:7.1f} us')
