@@ -6,9 +6,9 @@ Default workload = BASELINE.json configs[1]: Wav2Letter-char (66.5 M params, 38 
 STEP, batch 80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16.  One step = log-mel
 frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + mask layers -> decoder
 + log_softmax -> CTC loss -> backward through everything (CTC gradient, log_softmax, decoder, BN,
-dgrad and wgrad of every conv) -> clip_grad_norm_ + SGD(momentum, weight decay) update.  Everything except
-the gradient clipping / optimizer update (torch.nn.utils + torch.optim.SGD, the reference's train.py defaults;
-section 8f "next" #3) runs on this repo's kernels.  N > 1: DistributedDataParallel
+dgrad and wgrad of every conv) -> clip_grad_norm(100) + SGD(momentum 0.9, weight decay 1e-3) update (the
+reference's train.py defaults, train.py:657-662,776-779) as one native multi-tensor step.  The whole step
+runs on this repo's kernels.  N > 1: DistributedDataParallel
 gradient all-reduce over NCCL.
 
 Secondary workload (reported under "also", selectable with --workload): the inference path of the
@@ -215,8 +215,9 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		if world > 1:
 			net, _ = models.distributed_data_parallel_and_autocast(model, local_rank)
 		# train.py defaults: SGD(momentum 0.9, weight_decay 1e-3) after clip_grad_norm_(max_norm 100) (train.py:657-662,776-779)
+		from convasr_b200 import optimizers
 		train_params = [p for p in model.parameters() if p.requires_grad]
-		optimizer = torch.optim.SGD(train_params, lr = 1e-6, momentum = 0.9, weight_decay = 1e-3)
+		optimizer = optimizers.SGD(train_params, lr = 1e-6, momentum = 0.9, weight_decay = 1e-3)  # native multi-tensor step
 		flops = 3 * flops_fwd - flops_first  # forward + dgrad (all but the first layer) + wgrad
 
 		def run_eager(s, xl, yy, yl):
@@ -224,8 +225,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			out = net(s, xl, y = yy, ylen = yl)
 			loss = (out['loss'] * yl[:, 0]).mean()  # train.py:754-755
 			loss.backward()
-			torch.nn.utils.clip_grad_norm_(train_params, 100.0, error_if_nonfinite = False)
-			optimizer.step()
+			optimizer.step(max_grad_norm = 100.0)  # clip_grad_norm_ folded into the native step
 			return out['loss']
 
 		run = [run_eager]  # swapped for the CUDA-graph replay after the eager launch count (single GPU only)

@@ -300,9 +300,13 @@ class GraphedTrainStep:
 		out = self.model(sx, sxlen, y = sy, ylen = sylen)
 		loss = (out['loss'] * sylen[:, 0]).mean()  # train.py:754-755
 		loss.backward()
-		if self.max_grad_norm is not None:  # train.py:776-779
-			torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, error_if_nonfinite = False)
-		self.optimizer.step()
+		from . import optimizers
+		if isinstance(self.optimizer, optimizers._FusedOptimizer):
+			self.optimizer.step(max_grad_norm = self.max_grad_norm)  # clipping folded into the native step
+		else:
+			if self.max_grad_norm is not None:  # train.py:776-779
+				torch.nn.utils.clip_grad_norm_(self.params, self.max_grad_norm, error_if_nonfinite = False)
+			self.optimizer.step()
 		return out['loss'].detach()
 
 	def __call__(self, x, xlen, y, ylen):

@@ -178,6 +178,26 @@ int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int tra
 int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, float* class_sums,
                    cab_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * section 8f "next" #3: multi-tensor optimizer step with gradient-norm clipping folded in.
+ *   mode 0: torch.optim.SGD(momentum, dampening, weight_decay, nesterov)   (train.py:657-662)
+ *   mode 1: NovoGrad (optimizers.py:66-90); `momentum` = beta1, `dampening` != 0 = the dampening flag
+ *   max_grad_norm > 0: torch.nn.utils.clip_grad_norm_ (train.py:776-779) applied first.
+ *   Tensors are described by DEVICE tables: param/grad/momentum pointers (int64 [n]), element counts
+ *   (int64 [n]) and a flat chunk list (tensor index int32 [n_chunks], element offset int64
+ *   [n_chunks], chunk_elems elements per chunk, multiple of 4).  ema: fp32 [n] NovoGrad state.
+ *   step_cell: int64 device cell counting steps (0 = first step initialises ema / momentum);
+ *   lr_dev: fp32 device scalar (so CUDA-graph replays can change it); ws_*: workspaces of n floats /
+ *   one int32; total_norm_out: fp32 [1] or NULL (pre-clip global gradient norm).
+ * ------------------------------------------------------------------------------------- */
+int cab_optimizer_step(int mode, int n_tensors, const int64_t* param_ptrs, const int64_t* grad_ptrs,
+                       const int64_t* mom_ptrs, const int64_t* numels, int n_chunks,
+                       const int32_t* chunk_tensor, const int64_t* chunk_off, int chunk_elems,
+                       float* ws_sumsq, float* ema, float* ws_scale, int64_t* step_cell, int32_t* ws_first,
+                       const float* lr_dev, float momentum, float beta2, float eps, float weight_decay,
+                       float dampening, int nesterov, float max_grad_norm, float* total_norm_out,
+                       cab_stream_t stream);
+
 /* grouped Conv1d + bias + ReLU of the separable blocks (models.py:50-64): bf16 channels-last
  * in [B, T_rows, ld_in] / out [B, out_T_rows, ld_out] (channels C_out..ld_out-1 are zeroed),
  * weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1.

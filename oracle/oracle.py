@@ -505,3 +505,29 @@ def synth_state_dict(shapes, seed = 0):
 		else:
 			sd[k] = torch.randn(shape, generator = g)
 	return sd
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer step (section 8f "next" #3): optimizers.NovoGrad.step, optimizers.py:72-90
+# --------------------------------------------------------------------------------------------
+
+
+def novograd_step(params, grads, state, lr = 1.0, betas = (0.95, 0.98), eps = 1e-8, weight_decay = 0.0, dampening = False):
+	"""One NovoGrad step on lists of tensors; `state` is a list of dicts that persists across calls."""
+	for p, g, st in zip(params, grads, state):
+		g_2 = (g**2).sum()  # :77
+		st['_grads_ema'] = g_2 if '_grads_ema' not in st else st['_grads_ema'] * betas[1] + g_2 * (1. - betas[1])  # :78-79
+		grad = g / (st['_grads_ema'] + eps).sqrt()  # :81
+		if weight_decay > 0:
+			grad = grad + weight_decay * p  # :82-83
+		if dampening:
+			grad = grad * (1 - betas[0])  # :84-85
+		st['momentum_buffer'] = st['momentum_buffer'] * betas[0] + grad if 'momentum_buffer' in st else grad  # :87-89
+		p.sub_(lr * st['momentum_buffer'])  # :90
+
+
+def clip_grad_norm(grads, max_norm):
+	"""torch.nn.utils.clip_grad_norm_ as called at train.py:776-779: returns (scaled grads, total norm)."""
+	total = torch.sqrt(sum((g.double()**2).sum() for g in grads)).float()
+	coef = torch.clamp(max_norm / (total + 1e-6), max = 1.0)
+	return [g * coef for g in grads], total
