@@ -185,8 +185,8 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	from oracle import oracle as O  # only for the seeded synthetic weights + the cpu_baseline leg
 	model_name, C, B, seconds, precision, kind = WORKLOADS[name]
 	config = dict(workload = name, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
-				step = STEP_DESC[kind], parallelism = (f'DDP x{world} (NCCL gradient all-reduce)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
-				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = (kind == 'infer' or world == 1) and not args.no_cuda_graphs)
+				step = STEP_DESC[kind], parallelism = (f'data-parallel replicas x{world} (per-layer NCCL gradient all-reduce overlapped with the backward)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
+				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
 	cpu_baseline = None
 	if with_cpu_baseline:
 		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
@@ -228,7 +228,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			optimizer.step(max_grad_norm = 100.0)  # clip_grad_norm_ folded into the native step
 			return out['loss']
 
-		run = [run_eager]  # swapped for the CUDA-graph replay after the eager launch count (single GPU only)
+		run = [run_eager]  # swapped for the CUDA-graph replay after the eager launch count
 
 		def step_device():
 			return run[0](sig_d, xlen_d, y_d, ylen_d)

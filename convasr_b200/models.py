@@ -700,9 +700,16 @@ def data_parallel_and_autocast(model, optimizer = None, data_parallel = True, op
 
 
 def distributed_data_parallel_and_autocast(model, local_rank, optimizer = None, opt_level = None, synchronize_bn = False, **kwargs):
-	"""models.py:755-765: SyncBatchNorm (optional) + DistributedDataParallel; the gradient all-reduce
-	is NCCL over NVLink through torch.distributed."""
+	"""models.py:755-765: SyncBatchNorm (optional) + data parallelism over NCCL / NVLink.  Topologies
+	the native training step covers are returned UNWRAPPED with a parallel.GradSync attached (parameters
+	broadcast from rank 0; the native backward all-reduces each layer's gradient as soon as it exists);
+	everything else gets torch's DistributedDataParallel."""
 	training = model.training
+	from . import parallel, training as native_training
+	if not synchronize_bn and next(model.parameters()).is_cuda and native_training.supported(model):
+		if opt_level not in (None, '', 'O0'):
+			model.set_precision('bf16')
+		return parallel.attach_grad_sync(model), optimizer
 	if synchronize_bn:
 		model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
 	if opt_level not in (None, '', 'O0'):

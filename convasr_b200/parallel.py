@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, utterance-sharded replicas for inference (no
-data-path collective) and torch.distributed DDP (NCCL over NVLink) for the training gradient
-all-reduce -- SURVEY.md section 8(e), reference sites train.py:852-874 (init), models.py:755-765
-(DDP wrap), utils.py:193-211 (gather of variable-length results).
+data-path collective) and, for training, the gradient all-reduce (NCCL over NVLink) launched layer
+by layer from inside the native backward so it overlaps the remaining dgrad / wgrad kernels --
+SURVEY.md section 8(e), reference sites train.py:852-874 (init), models.py:755-765 (DDP wrap),
+utils.py:193-211 (gather of variable-length results).
 """
 import os
 
@@ -24,6 +25,49 @@ def init_from_env(backend = None, device = None):
 		else:
 			dist.init_process_group(backend)
 	return rank, world, local_rank
+
+
+class GradSync:
+	"""Gradient averaging across ranks for the native training step (what DistributedDataParallel's
+	reducer does for the reference, models.py:755-765).  The native backward is ONE autograd node that
+	walks the layers itself, so it hands every finished weight gradient to `reduce()` right away: the
+	all-reduce runs on the process group's communication stream while the compute stream continues with
+	the next dgrad / wgrad; `finish()` makes the compute stream wait for all of them.  No bucket copies
+	(gradients are reduced in place), one collective per conv layer plus one for all the small tensors.
+	Everything is stream-ordered (no host synchronisation), so the step can be captured in a CUDA graph."""
+
+	def __init__(self, group = None):
+		assert dist.is_initialized(), 'torch.distributed is not initialised'
+		self.group = group
+		self.world = dist.get_world_size(group)
+		self.native_avg = dist.get_backend(group) == 'nccl'  # gloo has no AVG: sum, then scale
+		self.pending = []
+		self.n_collectives = 0
+
+	def reduce(self, tensor):
+		if self.world == 1:
+			return
+		assert tensor.is_contiguous()
+		op = dist.ReduceOp.AVG if self.native_avg else dist.ReduceOp.SUM
+		self.pending.append((dist.all_reduce(tensor, op = op, group = self.group, async_op = True), tensor))
+		self.n_collectives += 1
+
+	def finish(self):
+		for work, tensor in self.pending:
+			work.wait()  # stream-level wait on CUDA, host wait on CPU (gloo)
+			if not self.native_avg:
+				tensor.mul_(1.0 / self.world)
+		self.pending.clear()
+
+
+def attach_grad_sync(model, group = None):
+	"""Make `model` a data-parallel replica: parameters and buffers are broadcast from rank 0 (as the
+	DDP constructor does) and the native backward averages gradients through a GradSync."""
+	with torch.no_grad():
+		for t in list(model.parameters()) + list(model.buffers()):
+			dist.broadcast(t, src = dist.get_global_rank(group, 0) if group is not None else 0, group = group)
+	model._grad_sync = GradSync(group)
+	return model
 
 
 def shard_bounds(n_items, rank, world):

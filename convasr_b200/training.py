@@ -172,7 +172,11 @@ class NativeStack(torch.autograd.Function):
 		dec = model.decoder[0]
 		c_ld = engine._ceil_to(C, 64)
 		g_cl = torch.empty(B, T, c_ld, dtype = BF16, device = dev)
-		d_bias = torch.empty(C, dtype = torch.float32, device = dev) if dec.bias is not None else None
+		# all the small gradients (decoder bias, BN gamma / beta) live in one flat buffer: one all-reduce
+		sync = getattr(model, '_grad_sync', None)
+		small = torch.zeros(c_ld + sum(2 * L.C_out for L in layers), dtype = torch.float32, device = dev)
+		small_off = c_ld
+		d_bias = small[:C] if dec.bias is not None else None
 		rc = lib.cab_bct_to_btc(ops._p(g), B, C, T, c_ld, ops._p(g_cl), ops._p(d_bias), ops._stream())
 		_lib.check(rc, 'cab_bct_to_btc')
 		grads = {}
@@ -180,6 +184,8 @@ class NativeStack(torch.autograd.Function):
 		x_last, T_last = ctx.x_last, ctx.T_last
 		packed = ops.conv1d_wgrad(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0)
 		grads[dec.weight] = _unpack(packed, 1, C, dec.in_channels, transposed = True)
+		if sync is not None:
+			sync.reduce(grads[dec.weight])
 		if dec.bias is not None:
 			grads[dec.bias] = d_bias
 		ci_alloc = x_last.shape[2]
@@ -190,7 +196,8 @@ class NativeStack(torch.autograd.Function):
 			L = layers[li]
 			x, x_T, y, T_out, ss, w_dgr, geom = saved[li]
 			code, a, b = L.act
-			sums = torch.empty(2, L.C_out, dtype = torch.float32, device = dev)
+			sums = small[small_off:small_off + 2 * L.C_out].view(2, L.C_out)
+			small_off += 2 * L.C_out
 			dy = torch.empty_like(y)
 			rc = lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(gx), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(sums), ops._p(dy), L.dropout, ops._p(ctx.seed), li, ops._stream())
 			_lib.check(rc, 'cab_bn_act_mask_bwd')
@@ -203,10 +210,15 @@ class NativeStack(torch.autograd.Function):
 				grads[L.conv.weight] = _unpack_stride2(packed, L)
 			else:
 				grads[L.conv.weight] = _wgrad(dy, T_out, L.C_out, x, x_T, L.C_in, L.k, L.dil, L.pad)
+			if sync is not None:
+				sync.reduce(grads[L.conv.weight])  # overlaps the dgrad / wgrad of the layers still to come
 			if li > 0:
 				gx = torch.empty(B, x_T, L.ci_alloc, dtype = BF16, device = dev)
 				# dx[j] = sum_k' W'[k'] dy[j + k'*d - (d*(K-1) - pad)], W' = flipped, transposed weights
 				ops.conv1d_fused([ops.Source(dy, w_dgr, L.co_alloc, L.k, L.dil, L.dil * (L.k - 1) - L.pad, T_in = T_out)], B, x_T, L.ci_alloc, out_hi = gx)
+		if sync is not None:
+			sync.reduce(small)
+			sync.finish()
 		return (None, None, None) + tuple(grads.get(p) for p in holder['params'])
 
 
@@ -277,8 +289,9 @@ class GraphedTrainStep:
 	"""One whole training step -- zero_grad, forward, CTC loss, backward, optimizer.step -- captured
 	once into a CUDA graph and replayed: ~190 kernel launches per step stop paying host launch
 	latency and inter-kernel gaps.  Inputs are copied into static buffers; the per-utterance loss of
-	the step is returned (a clone).  Shapes are fixed at construction; single process only (under
-	DistributedDataParallel use the eager step, whose all-reduce overlaps the backward)."""
+	the step is returned (a clone).  Shapes are fixed at construction.  Data-parallel replicas
+	(parallel.attach_grad_sync) capture their NCCL all-reduces inside the same graph, on the process
+	group's communication stream, so they still overlap the backward."""
 
 	def __init__(self, model, optimizer, x, xlen, y, ylen, warmup = 3, max_grad_norm = None):
 		self.model, self.optimizer, self.max_grad_norm = model, optimizer, max_grad_norm
@@ -290,8 +303,10 @@ class GraphedTrainStep:
 			for _ in range(warmup):
 				self._step()
 		torch.cuda.current_stream().wait_stream(side)
+		torch.cuda.synchronize()
 		self.graph = torch.cuda.CUDAGraph()
-		with torch.cuda.graph(self.graph):
+		# thread_local: the NCCL watchdog thread may query events while this thread captures
+		with torch.cuda.graph(self.graph, capture_error_mode = 'thread_local'):
 			self.loss = self._step()
 
 	def _step(self):

@@ -72,6 +72,25 @@ def _worker(rank, world, port, tmp):
 		ref_block.load_state_dict(block.state_dict(), strict = False)
 	for p, e in zip(models.master_module(ddp).parameters(), expect):
 		assert torch.allclose(p.grad, e / world, atol = 1e-5)
+	# (4) the native training step's gradient exchange (parallel.GradSync): asynchronous per-layer
+	#     all-reduces issued in backward order, one flat buffer for the small tensors, then finish()
+	lin = torch.nn.Linear(3, 2)
+	with torch.no_grad():
+		lin.weight.fill_(float(rank + 1))
+	parallel.attach_grad_sync(lin)
+	assert float(lin.weight[0, 0]) == 1.0  # rank 0's parameters everywhere, as the DDP constructor does
+	sync = lin._grad_sync
+	layers = [torch.full((5, 7), float(rank + 1 + k)) for k in range(3)]
+	small = torch.arange(10, dtype = torch.float32) * (rank + 1)
+	for t in layers:
+		sync.reduce(t)
+	sync.reduce(small)
+	sync.finish()
+	mean_rank = sum(range(1, world + 1)) / world
+	for k, t in enumerate(layers):
+		assert torch.allclose(t, torch.full((5, 7), mean_rank + k))
+	assert torch.allclose(small, torch.arange(10, dtype = torch.float32) * mean_rank)
+	assert sync.n_collectives == 4 and not sync.pending
 	dist.barrier()
 	dist.destroy_process_group()
 	open(os.path.join(tmp, f'ok{rank}'), 'w').write('ok')
