@@ -8,8 +8,8 @@ frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + m
 + log_softmax -> CTC loss -> backward through everything (CTC gradient, log_softmax, decoder, BN,
 dgrad and wgrad of every conv) -> clip_grad_norm(100) + SGD(momentum 0.9, weight decay 1e-3) update (the
 reference's train.py defaults, train.py:657-662,776-779) as one native multi-tensor step.  The whole step
-runs on this repo's kernels.  N > 1: DistributedDataParallel
-gradient all-reduce over NCCL.
+runs on this repo's kernels.  N > 1: data-parallel replicas; every layer's weight gradient is
+all-reduced (NCCL) from inside the native backward as soon as it exists, inside the same CUDA graph.
 
 Secondary workload (reported under "also", selectable with --workload): the inference path of the
 same shape -- eval-mode forward with folded BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
@@ -41,6 +41,7 @@ WORKLOADS = {
 	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer'),
 	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer'),
 	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer'),
+	'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16': ('Wav2Letter', 5000, 64, 15.0, 'bf16', 'infer'),
 }
 DEFAULT_WORKLOAD = 'wav2letter_char_train_step_B80x15s_bf16'
 SECONDARY_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'

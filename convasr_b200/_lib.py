@@ -38,6 +38,8 @@ EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
 MAX_CONV_SOURCES = 18
 
 # name -> argtypes; every function returns int except the three introspection calls
+BN_SUM_REPLICAS = 8  # CAB_BN_SUM_REPLICAS
+
 SIGNATURES = {
 	'cab_frontend_logmel': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
@@ -52,7 +54,7 @@ SIGNATURES = {
 	'cab_bn_act_mask_fwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_float,
 							c_void_p, c_i64, c_void_p],
 	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
-							c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p],
+							c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p, c_void_p],
 	'cab_pack_weight': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
 	'cab_unpack_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
 	'cab_bct_to_btc': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],

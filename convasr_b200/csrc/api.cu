@@ -19,8 +19,12 @@ void set_last_error(const char* fmt, ...) {
 }
 
 // Grouped Conv1d + bias + ReLU (models.py:50-64, first two stages of the separable
-// ConvSamePadding).  groups = 128 with 2-6 channels per group: tiny K, HBM bound, so this is a
-// SIMT kernel.  Block = one frame strip x all output channels; weights stay in L1.
+// ConvSamePadding): GENERIC kernel for shapes grouped_conv.cu's FFMA2 kernel does not cover
+// (kernel sizes outside its instantiations, very wide groups).  Block = one frame strip x all
+// output channels; weights stay in L1.
+int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in, int ld_in, const float* wgt,
+                      const float* bias, int C_out, int groups, int k, int pad_left, void* out, void* out_lo,
+                      int out_T_rows, int ld_out, cudaStream_t stream);
 constexpr int kGcFrames = 8;
 __global__ void __launch_bounds__(256)
 grouped_conv_relu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo, int T,
@@ -94,6 +98,10 @@ extern "C" int cab_grouped_conv1d_relu(const void* act, const void* act_lo, int 
     CAB_CHECK_ARG(groups > 0 && C_in % groups == 0 && C_out % groups == 0, "channels not divisible by groups");
     CAB_CHECK_ARG(T_rows >= T && out_T_rows >= T, "row allocation smaller than T");
     CAB_CHECK_ARG(ld_in >= C_in && ld_out >= C_out, "row pitch smaller than channel count");
+    {
+        const int rc = grouped_conv_fast(act, act_lo, B, T, T_rows, C_in, ld_in, wgt, bias, C_out, groups, k, pad_left, out, out_lo, out_T_rows, ld_out, stream);
+        if (rc <= 0) return rc;  // launched (0) or failed (< 0); 1 = shape not covered by the FFMA2 kernel
+    }
     dim3 grid((T + kGcFrames - 1) / kGcFrames, B);
     grouped_conv_relu_kernel<<<grid, 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(act), static_cast<const __nv_bfloat16*>(act_lo), T, T_rows, C_in, ld_in, wgt,

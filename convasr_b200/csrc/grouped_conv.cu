@@ -1,0 +1,241 @@
+// Grouped Conv1d + bias + ReLU: the depthwise-like first stage of the separable ConvSamePadding
+// (models.py:50-64; JasperNetSeparable: groups = 128, 2-7 channels per group, k = 11..25).
+//
+// Why SIMT and not tcgen05: with 2-7 input channels per group the contraction length per output is
+// cin_g * K = 22..150.  Laid on a 64-wide tensor-core tile the block-diagonal weights waste 10-30x of
+// the MMAs and the operand traffic per output tile (K taps x 24 KB) is L2 bound; on the fp32 pipe the
+// layer is issue bound at its real FLOPs.  B200-specific pieces: packed FFMA2 (fma.rn.f32x2, two
+// channels of the group per instruction, so the fma pipe runs at its full 128 lanes/clk/SM), weights
+// resident in shared memory for the whole life of a persistent CTA, register-blocked sliding window
+// over time (each weight pair feeds 8 outputs, each input pair up to K outputs).
+//
+//   CTA  = one block of 64 output channels x a persistent loop over (utterance, 32-frame) tiles
+//   thread = (output channel, strip of 8 frames); accumulators: 8 x float2 (even / odd input channel)
+//   x tile: the input channels those 64 outputs need (<= 96), 32 + K - 1 frames, fp32 in smem
+//           (hi + lo bf16 summed while staging); the next tile's global loads are in flight during
+//           the current tile's math.
+#include "common.cuh"
+#include "../../include/convasr_b200.h"
+#include <atomic>
+
+namespace cab {
+extern std::atomic<int64_t> g_launch_count;
+
+constexpr int kGcCo = 64;       // output channels per CTA
+constexpr int kGcStrips = 4;    // frame strips per tile
+constexpr int kGcTT = 8;        // frames per strip (register blocking)
+constexpr int kGcTile = kGcStrips * kGcTT;
+constexpr int kGcThreads = kGcCo * kGcStrips;
+constexpr int kGcMaxCols = 104;  // tile width in input channels (multiple of 8)
+constexpr int kGcMaxVec = 3;     // 16-byte prefetch vectors per thread and tensor
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+struct GroupedArgs {
+    const __nv_bfloat16* x;
+    const __nv_bfloat16* x_lo;
+    const float* w;     // [C_out][cin_g][K]
+    const float* bias;  // [C_out] or null
+    __nv_bfloat16* out;
+    __nv_bfloat16* out_lo;
+    int B, T, T_rows, C_in, ld_in, C_out, ld_out, out_T_rows, groups, pad;
+    int tiles_per_utt, n_items, parts;
+};
+
+template <int K, bool HAS_LO>
+__global__ void __launch_bounds__(kGcThreads, 2)
+grouped_conv_ffma2_kernel(const GroupedArgs p) {
+    constexpr int kRows = kGcTile + K - 1;   // frames in the x tile
+    constexpr int kWin = kGcTT + K - 1;      // frames one thread slides over
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cin_g = p.C_in / p.groups, cout_g = p.C_out / p.groups;
+    const int n_jp = (cin_g + 1) / 2;
+    float2* ws = reinterpret_cast<float2*>(smem_raw);                       // [n_jp][K][kGcCo]
+    float* xs = reinterpret_cast<float*>(smem_raw + sizeof(float2) * n_jp * K * kGcCo);  // [kRows][cols + 1]
+
+    const int tid = threadIdx.x;
+    const int co_l = tid % kGcCo, strip = tid / kGcCo;
+    const int cb = blockIdx.x, part = blockIdx.y;
+    const int co = cb * kGcCo + co_l;
+    const bool live = co < p.C_out;
+    // input channel window of this channel block, 16-byte aligned on the left
+    const int co_last = min(cb * kGcCo + kGcCo, p.C_out) - 1;
+    const int ci_first = co_last >= cb * kGcCo ? (cb * kGcCo / cout_g) * cin_g : 0;
+    const int ci_end = co_last >= cb * kGcCo ? (co_last / cout_g + 1) * cin_g + 1 : 8;  // +1: pad channel of an odd cin_g
+    const int ci_lo = ci_first & ~7;
+    const int cols = ((ci_end - ci_lo + 7) & ~7);
+    const int pitch = cols + 1;
+    const int n_vec = cols / 8;
+
+    // weights -> smem, paired over input channels: ws[jp][k][co] = (w[co][2jp][k], w[co][2jp+1][k] or 0)
+    for (int i = tid; i < n_jp * K * kGcCo; i += kGcThreads) {
+        const int c = i % kGcCo, k = (i / kGcCo) % K, jp = i / (kGcCo * K);
+        const int cg = cb * kGcCo + c;
+        float2 v = make_float2(0.f, 0.f);
+        if (cg < p.C_out) {
+            v.x = p.w[((size_t)cg * cin_g + 2 * jp) * K + k];
+            if (2 * jp + 1 < cin_g) v.y = p.w[((size_t)cg * cin_g + 2 * jp + 1) * K + k];
+        }
+        ws[i] = v;
+    }
+    const float bv = (live && p.bias) ? p.bias[co] : 0.f;
+    const int col0 = live ? (co / cout_g) * cin_g - ci_lo : 0;
+
+    // software pipeline: prefetch registers for the next x tile
+    uint4 pre_hi[kGcMaxVec], pre_lo[HAS_LO ? kGcMaxVec : 1];
+    const int total_vec = kRows * n_vec;
+    auto prefetch = [&](int item) {
+        const int b = item / p.tiles_per_utt, t0 = (item - b * p.tiles_per_utt) * kGcTile;
+#pragma unroll
+        for (int v = 0; v < kGcMaxVec; ++v) {
+            const int idx = tid + v * kGcThreads;
+            pre_hi[v] = make_uint4(0, 0, 0, 0);
+            if (HAS_LO) pre_lo[v] = make_uint4(0, 0, 0, 0);
+            if (idx < total_vec) {
+                const int r = idx / n_vec, cvec = idx - r * n_vec;
+                const int u = t0 - p.pad + r, ch = ci_lo + cvec * 8;
+                if (u >= 0 && u < p.T && ch < p.ld_in) {
+                    const size_t off = ((size_t)b * p.T_rows + u) * p.ld_in + ch;
+                    pre_hi[v] = *reinterpret_cast<const uint4*>(p.x + off);
+                    if (HAS_LO) pre_lo[v] = *reinterpret_cast<const uint4*>(p.x_lo + off);
+                }
+            }
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int v = 0; v < kGcMaxVec; ++v) {
+            const int idx = tid + v * kGcThreads;
+            if (idx < total_vec) {
+                const int r = idx / n_vec, cvec = idx - r * n_vec;
+                const uint32_t h[4] = {pre_hi[v].x, pre_hi[v].y, pre_hi[v].z, pre_hi[v].w};
+                const uint4 lv = HAS_LO ? pre_lo[v] : make_uint4(0, 0, 0, 0);
+                const uint32_t l[4] = {lv.x, lv.y, lv.z, lv.w};
+                float* dst = xs + r * pitch + cvec * 8;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // bf16 -> fp32 is a 16-bit shift; hi + lo restores the split-bf16 ("fp32 tier") value
+                    dst[2 * q] = __uint_as_float(h[q] << 16) + __uint_as_float(l[q] << 16);
+                    dst[2 * q + 1] = __uint_as_float(h[q] & 0xffff0000u) + __uint_as_float(l[q] & 0xffff0000u);
+                }
+            }
+        }
+    };
+
+    int item = part;
+    if (item < p.n_items) prefetch(item);
+    for (; item < p.n_items; item += p.parts) {
+        __syncthreads();  // the previous tile's readers are done (also orders the weight fill on the first pass)
+        stage();
+        __syncthreads();
+        if (item + p.parts < p.n_items) prefetch(item + p.parts);
+
+        const int b = item / p.tiles_per_utt, t0 = (item - b * p.tiles_per_utt) * kGcTile;
+        float2 acc[kGcTT];
+#pragma unroll
+        for (int i = 0; i < kGcTT; ++i) acc[i] = make_float2(bv, 0.f);
+        if (live) {
+            for (int jp = 0; jp < n_jp; ++jp) {
+                const float* xr = xs + (strip * kGcTT) * pitch + col0 + 2 * jp;
+                float2 xw[kWin];
+#pragma unroll
+                for (int m = 0; m < kWin; ++m) xw[m] = make_float2(xr[m * pitch], xr[m * pitch + 1]);
+                const float2* wr = ws + (size_t)jp * K * kGcCo + co_l;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float2 w2 = wr[k * kGcCo];
+#pragma unroll
+                    for (int i = 0; i < kGcTT; ++i) acc[i] = fma2(w2, xw[i + k], acc[i]);
+                }
+            }
+        }
+        if (co < p.ld_out) {
+#pragma unroll
+            for (int i = 0; i < kGcTT; ++i) {
+                const int t = t0 + strip * kGcTT + i;
+                if (t < p.T) {
+                    const size_t o = ((size_t)b * p.out_T_rows + t) * p.ld_out + co;
+                    const float v = live ? fmaxf(acc[i].x + acc[i].y, 0.f) : 0.f;  // padding channels: zeros (the pointwise GEMM contracts over them)
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    p.out[o] = h;
+                    if (p.out_lo) p.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                }
+            }
+        }
+    }
+}
+
+template <int K, bool HAS_LO>
+static int launch_grouped_t(const GroupedArgs& a, int n_cb, int cols_max, cudaStream_t stream) {
+    const int cin_g = a.C_in / a.groups;
+    const int n_jp = (cin_g + 1) / 2;
+    const size_t smem = sizeof(float2) * n_jp * K * kGcCo + sizeof(float) * (kGcTile + K - 1) * (cols_max + 1);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_ffma2_kernel<K, HAS_LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    grouped_conv_ffma2_kernel<K, HAS_LO><<<dim3(n_cb, a.parts), kGcThreads, smem, stream>>>(a);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+template <int K>
+static int launch_grouped(const GroupedArgs& a, int n_cb, int cols_max, cudaStream_t stream) {
+    return a.x_lo ? launch_grouped_t<K, true>(a, n_cb, cols_max, stream) : launch_grouped_t<K, false>(a, n_cb, cols_max, stream);
+}
+
+// returns 1 when this shape is not covered (caller runs the generic kernel), 0 on launch, < 0 on error
+int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in, int ld_in, const float* wgt,
+                      const float* bias, int C_out, int groups, int k, int pad_left, void* out, void* out_lo,
+                      int out_T_rows, int ld_out, cudaStream_t stream) {
+    if (ld_in % 8 != 0 || C_in % groups != 0 || C_out % groups != 0) return 1;
+    const int cin_g = C_in / groups, cout_g = C_out / groups;
+    const int n_cb = (ld_out + kGcCo - 1) / kGcCo;
+    // widest input window over the channel blocks, and the prefetch budget
+    int cols_max = 8;
+    for (int cb = 0; cb < n_cb; ++cb) {
+        const int co_last = (cb * kGcCo + kGcCo < C_out ? cb * kGcCo + kGcCo : C_out) - 1;
+        if (co_last < cb * kGcCo) continue;
+        const int ci_first = (cb * kGcCo / cout_g) * cin_g, ci_end = (co_last / cout_g + 1) * cin_g + 1;
+        const int cols = ((ci_end - (ci_first & ~7)) + 7) & ~7;
+        cols_max = cols > cols_max ? cols : cols_max;
+    }
+    if (cols_max > kGcMaxCols) return 1;
+    if ((kGcTile + k - 1) * (cols_max / 8) > kGcMaxVec * kGcThreads) return 1;
+    const size_t smem = sizeof(float2) * ((cin_g + 1) / 2) * k * kGcCo + sizeof(float) * (kGcTile + k - 1) * (cols_max + 1);
+    if (smem > 100 * 1024) return 1;
+    GroupedArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(act); a.x_lo = static_cast<const __nv_bfloat16*>(act_lo); a.w = wgt; a.bias = bias;
+    a.out = static_cast<__nv_bfloat16*>(out); a.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+    a.B = B; a.T = T; a.T_rows = T_rows; a.C_in = C_in; a.ld_in = ld_in; a.C_out = C_out; a.ld_out = ld_out; a.out_T_rows = out_T_rows;
+    a.groups = groups; a.pad = pad_left;
+    a.tiles_per_utt = (T + kGcTile - 1) / kGcTile;
+    a.n_items = B * a.tiles_per_utt;
+    int parts = (148 * 2 + n_cb - 1) / n_cb;
+    a.parts = parts < a.n_items ? parts : a.n_items;
+    switch (k) {
+        case 3: return launch_grouped<3>(a, n_cb, cols_max, stream);
+        case 5: return launch_grouped<5>(a, n_cb, cols_max, stream);
+        case 7: return launch_grouped<7>(a, n_cb, cols_max, stream);
+        case 9: return launch_grouped<9>(a, n_cb, cols_max, stream);
+        case 11: return launch_grouped<11>(a, n_cb, cols_max, stream);
+        case 13: return launch_grouped<13>(a, n_cb, cols_max, stream);
+        case 15: return launch_grouped<15>(a, n_cb, cols_max, stream);
+        case 17: return launch_grouped<17>(a, n_cb, cols_max, stream);
+        case 19: return launch_grouped<19>(a, n_cb, cols_max, stream);
+        case 21: return launch_grouped<21>(a, n_cb, cols_max, stream);
+        case 23: return launch_grouped<23>(a, n_cb, cols_max, stream);
+        case 25: return launch_grouped<25>(a, n_cb, cols_max, stream);
+        case 27: return launch_grouped<27>(a, n_cb, cols_max, stream);
+        default: return 1;
+    }
+}
+
+}  // namespace cab

@@ -47,10 +47,19 @@ __device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned l
 // Row-walker layout shared by the four activation-sized kernels: a thread owns ONE 16-byte channel
 // vector (8 bf16 channels) and walks down the rows, so the per-channel coefficients live in
 // registers and a warp touches 512 contiguous bytes per row.
-//   block (32, 8): x = channel vector, y = row lane;  grid (ceil(ld/8/32), ceil(R/kRowsPerBlock))
+//   block (32, 8): x = channel vector, y = row lane;  grid (ceil(ld/8/32), ceil(R/rows_per_block))
+// rows_per_block is picked on the host so that every layer width fills the machine: narrow layers
+// (256 channels = one block column) would otherwise launch fewer blocks than there are SMs x 2.
 // ---------------------------------------------------------------------------------------
-constexpr int kRowsPerBlock = 256;
 constexpr int kRowLanes = 8;
+constexpr int kWalkerBlocksTarget = 148 * 8;
+
+static inline int rows_per_block_for(int R, int ld) {
+    const long long cols = (ld / 8 + 31) / 32;
+    long long rpb = ((long long)R * cols + kWalkerBlocksTarget - 1) / kWalkerBlocksTarget;
+    rpb = (rpb + 31) / 32 * 32;
+    return (int)(rpb < 32 ? 32 : (rpb > 512 ? 512 : rpb));
+}
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -66,7 +75,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // reduce 2 x 8 per-thread partials over the row lanes, then one atomic per channel and statistic
-__device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8], int c0, int C, float* __restrict__ out) {
+// (mean, invstd given: the second statistic is centred first, q <- invstd * (q - mean * s))
+__device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8], int c0, int C, float* __restrict__ out,
+                                                    const float* __restrict__ mean = nullptr, const float* __restrict__ invstd = nullptr) {
     __shared__ float sm[kRowLanes][32][17];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -83,6 +94,7 @@ __device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8]
                 b += sm[y][threadIdx.x][8 + e];
             }
             if (c0 + e < C) {
+                if (mean != nullptr) b = invstd[c0 + e] * (b - mean[c0 + e] * a);
                 atomicAdd(out + c0 + e, a);
                 atomicAdd(out + C + c0 + e, b);
             }
@@ -92,7 +104,7 @@ __device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8]
 
 // per-channel sum / sum of squares of a bf16 [R, ld] matrix (R = B*t rows)
 __global__ void __launch_bounds__(256)
-colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float* __restrict__ out) {
+colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float* __restrict__ out, int kRowsPerBlock) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     float s[8], q[8];
@@ -143,7 +155,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float
 __global__ void __launch_bounds__(256)
 bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ ss, int B, int T, int C, int ld,
                        int act, float a, float bb, const float* __restrict__ xlen, __nv_bfloat16* __restrict__ out,
-                       float drop_p, const long long* __restrict__ seed_ptr, unsigned long long salt) {
+                       float drop_p, const long long* __restrict__ seed_ptr, unsigned long long salt, int kRowsPerBlock) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     if (c0 >= ld) return;
@@ -185,34 +197,35 @@ bn_act_mask_fwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restr
     }
 }
 
-// backward pass 1: per-channel sum(dz), sum(dz * xhat), dz = g * act'(z) * mask
+// backward pass 1: per-channel sum(dz), sum(dz * xhat), dz = g * act'(z) * mask.  The loop accumulates
+// sum(dz * y); xhat = (y - mean) * invstd is linear in y, so the block's partial is corrected once
+// at the end (sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz))) -- 16 fewer live registers.
 __global__ void __launch_bounds__(256)
 bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ g,
                          const float* __restrict__ ss, int B, int T, int C, int ld, int act, float a, float bb,
                          const float* __restrict__ xlen, float* __restrict__ out, float drop_p,
-                         const long long* __restrict__ seed_ptr, unsigned long long salt) {
+                         const long long* __restrict__ seed_ptr, unsigned long long salt, int kRowsPerBlock) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     float s[8], q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
     if (c0 < ld) {
-        float sc[8], sh[8], mu[8], is[8];
+        float sc[8], sh[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const bool ok = c0 + e < C;
             sc[e] = ok ? ss[c0 + e] : 0.f;
             sh[e] = ok ? ss[C + c0 + e] : 0.f;
-            mu[e] = ok ? ss[2 * C + c0 + e] : 0.f;
-            is[e] = ok ? ss[3 * C + c0 + e] : 0.f;
         }
         const int R = B * T;
         const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-        for (int r = r0 + threadIdx.y; r < r1; r += 2 * kRowLanes) {
-            uint4 yv[2], gv[2];
-            bool on[2];
+        constexpr int U = 4;  // 8 independent 16-byte loads in flight per thread
+        for (int r = r0 + threadIdx.y; r < r1; r += U * kRowLanes) {
+            uint4 yv[U], gv[U];
+            bool on[U];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int rr = r + u * kRowLanes;
                 const int b = rr / T, t = rr - b * T;
                 on[u] = rr < r1 && (xlen == nullptr || t < frac_len(__ldg(xlen + b), T));
@@ -220,7 +233,7 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
                 gv[u] = on[u] ? *reinterpret_cast<const uint4*>(g + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 if (!on[u]) continue;
                 float yf[8], gf[8];
                 unpack8(yv[u], yf);
@@ -236,12 +249,12 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat1
                 for (int e = 0; e < 8; ++e) {
                     const float dz = gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), act, a, bb);
                     s[e] += dz;
-                    q[e] = fmaf(dz, (yf[e] - mu[e]) * is[e], q[e]);
+                    q[e] = fmaf(dz, yf[e], q[e]);
                 }
             }
         }
     }
-    reduce_rows_and_add(s, q, c0, C, out);
+    reduce_rows_and_add(s, q, c0, C, out, ss + 2 * C, ss + 3 * C);
 }
 
 // backward pass 2: dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n) = scale*dz + k0 + k1*y
@@ -250,7 +263,7 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
                         const float* __restrict__ ss, const float* __restrict__ sums, float inv_n, int B, int T, int C,
                         int ld, int act, float a, float bb, const float* __restrict__ xlen,
                         __nv_bfloat16* __restrict__ dy, float drop_p, const long long* __restrict__ seed_ptr,
-                        unsigned long long salt) {
+                        unsigned long long salt, int kRowsPerBlock) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     if (c0 >= ld) return;
@@ -268,11 +281,11 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
     }
     const int R = B * T;
     const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
-    for (int r = r0 + threadIdx.y; r < r1; r += 2 * kRowLanes) {
-        uint4 yv[2], gv[2];
-        bool keep[2];
+    for (int r = r0 + threadIdx.y; r < r1; r += 4 * kRowLanes) {
+        uint4 yv[4], gv[4];
+        bool keep[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int rr = r + u * kRowLanes;
             const int b = rr / T, t = rr - b * T;
             keep[u] = rr < r1 && (xlen == nullptr || t < frac_len(__ldg(xlen + b), T));
@@ -280,7 +293,7 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
             gv[u] = keep[u] ? *reinterpret_cast<const uint4*>(g + (size_t)rr * ld + c0) : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int rr = r + u * kRowLanes;
             if (rr >= r1) break;
             float yf[8], gf[8], o[8];
@@ -300,6 +313,207 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16
             *reinterpret_cast<uint4*>(dy + (size_t)rr * ld + c0) = pack8(o);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Streamed versions of the three activation-sized kernels (the ones the training step uses).
+// The row walkers above keep at most 48-64 KB of loads in flight per SM (registers bound the
+// unroll), which measured 2.6-4.0 TB/s; HBM3e wants ~100 KB+ in flight per SM.  Here the loads
+// are decoupled from registers: a persistent CTA streams its chunks of FULL rows (contiguous in
+// the [R, ld] layout) through a ring of shared-memory stages with 1-D bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx), one elected thread issuing, everybody consuming.
+//   threads = vectors * lanes (vectors = ld/8 16-byte channel vectors per row); thread `tid` owns
+//   channel vector tid % vectors for the whole kernel (coefficients in registers) and touches the
+//   16-byte units tid, tid + threads, ... of every chunk: conflict-free smem reads, fully coalesced
+//   global writes.  A chunk is 4 * lanes rows; 2 CTAs per SM; stages fill ~100 KB per CTA.
+// ---------------------------------------------------------------------------------------
+constexpr int kStreamUnits = 4;        // 16-byte units per thread per chunk
+constexpr int kStreamMaxThreads = 512;
+constexpr int kBnSumReplicas = 8;      // atomics of the reduction are spread over this many copies
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct StreamArgs {
+    const __nv_bfloat16* y;
+    const __nv_bfloat16* g;    // grad w.r.t. the layer output (backward modes)
+    __nv_bfloat16* out;        // forward: activations; apply: grad_y
+    const float* ss;           // [4][C] scale, shift, mean, invstd
+    const float* xlen;
+    float* partials;           // [kBnSumReplicas][2][C]
+    float* sums;               // [2][C] totals (written by the apply pass)
+    const long long* seed_ptr;
+    unsigned long long salt;
+    float a, bb, drop_p, inv_n;
+    int B, T, C, ld, act;
+    int vectors, rows_per_chunk, n_chunks, stages, stage_bytes;
+};
+
+template <int MODE>  // 0: forward, 1: backward reduce, 2: backward apply
+__global__ void __launch_bounds__(kStreamMaxThreads)
+bn_stream_kernel(const StreamArgs p) {
+    constexpr int NIN = MODE == 0 ? 1 : 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.stages * NIN * p.stage_bytes);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int cv = tid % p.vectors, lane = tid / p.vectors, lanes = nthreads / p.vectors;
+    const int c0 = cv * 8, C = p.C, ld = p.ld, R = p.B * p.T;
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int stride = gridDim.x;
+    auto issue = [&](int chunk, int s) {
+        const int row0 = chunk * p.rows_per_chunk;
+        const uint32_t bytes = (uint32_t)(min(p.rows_per_chunk, R - row0) * ld) * 2u;
+        unsigned char* dst = smem_raw + (size_t)s * NIN * p.stage_bytes;
+        mbar_expect_tx(&full[s], bytes * NIN);
+        bulk_load_1d(dst, p.y + (size_t)row0 * ld, bytes, &full[s]);
+        if (NIN == 2) bulk_load_1d(dst + p.stage_bytes, p.g + (size_t)row0 * ld, bytes, &full[s]);
+    };
+    if (tid == 0)
+        for (int s = 0; s < p.stages; ++s)
+            if (blockIdx.x + s * stride < p.n_chunks) issue(blockIdx.x + s * stride, s);
+
+    // per-channel coefficients
+    float sc[8], sh[8], k0[8], k1[8], acc_s[8], acc_q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
+        const bool ok = c < C;
+        sc[e] = ok ? p.ss[c] : 0.f;
+        sh[e] = ok ? p.ss[C + c] : 0.f;
+        acc_s[e] = 0.f; acc_q[e] = 0.f; k0[e] = 0.f; k1[e] = 0.f;
+        if (MODE == 2) {
+            float m1 = 0.f, m2 = 0.f;
+            if (ok) {
+#pragma unroll
+                for (int r = 0; r < kBnSumReplicas; ++r) {
+                    m1 += p.partials[(size_t)r * 2 * C + c];
+                    m2 += p.partials[(size_t)r * 2 * C + C + c];
+                }
+                if (blockIdx.x == 0 && lane == 0) { p.sums[c] = m1; p.sums[C + c] = m2; }
+            }
+            const float mean = ok ? p.ss[2 * C + c] : 0.f, istd = ok ? p.ss[3 * C + c] : 0.f;
+            k1[e] = -sc[e] * (m2 * p.inv_n) * istd;          // coefficient of y
+            k0[e] = -sc[e] * (m1 * p.inv_n) - k1[e] * mean;  // constant term
+        }
+    }
+    const bool dropping = p.drop_p > 0.f;
+    const unsigned long long seed = dropping ? (unsigned long long)p.seed_ptr[0] + p.salt * 0xD1B54A32D192ED03ULL : 0ull;
+    const float inv_keep = dropping ? 1.f / (1.f - p.drop_p) : 1.f;
+
+    int it = 0;
+    for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += stride, ++it) {
+        const int s = it % p.stages;
+        mbar_wait(&full[s], (uint32_t)(it / p.stages) & 1u);
+        const unsigned char* src = smem_raw + (size_t)s * NIN * p.stage_bytes;
+        const int row0 = chunk * p.rows_per_chunk;
+#pragma unroll
+        for (int u = 0; u < kStreamUnits; ++u) {
+            const int rr = row0 + u * lanes + lane;
+            if (rr >= R) break;
+            const int b = rr / p.T, t = rr - b * p.T;
+            const bool keep = p.xlen == nullptr || t < frac_len(__ldg(p.xlen + b), p.T);
+            const size_t unit = (size_t)u * nthreads + tid;
+            if (MODE == 1 && !keep) continue;
+            float yf[8], o[8];
+            unpack8(*reinterpret_cast<const uint4*>(src + unit * 16), yf);
+            if (MODE == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (keep && c0 + e < C) ? act_fwd(fmaf(yf[e], sc[e], sh[e]), p.act, p.a, p.bb) : 0.f;
+                if (dropping) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, p.drop_p) ? o[e] * inv_keep : 0.f;
+                }
+            } else {
+                float gf[8];
+                unpack8(*reinterpret_cast<const uint4*>(src + p.stage_bytes + unit * 16), gf);
+                if (dropping) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) gf[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, p.drop_p) ? gf[e] * inv_keep : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    // padded rows may hold anything in g (nobody is required to write them): select, never multiply
+                    const float dz = keep ? gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), p.act, p.a, p.bb) : 0.f;
+                    if (MODE == 1) {
+                        acc_s[e] += dz;
+                        acc_q[e] = fmaf(dz, yf[e], acc_q[e]);
+                    } else {
+                        o[e] = fmaf(sc[e], dz, fmaf(k1[e], yf[e], k0[e]));
+                    }
+                }
+            }
+            if (MODE != 1) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.out) + ((size_t)row0 * ld * 2) + unit * 16) = pack8(o);
+        }
+        __syncthreads();  // everybody is done reading stage s
+        if (tid == 0 && chunk + p.stages * stride < p.n_chunks) issue(chunk + p.stages * stride, s);
+    }
+    if (MODE == 1) {
+        // every issued chunk was consumed, so the stages are free: reduce the 16 partials over the row lanes
+        float* red = reinterpret_cast<float*>(smem_raw);  // [lane][16][vectors]
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            red[((size_t)lane * 16 + e) * p.vectors + cv] = acc_s[e];
+            red[((size_t)lane * 16 + 8 + e) * p.vectors + cv] = acc_q[e];
+        }
+        __syncthreads();
+        if (lane == 0) {
+            float* dst = p.partials + (size_t)(blockIdx.x % kBnSumReplicas) * 2 * C;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float a_ = 0.f, b_ = 0.f;
+                for (int l = 0; l < lanes; ++l) {
+                    a_ += red[((size_t)l * 16 + e) * p.vectors + cv];
+                    b_ += red[((size_t)l * 16 + 8 + e) * p.vectors + cv];
+                }
+                const int c = c0 + e;
+                if (c < C) {
+                    // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)): linear, so per partial
+                    b_ = p.ss[3 * C + c] * (b_ - p.ss[2 * C + c] * a_);
+                    atomicAdd(dst + c, a_);
+                    atomicAdd(dst + C + c, b_);
+                }
+            }
+        }
+    }
+}
+
+// launch geometry of the streamed kernels; false = this row pitch is not covered (row walkers run)
+static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& threads, int& grid, size_t& smem) {
+    if (ld % 8 != 0 || R <= 0) return false;
+    const int vectors = ld / 8;
+    int lanes = (256 + vectors - 1) / vectors;
+    while ((vectors * lanes) % 32 != 0) ++lanes;
+    threads = vectors * lanes;
+    if (threads > kStreamMaxThreads) return false;
+    a.vectors = vectors;
+    a.rows_per_chunk = kStreamUnits * lanes;
+    a.n_chunks = (R + a.rows_per_chunk - 1) / a.rows_per_chunk;
+    a.stage_bytes = kStreamUnits * threads * 16;
+    int stages = (int)((100 * 1024) / ((size_t)n_inputs * a.stage_bytes));
+    a.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
+    smem = (size_t)a.stages * n_inputs * a.stage_bytes + 8 * a.stages;
+    if (smem < (size_t)threads * 64) smem = (size_t)threads * 64;  // the reduction scratch of the reduce pass
+    grid = a.n_chunks < 148 * 2 ? a.n_chunks : 148 * 2;
+    return true;
+}
+
+template <int MODE>
+static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, size_t smem, cudaStream_t stream) {
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    bn_stream_kernel<MODE><<<grid, threads, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -380,9 +594,9 @@ extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, co
     CAB_CHECK_ARG(y && ws_sums && out_ss, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout C=%d ld=%d", C, ld);
     CAB_CHECK_CUDA(cudaMemsetAsync(ws_sums, 0, sizeof(float) * 2 * C, stream));
-    const int R = B * T;
-    dim3 grid((ld / 8 + 31) / 32, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
-    colstats_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), R, C, ld, ws_sums);
+    const int R = B * T, rpb = rows_per_block_for(R, ld);
+    dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
+    colstats_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), R, C, ld, ws_sums, rpb);
     CAB_CHECK_LAUNCH();
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_sums, C, (float)R, gamma, beta, eps, momentum, running_mean, running_var, out_ss);
     CAB_CHECK_LAUNCH();
@@ -407,8 +621,20 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T,
     CAB_CHECK_ARG(y && ss && out, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
     CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
-    dim3 grid((ld / 8 + 31) / 32, (B * T + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
-    bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
+    StreamArgs sa{};
+    int threads, grid_s;
+    size_t smem;
+    if (stream_geometry(B * T, ld, 1, sa, threads, grid_s, smem)) {
+        sa.y = static_cast<const __nv_bfloat16*>(y); sa.out = static_cast<__nv_bfloat16*>(out); sa.ss = ss; sa.xlen = xlen_frac;
+        sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
+        sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+        CAB_CHECK_CUDA(stream_launch<0>(sa, threads, grid_s, smem, stream));
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return 0;
+    }
+    const int rpb = rows_per_block_for(B * T, ld);
+    dim3 grid((ld / 8 + 31) / 32, (B * T + rpb - 1) / rpb), block(32, kRowLanes);
+    bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -416,16 +642,35 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T,
 
 extern "C" int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld, int act,
                                    float act_a, float act_b, const float* xlen_frac, float* sums /*[2][C]: dbeta, dgamma*/,
-                                   void* grad_y, float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream_) {
+                                   void* grad_y, float dropout_p, const int64_t* seed, int64_t salt, float* ws_partials,
+                                   cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
+    CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    {
+        StreamArgs sa{};
+        int threads, grid_s;
+        size_t smem;
+        if (ws_partials != nullptr && stream_geometry(B * T, ld, 2, sa, threads, grid_s, smem)) {
+            sa.y = static_cast<const __nv_bfloat16*>(y); sa.g = static_cast<const __nv_bfloat16*>(grad_out);
+            sa.out = static_cast<__nv_bfloat16*>(grad_y); sa.ss = ss; sa.xlen = xlen_frac; sa.partials = ws_partials; sa.sums = sums;
+            sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
+            sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.inv_n = 1.f / (float)(B * T);
+            sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+            CAB_CHECK_CUDA(cudaMemsetAsync(ws_partials, 0, sizeof(float) * kBnSumReplicas * 2 * C, stream));
+            CAB_CHECK_CUDA(stream_launch<1>(sa, threads, grid_s, smem, stream));
+            CAB_CHECK_CUDA(stream_launch<2>(sa, threads, grid_s, smem, stream));
+            g_launch_count.fetch_add(2, std::memory_order_relaxed);
+            return 0;
+        }
+    }
     CAB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
-    const int R = B * T;
-    dim3 grid((ld / 8 + 31) / 32, (R + kRowsPerBlock - 1) / kRowsPerBlock), block(32, kRowLanes);
-    bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
+    const int R = B * T, rpb = rows_per_block_for(R, ld);
+    dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
+    bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
     CAB_CHECK_LAUNCH();
-    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt);
+    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return 0;

@@ -176,6 +176,7 @@ class NativeStack(torch.autograd.Function):
 		sync = getattr(model, '_grad_sync', None)
 		small = torch.zeros(c_ld + sum(2 * L.C_out for L in layers), dtype = torch.float32, device = dev)
 		small_off = c_ld
+		partials = torch.empty(_lib.BN_SUM_REPLICAS * 2 * max(L.C_out for L in layers), dtype = torch.float32, device = dev)  # scratch of the BN backward sums
 		d_bias = small[:C] if dec.bias is not None else None
 		rc = lib.cab_bct_to_btc(ops._p(g), B, C, T, c_ld, ops._p(g_cl), ops._p(d_bias), ops._stream())
 		_lib.check(rc, 'cab_bct_to_btc')
@@ -199,7 +200,7 @@ class NativeStack(torch.autograd.Function):
 			sums = small[small_off:small_off + 2 * L.C_out].view(2, L.C_out)
 			small_off += 2 * L.C_out
 			dy = torch.empty_like(y)
-			rc = lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(gx), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(sums), ops._p(dy), L.dropout, ops._p(ctx.seed), li, ops._stream())
+			rc = lib.cab_bn_act_mask_bwd(ops._p(y), ops._p(gx), ops._p(ss), B, T_out, L.C_out, L.co_alloc, code, a, b, ops._p(xlen if L.mask else None), ops._p(sums), ops._p(dy), L.dropout, ops._p(ctx.seed), li, ops._p(partials), ops._stream())
 			_lib.check(rc, 'cab_bn_act_mask_bwd')
 			grads[L.bn.bias] = sums[0]
 			grads[L.bn.weight] = sums[1]

@@ -151,7 +151,11 @@ int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total
  *                        dz = grad_out * act'(z) * mask  (hardtanh: a < z < b strictly).
  *   dropout_p > 0 applies F.dropout after the activation (ResidualActivation.forward, models.py:357-371):
  *   out *= keep / (1 - p) with a counter-based keep decision from (*seed, salt, element index) that
- *   the backward recomputes; *seed lives in device memory so CUDA-graph replays draw new masks. */
+ *   the backward recomputes; *seed lives in device memory so CUDA-graph replays draw new masks.
+ *   Both are HBM-bound streaming kernels: persistent CTAs pull whole rows through shared-memory stages
+ *   with bulk async copies.  The backward's channel sums are accumulated in CAB_BN_SUM_REPLICAS copies
+ *   (ws_partials) to keep same-address atomics short; with ws_partials == NULL a slower variant runs. */
+#define CAB_BN_SUM_REPLICAS 8
 int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var,
                        float* ws_sums, float* out_ss, cab_stream_t stream);
@@ -165,6 +169,7 @@ int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int
 int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld,
                         int act, float act_a, float act_b, const float* xlen_frac, float* sums,
                         void* grad_y, float dropout_p, const int64_t* seed, int64_t salt,
+                        float* ws_partials /* fp32 [CAB_BN_SUM_REPLICAS][2][C] scratch, or NULL */,
                         cab_stream_t stream);
 /* fp32 [Co,Ci,K] -> bf16 tap-major [K,Co,ci_ld] (forward operand) and/or [K,Ci,co_ld] with flipped
  * taps (dgrad operand); and the inverse for a packed fp32 gradient ([K,Co,ld] or, transposed,

@@ -312,3 +312,31 @@ def test_cuda_graph_forward_equals_eager(golden, dev):
 	assert torch.equal(eager['logits'][0], g1['logits'][0]) and torch.equal(g1['logits'][0], g2['logits'][0])
 	assert torch.equal(other['logits'][0], eager['logits'][0].roll(1, 0))
 	assert torch.equal(g1['log_probs'][0]._convasr_argmax, eager['log_probs'][0]._convasr_argmax)
+
+
+@pytest.mark.parametrize('C_in,C_out,groups,k', [(256, 256, 128, 11), (256, 384, 128, 13), (384, 384, 128, 13), (640, 768, 128, 25), (96, 160, 32, 17), (64, 64, 32, 5), (40, 40, 8, 19), (64, 64, 16, 31)])
+def test_grouped_conv_relu_kernel(dev, C_in, C_out, groups, k):
+	"""First stage of the separable ConvSamePadding (models.py:50-64): grouped Conv1d + bias + ReLU, both
+	precision tiers, odd channels per group, padded row pitches, ragged tile ends; k = 31 takes the generic kernel."""
+	from convasr_b200 import ops
+	g = torch.Generator().manual_seed(C_in + k)
+	B, T = 3, 77
+	ld_in, ld_out = (C_in + 63) // 64 * 64, (C_out + 63) // 64 * 64
+	x = torch.randn(B, C_in, T, generator = g)
+	w = torch.randn(C_out, C_in // groups, k, generator = g) / (k * C_in / groups) ** 0.5
+	bias = torch.randn(C_out, generator = g) * 0.1
+	hi = x.to(torch.bfloat16)
+	lo = (x - hi.float()).to(torch.bfloat16)
+
+	def cl(t):  # [B, C, T] -> channels-last with a zero-padded pitch and two spare rows
+		out = torch.zeros(B, T + 2, ld_in, dtype = torch.bfloat16)
+		out[:, :T, :C_in] = t.permute(0, 2, 1)
+		return out.to(dev)
+
+	for tier, xin, tol in (('bf16', hi.float(), 5e-3), ('fp32', hi.float() + lo.float(), 2e-5)):
+		ref = torch.nn.functional.conv1d(xin.double(), w.double(), bias.double(), padding = k // 2, groups = groups).relu()
+		o_hi, o_lo = ops.grouped_conv1d_relu(cl(hi), T, C_in, w.to(dev), bias.to(dev), groups, k // 2, ld_out = ld_out, act_lo = cl(lo) if tier == 'fp32' else None, want_lo = tier == 'fp32')
+		got = o_hi.float() + (o_lo.float() if o_lo is not None else 0)
+		assert got.shape == (B, T, ld_out)
+		assert rel(got[:, :, :C_out].permute(0, 2, 1), ref) < tol, (tier, rel(got[:, :, :C_out].permute(0, 2, 1), ref))
+		assert float(got[:, :, C_out:].abs().max()) == 0.0 if ld_out > C_out else True

@@ -60,8 +60,8 @@ def test_bn_act_mask_forward_backward_kernels():
 		out = torch.empty_like(yd)
 		xl = xlen.to(dev)
 		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), 0.0, None, 0, ops._stream()), 'fwd')
-		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd)
-		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._stream()), 'bwd')
+		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._p(part), ops._stream()), 'bwd')
 		torch.cuda.synchronize()
 		assert rel(out.float().permute(0, 2, 1), o) < 4e-3, act_name  # bf16 output rounding
 		assert torch.allclose(rm_d.cpu(), rm_ref, atol = 1e-5) and torch.allclose(rv_d.cpu(), rv_ref, rtol = 1e-4, atol = 1e-5)
@@ -101,8 +101,8 @@ def test_dropout_in_bn_act_kernels():
 	# backward against autograd with the recovered mask
 	mask = torch.where(pos, (outs[0] != 0).float(), torch.ones_like(z)) / (1 - p)  # where z ~ 0 the mask is irrelevant
 	(z * mask).backward(go)
-	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd)
-	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), p, ops._p(seed), 3, ops._stream()), 'bwd')
+	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), p, ops._p(seed), 3, ops._p(part), ops._stream()), 'bwd')
 	torch.cuda.synchronize()
 	assert rel(dy.float().permute(0, 2, 1), yr.grad) < 2e-2
 

@@ -1,5 +1,6 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel totals and the
-per-step share of each kernel over the LAST complete device step (frontend .. ctc_grad_scatter)."""
+per-step share of each kernel over the LAST complete device step (frontend .. ctc_grad_scatter for the
+inference workload, frontend .. mt_update_kernel for a training step)."""
 import collections
 import csv
 import sys
@@ -26,9 +27,10 @@ def short(name):
 def main(path):
 	rows = load(path)
 	print(f'# {len(rows)} launches in {path}')
-	# last complete step: from the last absmax launch that is followed by a ctc_grad_scatter
+	# last complete step: from the last absmax launch that is followed by the step's final kernel
+	end_name = sys.argv[2] if len(sys.argv) > 2 else ('mt_update_kernel' if any('mt_update_kernel' in r[0] for r in rows) else 'ctc_grad_scatter')
 	starts = [i for i, r in enumerate(rows) if 'absmax' in r[0]]
-	ends = [i for i, r in enumerate(rows) if 'ctc_grad_scatter' in r[0]]
+	ends = [i for i, r in enumerate(rows) if end_name in r[0]]
 	step = None
 	for s in reversed(starts):
 		e = [x for x in ends if x > s]
@@ -50,12 +52,12 @@ def main(path):
 	print('| kernel | launches | total us | share |\n|---|---|---|---|')
 	for k, (n, t) in sorted(agg.items(), key = lambda kv: -kv[1][1]):
 		print(f'| {k} | {n} | {t:.1f} | {t / tot * 100:.1f}% |')
-	print('\n### conv1d_umma_kernel launches in step order\n')
-	print('| # | grid | us |\n|---|---|---|')
+	print('\n### tensor-pipe kernel launches in step order\n')
+	print('| # | kernel | grid | us |\n|---|---|---|---|')
 	i = 0
 	for name, grid, block, us in seg:
-		if 'conv1d_umma' in name:
-			print(f'| {i} | {grid} | {us:.1f} |')
+		if 'conv1d_umma' in name or 'wgrad_umma' in name:
+			print(f'| {i} | {short(name)} | {grid} | {us:.1f} |')
 			i += 1
 
 
