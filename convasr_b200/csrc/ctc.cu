@@ -233,12 +233,21 @@ __global__ void ctc_grad_init_kernel(const float* __restrict__ lp, int64_t st, i
                                      const int64_t* __restrict__ in_len, const float* __restrict__ go,
                                      int B, int T, int C, float* __restrict__ grad, int64_t gt, int64_t gb,
                                      int64_t gc) {
+    if (gt == 1) {  // [B, C, T]-like (the model's layout): one (b, c) row of T frames at a time, no per-element division
+        for (int row = blockIdx.x; row < B * C; row += gridDim.x) {
+            const int b = row / C, c = row - b * C;
+            const int il = (int)in_len[b];
+            const float g0 = go[b];
+            const float* src = lp + (int64_t)b * sb + (int64_t)c * sc;
+            float* dst = grad + (int64_t)b * gb + (int64_t)c * gc;
+            for (int t = threadIdx.x; t < T; t += blockDim.x) dst[t] = t < il ? expf(src[(int64_t)t * st]) * g0 : 0.f;
+        }
+        return;
+    }
     const int64_t n = (int64_t)B * T * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int b, c, t;
-        if (gt == 1) {  // [B, C, T]-like: t fastest
-            t = (int)(i % T); c = (int)((i / T) % C); b = (int)(i / ((int64_t)T * C));
-        } else {        // c fastest
+        {               // c fastest
             c = (int)(i % C); const int64_t r = i / C;
             if (gb < gt) { b = (int)(r % B); t = (int)(r / B); } else { t = (int)(r % T); b = (int)(r / T); }
         }
@@ -396,11 +405,20 @@ log_softmax_argmax_kernel(const float* __restrict__ x, int B, int C, int T, floa
     float m = -INFINITY, s = 0.f;
     int im = 0x7fffffff;
     if (ok) {
-        for (int c = grp; c < C; c += 8) {
-            const float v = xb[(size_t)c * T + t];
-            if (v > m) { s = s * expf(m - v) + 1.f; m = v; im = c; }
-            else if (v == -INFINITY && m == -INFINITY) { if (im == 0x7fffffff) im = c; }
-            else s += expf(v - m);
+        // 4 independent loads in flight per thread (a vocabulary of 5000 is 625 dependent updates otherwise)
+        for (int c0 = grp; c0 < C; c0 += 32) {
+            float v4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v4[u] = c0 + 8 * u < C ? xb[(size_t)(c0 + 8 * u) * T + t] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 8 * u;
+                if (c >= C) break;
+                const float v = v4[u];
+                if (v > m) { s = s * expf(m - v) + 1.f; m = v; im = c; }
+                else if (v == -INFINITY && m == -INFINITY) { if (im == 0x7fffffff) im = c; }
+                else s += expf(v - m);
+            }
         }
     }
     s_m[grp][lane] = m; s_s[grp][lane] = s; s_i[grp][lane] = im;
@@ -421,7 +439,14 @@ log_softmax_argmax_kernel(const float* __restrict__ x, int B, int C, int T, floa
     if (ok) {
         if (out != nullptr) {
             float* ob = out + (size_t)b * C * T;
-            for (int c = grp; c < C; c += 8) ob[(size_t)c * T + t] = xb[(size_t)c * T + t] - lse;
+            for (int c0 = grp; c0 < C; c0 += 32) {
+                float v4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v4[u] = c0 + 8 * u < C ? xb[(size_t)(c0 + 8 * u) * T + t] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + 8 * u < C) ob[(size_t)(c0 + 8 * u) * T + t] = v4[u] - lse;
+            }
         }
         if (amax != nullptr && grp == 0) amax[(size_t)b * T + t] = IM == 0x7fffffff ? 0 : IM;
     }

@@ -23,11 +23,11 @@ extern std::atomic<int64_t> g_launch_count;
 
 constexpr int kGcCo = 64;       // output channels per CTA
 constexpr int kGcStrips = 4;    // frame strips per tile
-constexpr int kGcTT = 8;        // frames per strip (register blocking)
+constexpr int kGcTT = 16;       // frames per strip (register blocking)
 constexpr int kGcTile = kGcStrips * kGcTT;
 constexpr int kGcThreads = kGcCo * kGcStrips;
 constexpr int kGcMaxCols = 104;  // tile width in input channels (multiple of 8)
-constexpr int kGcMaxVec = 3;     // 16-byte prefetch vectors per thread and tensor
+constexpr int kGcMaxVec = 5;    // 16-byte prefetch vectors per thread and tensor
 
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
@@ -56,7 +56,7 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
     const int cin_g = p.C_in / p.groups, cout_g = p.C_out / p.groups;
     const int n_jp = (cin_g + 1) / 2;
     float2* ws = reinterpret_cast<float2*>(smem_raw);                       // [n_jp][K][kGcCo]
-    float* xs = reinterpret_cast<float*>(smem_raw + sizeof(float2) * n_jp * K * kGcCo);  // [kRows][cols + 1]
+    float* xs = reinterpret_cast<float*>(smem_raw + sizeof(float2) * n_jp * K * kGcCo);  // [kRows][cols]
 
     const int tid = threadIdx.x;
     const int co_l = tid % kGcCo, strip = tid / kGcCo;
@@ -69,7 +69,7 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
     const int ci_end = co_last >= cb * kGcCo ? (co_last / cout_g + 1) * cin_g + 1 : 8;  // +1: pad channel of an odd cin_g
     const int ci_lo = ci_first & ~7;
     const int cols = ((ci_end - ci_lo + 7) & ~7);
-    const int pitch = cols + 1;
+    const int pitch = cols;  // reads of one instruction stay inside one row, so no padding column is needed
     const int n_vec = cols / 8;
 
     // weights -> smem, paired over input channels: ws[jp][k][co] = (w[co][2jp][k], w[co][2jp+1][k] or 0)
@@ -116,13 +116,16 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
                 const uint32_t h[4] = {pre_hi[v].x, pre_hi[v].y, pre_hi[v].z, pre_hi[v].w};
                 const uint4 lv = HAS_LO ? pre_lo[v] : make_uint4(0, 0, 0, 0);
                 const uint32_t l[4] = {lv.x, lv.y, lv.z, lv.w};
-                float* dst = xs + r * pitch + cvec * 8;
+                float4* dst = reinterpret_cast<float4*>(xs + r * pitch + cvec * 8);
+                float f[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     // bf16 -> fp32 is a 16-bit shift; hi + lo restores the split-bf16 ("fp32 tier") value
-                    dst[2 * q] = __uint_as_float(h[q] << 16) + __uint_as_float(l[q] << 16);
-                    dst[2 * q + 1] = __uint_as_float(h[q] & 0xffff0000u) + __uint_as_float(l[q] & 0xffff0000u);
+                    f[2 * q] = __uint_as_float(h[q] << 16) + __uint_as_float(l[q] << 16);
+                    f[2 * q + 1] = __uint_as_float(h[q] & 0xffff0000u) + __uint_as_float(l[q] & 0xffff0000u);
                 }
+                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
+                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
             }
         }
     };
@@ -174,7 +177,7 @@ template <int K, bool HAS_LO>
 static int launch_grouped_t(const GroupedArgs& a, int n_cb, int cols_max, cudaStream_t stream) {
     const int cin_g = a.C_in / a.groups;
     const int n_jp = (cin_g + 1) / 2;
-    const size_t smem = sizeof(float2) * n_jp * K * kGcCo + sizeof(float) * (kGcTile + K - 1) * (cols_max + 1);
+    const size_t smem = sizeof(float2) * n_jp * K * kGcCo + sizeof(float) * (kGcTile + K - 1) * cols_max;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_ffma2_kernel<K, HAS_LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -209,7 +212,7 @@ int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_r
     }
     if (cols_max > kGcMaxCols) return 1;
     if ((kGcTile + k - 1) * (cols_max / 8) > kGcMaxVec * kGcThreads) return 1;
-    const size_t smem = sizeof(float2) * ((cin_g + 1) / 2) * k * kGcCo + sizeof(float) * (kGcTile + k - 1) * (cols_max + 1);
+    const size_t smem = sizeof(float2) * ((cin_g + 1) / 2) * k * kGcCo + sizeof(float) * (kGcTile + k - 1) * cols_max;
     if (smem > 100 * 1024) return 1;
     GroupedArgs a{};
     a.x = static_cast<const __nv_bfloat16*>(act); a.x_lo = static_cast<const __nv_bfloat16*>(act_lo); a.w = wgt; a.bias = bias;
@@ -218,7 +221,9 @@ int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_r
     a.groups = groups; a.pad = pad_left;
     a.tiles_per_utt = (T + kGcTile - 1) / kGcTile;
     a.n_items = B * a.tiles_per_utt;
-    int parts = (148 * 2 + n_cb - 1) / n_cb;
+    // one wave: every CTA must be resident at once (2 per SM), a 297th CTA would run alone afterwards
+    int parts = (148 * 2) / n_cb;
+    parts = parts < 1 ? 1 : parts;
     a.parts = parts < a.n_items ? parts : a.n_items;
     switch (k) {
         case 3: return launch_grouped<3>(a, n_cb, cols_max, stream);
