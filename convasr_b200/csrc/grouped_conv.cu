@@ -11,9 +11,9 @@
 //
 //   CTA  = one block of 64 output channels x a persistent loop over (utterance, 32-frame) tiles
 //   thread = (output channel, strip of 8 frames); accumulators: 8 x float2 (even / odd input channel)
-//   x tile: the input channels those 64 outputs need (<= 96), 32 + K - 1 frames, fp32 in smem
-//           (hi + lo bf16 summed while staging); the next tile's global loads are in flight during
-//           the current tile's math.
+//   x tile: the input channels those 64 outputs need (<= 104), 64 + K - 1 frames, raw bf16 in smem,
+//           double buffered with cp.async (zero fill = conv padding): the next tile lands during
+//           the current tile's math; bf16 -> fp32 is a shift at load time.
 #include "common.cuh"
 #include "../../include/convasr_b200.h"
 #include <atomic>
@@ -44,19 +44,40 @@ struct GroupedArgs {
     __nv_bfloat16* out;
     __nv_bfloat16* out_lo;
     int B, T, T_rows, C_in, ld_in, C_out, ld_out, out_T_rows, groups, pad;
-    int tiles_per_utt, n_items, parts;
+    int tiles_per_utt, n_items, parts, cols_max;
 };
 
-template <int K, bool HAS_LO>
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;  // src-size 0: the 16 bytes are zero-filled (conv padding, rows outside [0, T))
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// two adjacent bf16 channels -> float2; ALIGNED: the pair sits in one 32-bit word
+template <bool ALIGNED>
+__device__ __forceinline__ float2 load_pair(const unsigned char* p) {
+    if (ALIGNED) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+        return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    }
+    const uint32_t a = *reinterpret_cast<const unsigned short*>(p), b = *reinterpret_cast<const unsigned short*>(p + 2);
+    return make_float2(__uint_as_float(a << 16), __uint_as_float(b << 16));
+}
+
+template <int K, bool HAS_LO, bool ALIGNED>
 __global__ void __launch_bounds__(kGcThreads, 2)
 grouped_conv_ffma2_kernel(const GroupedArgs p) {
     constexpr int kRows = kGcTile + K - 1;   // frames in the x tile
     constexpr int kWin = kGcTT + K - 1;      // frames one thread slides over
+    constexpr int NT = HAS_LO ? 2 : 1;       // tensors per tile (hi, lo)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cin_g = p.C_in / p.groups, cout_g = p.C_out / p.groups;
     const int n_jp = (cin_g + 1) / 2;
-    float2* ws = reinterpret_cast<float2*>(smem_raw);                       // [n_jp][K][kGcCo]
-    float* xs = reinterpret_cast<float*>(smem_raw + sizeof(float2) * n_jp * K * kGcCo);  // [kRows][cols]
+    float2* ws = reinterpret_cast<float2*>(smem_raw);                                  // [n_jp][K][kGcCo]
+    unsigned char* xs = smem_raw + sizeof(float2) * n_jp * K * kGcCo;                  // [2 buffers][NT][kRows][cols] bf16
+    constexpr int tile_bytes = kRows * kGcMaxCols * 2;
 
     const int tid = threadIdx.x;
     const int co_l = tid % kGcCo, strip = tid / kGcCo;
@@ -69,8 +90,8 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
     const int ci_end = co_last >= cb * kGcCo ? (co_last / cout_g + 1) * cin_g + 1 : 8;  // +1: pad channel of an odd cin_g
     const int ci_lo = ci_first & ~7;
     const int cols = ((ci_end - ci_lo + 7) & ~7);
-    const int pitch = cols;  // reads of one instruction stay inside one row, so no padding column is needed
     const int n_vec = cols / 8;
+    constexpr int pitch = kGcMaxCols * 2;  // bytes, compile-time: the window loads below use immediate offsets
 
     // weights -> smem, paired over input channels: ws[jp][k][co] = (w[co][2jp][k], w[co][2jp+1][k] or 0)
     for (int i = tid; i < n_jp * K * kGcCo; i += kGcThreads) {
@@ -86,68 +107,51 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
     const float bv = (live && p.bias) ? p.bias[co] : 0.f;
     const int col0 = live ? (co / cout_g) * cin_g - ci_lo : 0;
 
-    // software pipeline: prefetch registers for the next x tile
-    uint4 pre_hi[kGcMaxVec], pre_lo[HAS_LO ? kGcMaxVec : 1];
     const int total_vec = kRows * n_vec;
-    auto prefetch = [&](int item) {
+    auto issue = [&](int item, int buf) {
         const int b = item / p.tiles_per_utt, t0 = (item - b * p.tiles_per_utt) * kGcTile;
+        const uint32_t base = smem_u32(xs) + buf * NT * tile_bytes;
 #pragma unroll
         for (int v = 0; v < kGcMaxVec; ++v) {
             const int idx = tid + v * kGcThreads;
-            pre_hi[v] = make_uint4(0, 0, 0, 0);
-            if (HAS_LO) pre_lo[v] = make_uint4(0, 0, 0, 0);
-            if (idx < total_vec) {
-                const int r = idx / n_vec, cvec = idx - r * n_vec;
-                const int u = t0 - p.pad + r, ch = ci_lo + cvec * 8;
-                if (u >= 0 && u < p.T && ch < p.ld_in) {
-                    const size_t off = ((size_t)b * p.T_rows + u) * p.ld_in + ch;
-                    pre_hi[v] = *reinterpret_cast<const uint4*>(p.x + off);
-                    if (HAS_LO) pre_lo[v] = *reinterpret_cast<const uint4*>(p.x_lo + off);
-                }
-            }
+            if (idx >= total_vec) break;
+            const int r = idx / n_vec, cvec = idx - r * n_vec;
+            const int u = t0 - p.pad + r, ch = ci_lo + cvec * 8;
+            const bool ok = u >= 0 && u < p.T && ch < p.ld_in;
+            const size_t off = ok ? ((size_t)b * p.T_rows + u) * p.ld_in + ch : 0;
+            const uint32_t dst = base + r * pitch + cvec * 16;
+            cp_async_16(dst, p.x + off, ok);
+            if (HAS_LO) cp_async_16(dst + tile_bytes, p.x_lo + off, ok);
         }
-    };
-    auto stage = [&]() {
-#pragma unroll
-        for (int v = 0; v < kGcMaxVec; ++v) {
-            const int idx = tid + v * kGcThreads;
-            if (idx < total_vec) {
-                const int r = idx / n_vec, cvec = idx - r * n_vec;
-                const uint32_t h[4] = {pre_hi[v].x, pre_hi[v].y, pre_hi[v].z, pre_hi[v].w};
-                const uint4 lv = HAS_LO ? pre_lo[v] : make_uint4(0, 0, 0, 0);
-                const uint32_t l[4] = {lv.x, lv.y, lv.z, lv.w};
-                float4* dst = reinterpret_cast<float4*>(xs + r * pitch + cvec * 8);
-                float f[8];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    // bf16 -> fp32 is a 16-bit shift; hi + lo restores the split-bf16 ("fp32 tier") value
-                    f[2 * q] = __uint_as_float(h[q] << 16) + __uint_as_float(l[q] << 16);
-                    f[2 * q + 1] = __uint_as_float(h[q] & 0xffff0000u) + __uint_as_float(l[q] & 0xffff0000u);
-                }
-                dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-                dst[1] = make_float4(f[4], f[5], f[6], f[7]);
-            }
-        }
+        cp_async_commit();
     };
 
-    int item = part;
-    if (item < p.n_items) prefetch(item);
-    for (; item < p.n_items; item += p.parts) {
-        __syncthreads();  // the previous tile's readers are done (also orders the weight fill on the first pass)
-        stage();
-        __syncthreads();
-        if (item + p.parts < p.n_items) prefetch(item + p.parts);
+    int item = part, buf = 0;
+    if (item < p.n_items) issue(item, 0);
+    for (; item < p.n_items; item += p.parts, buf ^= 1) {
+        const bool more = item + p.parts < p.n_items;
+        if (more) issue(item + p.parts, buf ^ 1);  // lands while this tile is being computed
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();  // tile `buf` is complete for everybody (and, first pass, so are the weights)
 
         const int b = item / p.tiles_per_utt, t0 = (item - b * p.tiles_per_utt) * kGcTile;
         float2 acc[kGcTT];
 #pragma unroll
         for (int i = 0; i < kGcTT; ++i) acc[i] = make_float2(bv, 0.f);
         if (live) {
+            const unsigned char* xt = xs + buf * NT * tile_bytes + (strip * kGcTT) * pitch + col0 * 2;
             for (int jp = 0; jp < n_jp; ++jp) {
-                const float* xr = xs + (strip * kGcTT) * pitch + col0 + 2 * jp;
+                const unsigned char* xr = xt + jp * 4;
                 float2 xw[kWin];
 #pragma unroll
-                for (int m = 0; m < kWin; ++m) xw[m] = make_float2(xr[m * pitch], xr[m * pitch + 1]);
+                for (int m = 0; m < kWin; ++m) {
+                    xw[m] = load_pair<ALIGNED>(xr + m * pitch);
+                    if (HAS_LO) {  // split-bf16 ("fp32 tier"): value = hi + lo
+                        const float2 l = load_pair<ALIGNED>(xr + tile_bytes + m * pitch);
+                        xw[m].x += l.x;
+                        xw[m].y += l.y;
+                    }
+                }
                 const float2* wr = ws + (size_t)jp * K * kGcCo + co_l;
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
@@ -158,40 +162,47 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
             }
         }
         if (co < p.ld_out) {
+            const int t_first = t0 + strip * kGcTT;
+            __nv_bfloat16* o_hi = p.out + ((size_t)b * p.out_T_rows + t_first) * p.ld_out + co;
+            __nv_bfloat16* o_lo = HAS_LO && p.out_lo ? p.out_lo + ((size_t)b * p.out_T_rows + t_first) * p.ld_out + co : nullptr;
+            const int n_t = min(kGcTT, p.T - t_first);
 #pragma unroll
             for (int i = 0; i < kGcTT; ++i) {
-                const int t = t0 + strip * kGcTT + i;
-                if (t < p.T) {
-                    const size_t o = ((size_t)b * p.out_T_rows + t) * p.ld_out + co;
+                if (i < n_t) {
                     const float v = live ? fmaxf(acc[i].x + acc[i].y, 0.f) : 0.f;  // padding channels: zeros (the pointwise GEMM contracts over them)
                     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                    p.out[o] = h;
-                    if (p.out_lo) p.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                    o_hi[i * p.ld_out] = h;
+                    if (HAS_LO && o_lo) o_lo[i * p.ld_out] = __float2bfloat16_rn(v - __bfloat162float(h));
                 }
             }
         }
+        __syncthreads();  // everybody is done with tile `buf` before the next iteration refills it
     }
 }
 
-template <int K, bool HAS_LO>
-static int launch_grouped_t(const GroupedArgs& a, int n_cb, int cols_max, cudaStream_t stream) {
-    const int cin_g = a.C_in / a.groups;
-    const int n_jp = (cin_g + 1) / 2;
-    const size_t smem = sizeof(float2) * n_jp * K * kGcCo + sizeof(float) * (kGcTile + K - 1) * cols_max;
+static size_t grouped_smem_bytes(int cin_g, int K, int cols_max, bool has_lo) {
+    return sizeof(float2) * ((cin_g + 1) / 2) * K * kGcCo + (size_t)2 * (has_lo ? 2 : 1) * (kGcTile + K - 1) * kGcMaxCols * 2;
+}
+
+template <int K, bool HAS_LO, bool ALIGNED>
+static int launch_grouped_t(const GroupedArgs& a, int n_cb, cudaStream_t stream) {
+    const size_t smem = grouped_smem_bytes(a.C_in / a.groups, K, a.cols_max, HAS_LO);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_ffma2_kernel<K, HAS_LO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_ffma2_kernel<K, HAS_LO, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    grouped_conv_ffma2_kernel<K, HAS_LO><<<dim3(n_cb, a.parts), kGcThreads, smem, stream>>>(a);
+    grouped_conv_ffma2_kernel<K, HAS_LO, ALIGNED><<<dim3(n_cb, a.parts), kGcThreads, smem, stream>>>(a);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
 template <int K>
-static int launch_grouped(const GroupedArgs& a, int n_cb, int cols_max, cudaStream_t stream) {
-    return a.x_lo ? launch_grouped_t<K, true>(a, n_cb, cols_max, stream) : launch_grouped_t<K, false>(a, n_cb, cols_max, stream);
+static int launch_grouped(const GroupedArgs& a, int n_cb, cudaStream_t stream) {
+    const bool aligned = (a.C_in / a.groups) % 2 == 0;
+    if (a.x_lo) return aligned ? launch_grouped_t<K, true, true>(a, n_cb, stream) : launch_grouped_t<K, true, false>(a, n_cb, stream);
+    return aligned ? launch_grouped_t<K, false, true>(a, n_cb, stream) : launch_grouped_t<K, false, false>(a, n_cb, stream);
 }
 
 // returns 1 when this shape is not covered (caller runs the generic kernel), 0 on launch, < 0 on error
@@ -212,33 +223,34 @@ int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_r
     }
     if (cols_max > kGcMaxCols) return 1;
     if ((kGcTile + k - 1) * (cols_max / 8) > kGcMaxVec * kGcThreads) return 1;
-    const size_t smem = sizeof(float2) * ((cin_g + 1) / 2) * k * kGcCo + sizeof(float) * (kGcTile + k - 1) * cols_max;
-    if (smem > 100 * 1024) return 1;
+    const size_t smem = grouped_smem_bytes(cin_g, k, cols_max, act_lo != nullptr);
+    if (smem > 200 * 1024) return 1;
+    const int ctas_per_sm = smem > 113 * 1024 ? 1 : 2;
     GroupedArgs a{};
     a.x = static_cast<const __nv_bfloat16*>(act); a.x_lo = static_cast<const __nv_bfloat16*>(act_lo); a.w = wgt; a.bias = bias;
     a.out = static_cast<__nv_bfloat16*>(out); a.out_lo = static_cast<__nv_bfloat16*>(out_lo);
     a.B = B; a.T = T; a.T_rows = T_rows; a.C_in = C_in; a.ld_in = ld_in; a.C_out = C_out; a.ld_out = ld_out; a.out_T_rows = out_T_rows;
-    a.groups = groups; a.pad = pad_left;
+    a.groups = groups; a.pad = pad_left; a.cols_max = cols_max;
     a.tiles_per_utt = (T + kGcTile - 1) / kGcTile;
     a.n_items = B * a.tiles_per_utt;
     // one wave: every CTA must be resident at once (2 per SM), a 297th CTA would run alone afterwards
-    int parts = (148 * 2) / n_cb;
+    int parts = (148 * ctas_per_sm) / n_cb;
     parts = parts < 1 ? 1 : parts;
     a.parts = parts < a.n_items ? parts : a.n_items;
     switch (k) {
-        case 3: return launch_grouped<3>(a, n_cb, cols_max, stream);
-        case 5: return launch_grouped<5>(a, n_cb, cols_max, stream);
-        case 7: return launch_grouped<7>(a, n_cb, cols_max, stream);
-        case 9: return launch_grouped<9>(a, n_cb, cols_max, stream);
-        case 11: return launch_grouped<11>(a, n_cb, cols_max, stream);
-        case 13: return launch_grouped<13>(a, n_cb, cols_max, stream);
-        case 15: return launch_grouped<15>(a, n_cb, cols_max, stream);
-        case 17: return launch_grouped<17>(a, n_cb, cols_max, stream);
-        case 19: return launch_grouped<19>(a, n_cb, cols_max, stream);
-        case 21: return launch_grouped<21>(a, n_cb, cols_max, stream);
-        case 23: return launch_grouped<23>(a, n_cb, cols_max, stream);
-        case 25: return launch_grouped<25>(a, n_cb, cols_max, stream);
-        case 27: return launch_grouped<27>(a, n_cb, cols_max, stream);
+        case 3: return launch_grouped<3>(a, n_cb, stream);
+        case 5: return launch_grouped<5>(a, n_cb, stream);
+        case 7: return launch_grouped<7>(a, n_cb, stream);
+        case 9: return launch_grouped<9>(a, n_cb, stream);
+        case 11: return launch_grouped<11>(a, n_cb, stream);
+        case 13: return launch_grouped<13>(a, n_cb, stream);
+        case 15: return launch_grouped<15>(a, n_cb, stream);
+        case 17: return launch_grouped<17>(a, n_cb, stream);
+        case 19: return launch_grouped<19>(a, n_cb, stream);
+        case 21: return launch_grouped<21>(a, n_cb, stream);
+        case 23: return launch_grouped<23>(a, n_cb, stream);
+        case 25: return launch_grouped<25>(a, n_cb, stream);
+        case 27: return launch_grouped<27>(a, n_cb, stream);
         default: return 1;
     }
 }
