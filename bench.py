@@ -3,7 +3,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload NAME]
 
 Default workload = BASELINE.json configs[1]: Wav2Letter-char (66.5 M params, 38 classes) TRAINING
-STEP, batch 80 x 15 s of synthetic 8 kHz int16 PCM with ragged lengths, bf16.  One step = log-mel
+STEP, batch 80 x 15 s of synthetic 8 kHz int16 PCM, every utterance full length (xlen = 1, as the
+reference's own benchmark.py feeds it), bf16.  One step = log-mel
 frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + mask layers -> decoder
 + log_softmax -> CTC loss -> backward through everything (CTC gradient, log_softmax, decoder, BN,
 dgrad and wgrad of every conv) -> clip_grad_norm(100) + SGD(momentum 0.9, weight decay 1e-3) update (the
@@ -11,8 +12,10 @@ reference's train.py defaults, train.py:657-662,776-779) as one native multi-ten
 runs on this repo's kernels.  N > 1: data-parallel replicas; every layer's weight gradient is
 all-reduced (NCCL) from inside the native backward as soon as it exists, inside the same CUDA graph.
 
-Secondary workload (reported under "also", selectable with --workload): the inference path of the
-same shape -- eval-mode forward with folded BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
+Secondary workloads (reported under "also", selectable with --workload): the same training step on a
+RAGGED batch (xlen ~ U(0.5, 1], SURVEY.md 8d: masks exercised; tiles of pure padding are structural zeros
+and are left out of the GEMMs) and the inference path of the same shape -- eval-mode forward with folded
+BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
 
 value  = whole-job audio-seconds / second with the PCM already resident in HBM (CUDA events).
 e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM + targets
@@ -36,18 +39,24 @@ if ROOT not in sys.path:
 import torch
 
 WORKLOADS = {
-	# name: (model, num_classes, batch, seconds, precision, kind)
-	'wav2letter_char_train_step_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'train'),
-	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer'),
-	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer'),
-	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer'),
-	'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16': ('Wav2Letter', 5000, 64, 15.0, 'bf16', 'infer'),
+	# name: (model, num_classes, batch, seconds, precision, kind, lengths)
+	#   lengths 'full'  : every utterance fills its row, xlen = 1 (the reference's own benchmark.py:126 style; BASELINE "80 x 15 s")
+	#   lengths 'ragged': xlen ~ U(0.5, 1] (SURVEY.md 8d "recommended additionally": exercises masks); on average 25 % of every row
+	#                     is padding, whose tiles the conv / wgrad kernels leave out (exact: they are structural zeros)
+	'wav2letter_char_train_step_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'train', 'full'),
+	'wav2letter_char_train_step_B80x15s_bf16_ragged': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'train', 'ragged'),
+	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer', 'full'),
+	'wav2letter_char_fwd_ctc_B80x15s_bf16_ragged': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer', 'ragged'),
+	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer', 'ragged'),
+	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer', 'ragged'),
+	'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16': ('Wav2Letter', 5000, 64, 15.0, 'bf16', 'infer', 'ragged'),
 }
 DEFAULT_WORKLOAD = 'wav2letter_char_train_step_B80x15s_bf16'
-SECONDARY_WORKLOAD = 'wav2letter_char_fwd_ctc_B80x15s_bf16'
+SECONDARY_WORKLOADS = ['wav2letter_char_train_step_B80x15s_bf16_ragged', 'wav2letter_char_fwd_ctc_B80x15s_bf16']
 # mean DRAM bytes per launch of the tensor-pipe kernels, from the committed ncu --set full captures
 NCU_DRAM_BYTES_PER_LAUNCH = {
 	'wav2letter_char_train_step_B80x15s_bf16': 131.2e6,  # profiles/r01_train_step_tensor_kernels_ncu_full.csv (56 launches)
+	'wav2letter_char_train_step_B80x15s_bf16_ragged': 131.2e6,
 	'wav2letter_char_fwd_ctc_B80x15s_bf16': 105.0e6,  # profiles/r01_step_kernels_ncu_full.csv (conv1d_umma_kernel launches)
 }
 STEP_DESC = {
@@ -55,20 +64,31 @@ STEP_DESC = {
 	'infer': 'frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)',
 }
 SAMPLE_RATE = 8000
+LENGTHS_DESC = {
+	'full': 'xlen = 1: every utterance fills its row (benchmark.py:126 style)',
+	'ragged': 'xlen ~ U(0.5, 1]: ~25 % of each row is padding; value counts PADDED seconds; tiles of pure padding are left out of the GEMMs (structural zeros, exact)',
+}
 
 
-def synth_batch(B, seconds, C, seed):
-	"""int16 PCM round(3000*N(0,1)), xlen ~ U(0.5, 1] with one full-length row,
-	targets never the blank, lengths such that an alignment exists."""
+def synth_batch(B, seconds, C, seed, lengths = 'ragged'):
+	"""int16 PCM round(3000*N(0,1)); targets never the blank, lengths such that an alignment exists.
+	'ragged': xlen ~ U(0.5, 1] with one full-length row; 'full': xlen = 1 (benchmark.py:126), target lengths up to
+	0.3 * t_out (L <~ 225 of t = 753)."""
 	g = torch.Generator().manual_seed(seed)
 	T = int(seconds * SAMPLE_RATE)
 	sig = (torch.randn(B, T, generator = g) * 3000).round().clamp(-32767, 32767).to(torch.int16)
 	xlen = torch.rand(B, generator = g) * 0.5 + 0.5
 	xlen[0] = 1.0
 	t_out = (T // 80 + 1 - 1) // 2 + 1 + 2
-	t_min = int((xlen.min() * t_out).ceil())
-	L = int(0.45 * t_min)
-	ylen = torch.randint(max(1, int(0.2 * t_min / 2)), L + 1, (B, ), generator = g)
+	if lengths == 'full':
+		xlen = torch.ones(B)
+		L = int(0.3 * t_out)
+		lo = max(1, L // 3)
+	else:
+		t_min = int((xlen.min() * t_out).ceil())
+		L = int(0.45 * t_min)
+		lo = max(1, int(0.2 * t_min / 2))
+	ylen = torch.randint(lo, L + 1, (B, ), generator = g)
 	y = torch.randint(0, C - 1, (B, 1, L), generator = g)
 	return sig, xlen, y, ylen.unsqueeze(1)
 
@@ -165,12 +185,12 @@ def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind):
 	return loss
 
 
-def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup, kind):
+def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup, kind, lengths = 'ragged'):
 	from oracle import oracle as O
 	torch.set_num_threads(os.cpu_count())
 	shapes = {k: s for k, s in model_shapes(model_name, C).items() if not k.startswith('frontend.')}
 	sd = O.synth_state_dict(shapes, seed = 0)
-	sig, xlen, y, ylen = synth_batch(sample_B, seconds, C, seed = 0)
+	sig, xlen, y, ylen = synth_batch(sample_B, seconds, C, seed = 0, lengths = lengths)
 	for _ in range(warmup):
 		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind)
 	t0 = time.perf_counter()
@@ -184,14 +204,14 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	"""one workload on this rank's GPU; `full` adds roofline / e2e / clocks (primary line)"""
 	from convasr_b200 import _lib, models, ops
 	from oracle import oracle as O  # only for the seeded synthetic weights + the cpu_baseline leg
-	model_name, C, B, seconds, precision, kind = WORKLOADS[name]
-	config = dict(workload = name, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
+	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[name]
+	config = dict(workload = name, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
 				step = STEP_DESC[kind], parallelism = (f'data-parallel replicas x{world} (per-layer NCCL gradient all-reduce overlapped with the backward)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
 				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
 	cpu_baseline = None
 	if with_cpu_baseline:
 		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
-		v, sec = run_cpu_baseline(model_name, C, seconds, sB, 3, 1, kind)
+		v, sec = run_cpu_baseline(model_name, C, seconds, sB, 3, 1, kind, lengths)
 		cpu_baseline = dict(value = v, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, 3 steps after 1 warm-up ({sec:.2f} s/step; oracle port: torch {torch.__version__} CPU ops, {kind} step)')
 
 	frontend = models.LogFilterBankFrontend(64, SAMPLE_RATE, .02, .01, 'hann_window')
@@ -199,7 +219,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
 	model.load_state_dict(O.synth_state_dict(shapes, seed = 0), strict = False)
 	model = model.to(dev)
-	sig, xlen, y, ylen = synth_batch(B, seconds, C, seed = 1000 + rank)
+	sig, xlen, y, ylen = synth_batch(B, seconds, C, seed = 1000 + rank, lengths = lengths)
 	sig_pin, xlen_pin, y_pin, ylen_pin = [t.pin_memory() for t in (sig, xlen, y, ylen)]
 	sig_d, xlen_d, y_d, ylen_d = [t.to(dev) for t in (sig, xlen, y, ylen)]
 	flush = torch.empty(256 << 20, dtype = torch.uint8, device = dev)
@@ -290,7 +310,13 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	if config['cuda_graphs'] and kind == 'infer':
 		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
 	if config['cuda_graphs'] and kind == 'train':
-		run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d, max_grad_norm = 100.0)  # whole step = one replay
+		try:
+			run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d, max_grad_norm = 100.0)  # whole step = one replay
+		except Exception as e:  # data-parallel capture includes the NCCL collectives; keep the eager step if a stack refuses it
+			if world == 1:
+				raise
+			print(f'[bench] rank {rank}: CUDA-graph capture of the data-parallel step failed ({e!r}); eager step instead', file = sys.stderr)
+			config['cuda_graphs'] = False
 	for _ in range(warmup):
 		nll = step_device()
 	torch.cuda.synchronize()
@@ -352,11 +378,11 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		roofline = dict(
 			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
 			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
-			peak_burst = peaks['bf16_tflops'] if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name), traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed',
+			peak_burst = peaks['bf16_tflops'] if peaks else None, frac_of_burst = (achieved / peaks['bf16_tflops']) if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name), traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed',
 			launches_per_step = n_kern, kernel_ms_per_step = kern_ms,
 			algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1, share_of_step = kern_ms / (ms / steps)
 		)
-	result.update(config = config, cpu_baseline = cpu_baseline, clocks = clocks, roofline = roofline, launches = launches_per_step * steps, B = B, seconds = seconds, precision = precision,
+	result.update(valid_fraction = float(xlen.mean()), config = config, cpu_baseline = cpu_baseline, clocks = clocks, roofline = roofline, launches = launches_per_step * steps, B = B, seconds = seconds, precision = precision,
 					h2d = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen)), d2h = d2h)
 	del model, flush
 	torch.cuda.empty_cache()
@@ -375,7 +401,7 @@ def main():
 	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
 	ap.add_argument('--no-cuda-graphs', action = 'store_true')
 	args = ap.parse_args()
-	model_name, C, B, seconds, precision, kind = WORKLOADS[args.workload]
+	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[args.workload]
 	rank = int(os.environ.get('RANK', 0))
 	world = int(os.environ.get('WORLD_SIZE', 1))
 	local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -386,8 +412,8 @@ def main():
 			return
 		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
 		n_steps = max(1, min(steps, 3))
-		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1, kind)
-		config = dict(workload = args.workload, model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = 'fp32', kind = kind, step = STEP_DESC[kind])
+		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1, kind, lengths)
+		config = dict(workload = args.workload, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = 'fp32', kind = kind, step = STEP_DESC[kind])
 		line = dict(
 			impl = 'reference', metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = args.gpus, steps = n_steps, warmup = 1, ms_per_step = sec * 1e3,
 			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config,
@@ -416,9 +442,11 @@ def main():
 	ms, ms_e2e = reduce_max([r['ms'], r['ms_e2e']])
 	also = None
 	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD:
-		r2 = measure(SECONDARY_WORKLOAD, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
-		ms2, = reduce_max([r2['ms']])
-		also = {SECONDARY_WORKLOAD: dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'])}
+		also = {}
+		for name2 in SECONDARY_WORKLOADS:
+			r2 = measure(name2, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
+			ms2, = reduce_max([r2['ms']])
+			also[name2] = dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, lengths = r2['config']['lengths'], valid_audio_fraction = r2['valid_fraction'], step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'])
 	if rank == 0:
 		audio_s = r['B'] * r['seconds'] * world
 		line = dict(

@@ -29,7 +29,8 @@ class ConvEpilogue(ctypes.Structure):
 		('B', c_i32), ('T_out', c_i32), ('C_out', c_i32), ('block_n', c_i32), ('epilogue', c_i32), ('act', c_i32),
 		('act_a', c_float), ('act_b', c_float), ('bias', c_void_p), ('xlen_frac', c_void_p), ('out_hi', c_void_p),
 		('out_lo', c_void_p), ('out_T_rows', c_i32), ('out_ld_ch', c_i32), ('logits', c_void_p),
-		('log_probs', c_void_p), ('argmax', c_void_p), ('stats', c_void_p)
+		('log_probs', c_void_p), ('argmax', c_void_p), ('stats', c_void_p), ('skip_frac', c_void_p), ('skip_T', c_i32),
+		('skip_margin', c_i32)
 	]
 
 
@@ -47,7 +48,7 @@ SIGNATURES = {
 						c_void_p, c_void_p, c_void_p],
 	'cab_conv1d_fused': [ctypes.POINTER(ConvSource), c_int, ctypes.POINTER(ConvEpilogue), c_void_p],
 	'cab_conv1d_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-						c_void_p, c_int, c_int, c_void_p],
+						c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
 	'cab_bn_batch_stats': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_void_p],
 	'cab_bn_finalize': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],

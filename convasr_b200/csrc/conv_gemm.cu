@@ -67,6 +67,31 @@ struct alignas(64) ConvParams {
     float* log_probs;
     int* argmax;
     float* stats;  // [2][C_out] per-channel sum / sum of squares of the bf16 outputs, or null
+    // rows t >= ceil(skip_frac[b] * skip_T) + skip_margin of utterance b are structural zeros (padding of a
+    // ragged batch): M tiles that lie entirely there are not computed, the epilogue stores zeros
+    const float* skip_frac;
+    int skip_T, skip_margin;
+};
+
+// Tile schedule.  Only M tiles that hold at least one live row are enumerated ("compacted" index am), so
+// the static round-robin over CTAs stays balanced on ragged batches; every role walks the same
+// sequence with its own cursor (utterance b owns compacted indices [base, end)).
+__device__ __forceinline__ int live_mtiles(const ConvParams& p, int b) {
+    if (p.skip_frac == nullptr) return p.mtiles_per_b;
+    const int rows = min(p.T_out, frac_len(__ldg(p.skip_frac + b), p.skip_T) + p.skip_margin);
+    return rows <= 0 ? 0 : (rows + 127) / 128;
+}
+struct TileCursor {
+    int b, base, end;
+    __device__ __forceinline__ void init(const ConvParams& p) { b = 0; base = 0; end = live_mtiles(p, 0); }
+    __device__ __forceinline__ bool seek(const ConvParams& p, int am) {  // false: past the last utterance
+        while (am >= end) {
+            if (++b >= p.B) return false;
+            base = end;
+            end += live_mtiles(p, b);
+        }
+        return true;
+    }
 };
 
 __device__ __forceinline__ float apply_act(float x, int act, float a, float b) {
@@ -201,11 +226,14 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            TileCursor cur;
+            cur.init(p);
+            for (int tile = blockIdx.x;; tile += gridDim.x) {
                 const int nt = tile % p.n_ntiles;
-                const int mt = tile / p.n_ntiles;
-                const int b = mt / p.mtiles_per_b;
-                const int t0 = (mt % p.mtiles_per_b) * kBlockM;
+                const int am = tile / p.n_ntiles;
+                if (!cur.seek(p, am)) break;
+                const int b = cur.b;
+                const int t0 = (am - cur.base) * kBlockM;
                 const int n0 = nt * block_n;
                 for (int s = 0; s < p.n_src; ++s) {
                     const SrcDev sd = p.src[s];
@@ -234,7 +262,10 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            TileCursor cur;
+            cur.init(p);
+            for (int tile = blockIdx.x;; tile += gridDim.x) {
+                if (!cur.seek(p, tile / p.n_ntiles)) break;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
@@ -269,11 +300,14 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         int acc = 0;
         uint32_t acc_phase = 0;
         uint32_t epi_chunks = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        TileCursor cur;
+        cur.init(p);
+        for (int tile = blockIdx.x;; tile += gridDim.x) {
             const int nt = tile % p.n_ntiles;
-            const int mt = tile / p.n_ntiles;
-            const int b = mt / p.mtiles_per_b;
-            const int t0 = (mt % p.mtiles_per_b) * kBlockM;
+            const int am = tile / p.n_ntiles;
+            if (!cur.seek(p, am)) break;
+            const int b = cur.b;
+            const int t0 = (am - cur.base) * kBlockM;
             const int n0 = nt * block_n;
             const int t = t0 + row;
             const bool row_ok = t < p.T_out;
@@ -440,6 +474,50 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
         }
+        if (p.skip_frac != nullptr && p.epilogue == CAB_EPI_ACT_BF16) {
+            // M tiles that are pure padding: nobody computed them, store zeros (same staging buffers / TMA
+            // stores as above).  Cursor over the compacted index of SKIPPED tiles.
+            const int et = threadIdx.x - 128;
+            const bool has_lo = p.out_lo != nullptr;
+            uint8_t* stage = smem + kOffStageOut;
+            int b = 0, base = 0, end = p.mtiles_per_b - live_mtiles(p, 0);
+            for (int z = blockIdx.x;; z += gridDim.x) {
+                const int nt = z % p.n_ntiles;
+                const int sm = z / p.n_ntiles;
+                bool done = false;
+                while (sm >= end) {
+                    if (++b >= p.B) { done = true; break; }
+                    base = end;
+                    end += p.mtiles_per_b - live_mtiles(p, b);
+                }
+                if (done) break;
+                const int t0 = (live_mtiles(p, b) + (sm - base)) * kBlockM;
+                const int n0 = nt * block_n;
+                for (int c0 = 0; c0 < block_n; c0 += kEpiCols) {
+                    if (n0 + c0 >= p.C_out) break;  // uniform
+                    const int buf = epi_chunks & 1;
+                    uint8_t* st_hi = stage + buf * kEpiTileBytes;
+                    uint8_t* st_lo = stage + (2 + buf) * kEpiTileBytes;
+                    if (et == 0) bulk_wait_read<1>();
+                    epi_bar(2);
+                    uint4* zh = reinterpret_cast<uint4*>(st_hi + row * 64);
+                    uint4* zl = reinterpret_cast<uint4*>(st_lo + row * 64);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        zh[qd] = make_uint4(0, 0, 0, 0);
+                        if (has_lo) zl[qd] = make_uint4(0, 0, 0, 0);
+                    }
+                    fence_async_smem();
+                    epi_bar(3);
+                    if (et == 0) {
+                        tma_store_3d(&p.omap_hi, st_hi, n0 + c0, t0, b);
+                        if (has_lo) tma_store_3d(&p.omap_lo, st_lo, n0 + c0, t0, b);
+                        bulk_commit();
+                    }
+                    ++epi_chunks;
+                }
+            }
+        }
         if (threadIdx.x == 128) bulk_wait_all();  // all TMA stores of this CTA have completed
     }
 
@@ -561,6 +639,17 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     p.log_probs = ep->log_probs;
     p.argmax = ep->argmax;
     p.stats = ep->epilogue == CAB_EPI_ACT_BF16 ? ep->stats : nullptr;
+    // structural-zero rows: given explicitly (training: zero input rows / don't-care gradient rows), or implied
+    // by the temporal mask this launch applies itself
+    p.skip_frac = nullptr; p.skip_T = 0; p.skip_margin = 0;
+    if (ep->epilogue == CAB_EPI_ACT_BF16) {
+        if (ep->skip_frac != nullptr) {
+            CAB_CHECK_ARG(ep->skip_T > 0 && ep->skip_margin >= 0, "bad skip_T=%d / skip_margin=%d", ep->skip_T, ep->skip_margin);
+            p.skip_frac = ep->skip_frac; p.skip_T = ep->skip_T; p.skip_margin = ep->skip_margin;
+        } else if (ep->xlen_frac != nullptr) {
+            p.skip_frac = ep->xlen_frac; p.skip_T = ep->T_out;
+        }
+    }
     if (p.stats != nullptr) CAB_CHECK_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * ep->C_out, stream));
     if (ep->epilogue == CAB_EPI_ACT_BF16) {
         CAB_CHECK_ARG(ep->out_lo == nullptr || (reinterpret_cast<uintptr_t>(ep->out_lo) & 15) == 0, "out_lo must be 16-byte aligned");

@@ -48,7 +48,17 @@ struct alignas(64) Params {
     float* out;             // fp32 [taps][M_total][out_ld]
     int out_ld;
     int accumulate;         // use reductions instead of stores
+    const float* skip_frac; // frames >= ceil(skip_frac[b] * skip_T) + skip_margin contribute zeros: not contracted
+    int skip_T, skip_margin;
 };
+
+// 64-frame K chunks of utterance b that can hold non-zero products
+__device__ __forceinline__ int live_chunks(const Params& p, int b) {
+    if (p.skip_frac == nullptr) return p.chunks_per_b;
+    const int rows = min(p.T_a, frac_len(__ldg(p.skip_frac + b), p.skip_T) + p.skip_margin);
+    const int n = (rows + 63) / 64;
+    return n < 1 ? 1 : n;
+}
 
 // MN-major, 128B-swizzled operand: 64-channel atoms LBO bytes apart, 8-frame groups SBO bytes apart
 __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -121,7 +131,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
                 const int m0 = mt * kBlockM, n0 = nt * block_n;
                 const int shift = tap * p.dil - p.pad_left;
                 for (int b = b0; b < b1; ++b) {
-                    for (int j = 0; j < p.chunks_per_b; ++j) {
+                    const int n_chunks = live_chunks(p, b);
+                    for (int j = 0; j < n_chunks; ++j) {
                         const int t0 = j * kBlockK;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* a_dst = smem + stage * kStageBytes;
@@ -150,7 +161,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
                 uint32_t accumulate = 0;
-                const int ksteps = (b1 - b0) * p.chunks_per_b;
+                int ksteps = 0;
+                for (int b = b0; b < b1; ++b) ksteps += live_chunks(p, b);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -259,7 +271,8 @@ using namespace cab;
 
 extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total, const void* bx, int b_T,
                                 int b_T_rows, int b_ld, int N_total, int B, int taps, int dilation, int pad_left,
-                                float* out, int out_ld, int n_splits, cab_stream_t stream_) {
+                                float* out, int out_ld, int n_splits, const float* skip_frac, int skip_T, int skip_margin,
+                                cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(a && bx && out, "null pointer argument");
     CAB_CHECK_ARG(B > 0 && a_T > 0 && b_T > 0 && taps > 0 && dilation != 0, "bad shape");
@@ -310,6 +323,8 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
     p.n_items = tiles * n_splits;
     p.chunks_per_b = (a_T + wg::kBlockK - 1) / wg::kBlockK;
     p.out = out; p.out_ld = out_ld;
+    CAB_CHECK_ARG(skip_frac == nullptr || (skip_T > 0 && skip_margin >= 0), "bad skip_T=%d / skip_margin=%d", skip_T, skip_margin);
+    p.skip_frac = skip_frac; p.skip_T = skip_T; p.skip_margin = skip_margin;
     p.accumulate = n_splits > 1 ? 1 : 0;
     if (p.accumulate) CAB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)taps * M_total * out_ld, stream));
     const int grid = p.n_items < num_sms ? p.n_items : num_sms;

@@ -127,8 +127,11 @@ class Source:
 
 def conv1d_fused(
 	sources, B, T_out, C_out, bias = None, act = _lib.ACT_NONE, act_a = 0.0, act_b = 0.0, xlen = None, out_hi = None,
-	out_lo = None, logits = None, log_probs = None, argmax = None, epilogue = _lib.EPI_ACT_BF16, block_n = 0, stats = None
+	out_lo = None, logits = None, log_probs = None, argmax = None, epilogue = _lib.EPI_ACT_BF16, block_n = 0, stats = None,
+	skip = None
 ):
+	"""skip = (frac [B] fp32, T, margin): output rows t >= ceil(frac[b]*T) + margin are structural zeros (ragged-batch
+	padding) -- whole 128-row tiles there are stored as zeros without being computed"""
 	_need_cuda(*(s.act for s in sources), bias, xlen, out_hi, out_lo, logits, log_probs, argmax)
 	n = len(sources)
 	arr = (_lib.ConvSource * n)(*[s.to_c() for s in sources])
@@ -145,12 +148,16 @@ def conv1d_fused(
 	ep.log_probs = None if log_probs is None else log_probs.data_ptr()
 	ep.argmax = None if argmax is None else argmax.data_ptr()
 	ep.stats = None if stats is None else stats.data_ptr()
+	if skip is not None:
+		_need_cuda(skip[0])
+		ep.skip_frac, ep.skip_T, ep.skip_margin = skip[0].data_ptr(), int(skip[1]), int(skip[2])
 	rc = _lib.load().cab_conv1d_fused(arr, n, ctypes.byref(ep), _stream())
 	_lib.check(rc, 'cab_conv1d_fused')
 
 
-def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0):
-	"""out[tap, m, n] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dilation - pad_left, n]  (fp32 [taps, M, N_ld])"""
+def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0, skip = None):
+	"""out[tap, m, n] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dilation - pad_left, n]  (fp32 [taps, M, N_ld]);
+	skip = (frac [B], T, margin): frames t >= ceil(frac[b]*T) + margin only contribute zeros and are left out"""
 	_need_cuda(a, bx)
 	assert a.dtype == BF16 and bx.dtype == BF16 and a.is_contiguous() and bx.is_contiguous()
 	B = a.shape[0]
@@ -158,7 +165,8 @@ def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_
 	out = torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
 	rc = _lib.load().cab_conv1d_wgrad(
 		_p(a), a_T, a.shape[1], a.shape[2], M_total, _p(bx), b_T, bx.shape[1], bx.shape[2], N_total, B, taps, dilation, pad_left,
-		_p(out), out_ld, n_splits, _stream()
+		_p(out), out_ld, n_splits, _p(skip[0]) if skip is not None else None, int(skip[1]) if skip is not None else 0,
+		int(skip[2]) if skip is not None else 0, _stream()
 	)
 	_lib.check(rc, 'cab_conv1d_wgrad')
 	return out  # [taps, M_total, ld >= N_total]; columns past N_total are padding

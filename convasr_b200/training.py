@@ -24,6 +24,7 @@ from . import _lib, engine, ops
 
 BF16 = torch.bfloat16
 _SEPARATE_BN_STATS = __import__('os').environ.get('CONVASR_B200_SEPARATE_BN_STATS', '0') == '1'
+_SKIP_PADDING = __import__('os').environ.get('CONVASR_B200_SKIP_PADDING', '1') == '1'  # A/B switch: leave tiles of pure padding out
 
 
 def supported(model):
@@ -116,20 +117,26 @@ class NativeStack(torch.autograd.Function):
 				src = ops.Source(src_view, w_fwd, 2 * L.ci_alloc, taps, 1, pad_left, T_in = src_view.shape[1])
 				T_out = (x_T + 2 * L.pad - (L.k - 1) - 1) // 2 + 1
 				geom = ('pair', taps, pad_left)
+				skip = None
 			else:
+				skip = None
 				w_fwd, w_dgr = _pack(w.detach(), L.ci_alloc, L.co_alloc, want_dgrad = li > 0)
 				src = ops.Source(x, w_fwd, L.ci_alloc, L.k, L.dil, L.pad, T_in = x_T)
 				T_out = x_T + 2 * L.pad - L.dil * (L.k - 1)
 				geom = ('plain', L.k, L.pad)
+				if _SKIP_PADDING and xlen is not None and li > 0 and layers[li - 1].mask:
+					# the input is exactly zero from frame ceil(xlen*x_T) on (the previous layer's mask), the conv has no
+					# bias: output rows >= that + pad are zeros -- tiles of pure padding are not computed
+					skip = (xlen, x_T, L.pad)
 			y = torch.empty(B, T_out, L.co_alloc, dtype = BF16, device = x.device)
 			if _SEPARATE_BN_STATS:  # A/B switch: statistics as a separate pass over y
-				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y)
+				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y, skip = skip)
 				ws = torch.empty(2, L.C_out, dtype = torch.float32, device = x.device)
 				ss = torch.empty(4, L.C_out, dtype = torch.float32, device = x.device)
 				_lib.check(lib.cab_bn_batch_stats(ops._p(y), B, T_out, L.C_out, L.co_alloc, ops._p(L.bn.weight), ops._p(L.bn.bias), float(L.bn.eps), float(L.bn.momentum), ops._p(L.bn.running_mean), ops._p(L.bn.running_var), ops._p(ws), ops._p(ss), ops._stream()), 'cab_bn_batch_stats')
 			else:
 				sums = torch.empty(2, L.co_alloc, dtype = torch.float32, device = x.device)
-				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y, stats = sums)  # batch statistics in the epilogue
+				ops.conv1d_fused([src], B, T_out, L.co_alloc, out_hi = y, stats = sums, skip = skip)  # batch statistics in the epilogue
 				ss = _bn_finalize(sums, B * T_out, L)
 			out = torch.empty_like(y)
 			code, a, b = L.act
@@ -183,7 +190,9 @@ class NativeStack(torch.autograd.Function):
 		grads = {}
 		# decoder: the wide side (input channels) sits on the 128-row M side -> packed gradient is [1, Ci, Co]
 		x_last, T_last = ctx.x_last, ctx.T_last
-		packed = ops.conv1d_wgrad(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0)
+		masked_in = lambda li: _SKIP_PADDING and xlen is not None and (layers[li - 1].mask if li > 0 else False)  # is layer li's input zero past ceil(xlen*T)?
+		skip_last = (xlen, T_last, 0) if _SKIP_PADDING and xlen is not None and layers[-1].mask else None
+		packed = ops.conv1d_wgrad(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0, skip = skip_last)
 		grads[dec.weight] = _unpack(packed, 1, C, dec.in_channels, transposed = True)
 		if sync is not None:
 			sync.reduce(grads[dec.weight])
@@ -191,7 +200,8 @@ class NativeStack(torch.autograd.Function):
 			grads[dec.bias] = d_bias
 		ci_alloc = x_last.shape[2]
 		gx = torch.empty(B, T_last, ci_alloc, dtype = BF16, device = dev)
-		ops.conv1d_fused([ops.Source(g_cl, ctx.w_dec_dgr, c_ld, 1, 1, 0, T_in = T)], B, T_last, ci_alloc, out_hi = gx)
+		# gradient rows of masked frames are never read (the mask's backward selects, it does not multiply)
+		ops.conv1d_fused([ops.Source(g_cl, ctx.w_dec_dgr, c_ld, 1, 1, 0, T_in = T)], B, T_last, ci_alloc, out_hi = gx, skip = skip_last)
 
 		for li in range(len(layers) - 1, -1, -1):
 			L = layers[li]
@@ -210,13 +220,13 @@ class NativeStack(torch.autograd.Function):
 				packed = ops.conv1d_wgrad(dy, T_out, L.C_out, xv, xv.shape[1], 2 * L.ci_alloc, taps, 1, pad_left)
 				grads[L.conv.weight] = _unpack_stride2(packed, L)
 			else:
-				grads[L.conv.weight] = _wgrad(dy, T_out, L.C_out, x, x_T, L.C_in, L.k, L.dil, L.pad)
+				grads[L.conv.weight] = _wgrad(dy, T_out, L.C_out, x, x_T, L.C_in, L.k, L.dil, L.pad, xlen if masked_in(li) else None)
 			if sync is not None:
 				sync.reduce(grads[L.conv.weight])  # overlaps the dgrad / wgrad of the layers still to come
 			if li > 0:
 				gx = torch.empty(B, x_T, L.ci_alloc, dtype = BF16, device = dev)
 				# dx[j] = sum_k' W'[k'] dy[j + k'*d - (d*(K-1) - pad)], W' = flipped, transposed weights
-				ops.conv1d_fused([ops.Source(dy, w_dgr, L.co_alloc, L.k, L.dil, L.dil * (L.k - 1) - L.pad, T_in = T_out)], B, x_T, L.ci_alloc, out_hi = gx)
+				ops.conv1d_fused([ops.Source(dy, w_dgr, L.co_alloc, L.k, L.dil, L.dil * (L.k - 1) - L.pad, T_in = T_out)], B, x_T, L.ci_alloc, out_hi = gx, skip = (xlen, x_T, 0) if masked_in(li) else None)
 		if sync is not None:
 			sync.reduce(small)
 			sync.finish()
@@ -229,14 +239,15 @@ def _padded_work(M, N):
 	return ((M + 127) // 128 * 128) * n_nt * bn
 
 
-def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad):
+def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None):
 	"""dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * x[b, t + tap*dil - pad, ci].  Either tensor can sit on the
 	128-row M side of the GEMM; pick the orientation with less tile padding (e.g. 640 -> 768 wastes 20 %
 	one way and nothing the other way).  Swapping sides negates the frame shift."""
+	# xlen_zero: x is exactly zero from frame ceil(xlen*x_T) on, so products with t + tap*dil - pad >= that vanish
 	if _padded_work(C_out, C_in) <= _padded_work(C_in, C_out):
-		packed = ops.conv1d_wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad)
+		packed = ops.conv1d_wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, skip = (xlen_zero, x_T, pad) if xlen_zero is not None else None)
 		return _unpack(packed, k, C_out, C_in, transposed = False)
-	packed = ops.conv1d_wgrad(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad)
+	packed = ops.conv1d_wgrad(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad, skip = (xlen_zero, x_T, 0) if xlen_zero is not None else None)
 	return _unpack(packed, k, C_out, C_in, transposed = True)
 
 

@@ -123,6 +123,12 @@ typedef struct {
     float* stats;            /* ACT_BF16: NULL, or fp32 [2][C_out]: the call zeroes it and the epilogue
                                 accumulates per-channel sum / sum of squares of the (bf16-rounded) outputs
                                 over all B*T_out rows -- BatchNorm batch statistics for training */
+    const float* skip_frac;  /* ACT_BF16: NULL, or [B]: output rows t >= ceil(skip_frac[b]*skip_T) + skip_margin of
+                                utterance b are structural zeros (padding of a ragged batch whose input rows are
+                                zero there, or gradient rows nobody reads): 128-row tiles lying entirely in that
+                                range are not computed and are stored as zeros.  With xlen_frac set and skip_frac
+                                NULL the launch's own temporal mask implies (xlen_frac, T_out, 0). */
+    int32_t skip_T, skip_margin;
 } cab_conv_epilogue_t;
 
 int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
@@ -135,10 +141,13 @@ int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
  *   (conv input) -- or swapped by the caller, whichever side should be the 128-row M side.
  *   out: fp32 [taps, M_total, out_ld].  n_splits = 0 picks a batch split for >= 4 waves;
  *   with n_splits > 1 partial sums are reduced in L2 (the call zeroes `out` first).
+ *   skip_frac (or NULL): frames t >= ceil(skip_frac[b]*skip_T) + skip_margin of utterance b contribute
+ *   exact zeros (one operand is zero there: ragged batch padding) and are left out of the contraction.
  * ------------------------------------------------------------------------------------- */
 int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total, const void* bx,
                      int b_T, int b_T_rows, int b_ld, int N_total, int B, int taps, int dilation,
-                     int pad_left, float* out, int out_ld, int n_splits, cab_stream_t stream);
+                     int pad_left, float* out, int out_ld, int n_splits, const float* skip_frac, int skip_T,
+                     int skip_margin, cab_stream_t stream);
 
 /* Training-mode BatchNorm1d + activation + temporal mask around the conv GEMMs
  * (nn.BatchNorm1d(momentum, eps) inside ConvBn1d.forward, models.py:112-113,127-139):

@@ -350,3 +350,61 @@ def test_data_parallel_native_grad_sync_two_gpus(tmp_path):
 	s.close()
 	mp.spawn(_grad_sync_worker, args = (2, port, str(tmp_path)), nprocs = 2, join = True)
 	assert all((tmp_path / f'ok{r}').exists() for r in range(2))
+
+
+# ------------------------------------------------------------------------------------------ ragged batches
+def test_padding_tiles_are_skipped_exactly():
+	"""Tiles that lie entirely in the padding of a ragged batch are not computed (cab_conv_epilogue_t.skip_frac,
+	cab_conv1d_wgrad skip_*): the forward result is bit-identical, its BN statistics and the weight gradient equal
+	up to the order of the fp32 reductions."""
+	from convasr_b200 import ops, training
+	dev = torch.device('cuda:0')
+	g = torch.Generator().manual_seed(11)
+	B, T, Ci, Co, K, pad = 4, 700, 128, 192, 11, 5
+	xlen = torch.tensor([1.0, 0.55, 0.3, 0.05]).to(dev)
+	lens = ops.frac_lengths(xlen, T)
+	x = torch.randn(B, T, Ci, generator = g).to(BF16).to(dev)
+	x = x * (torch.arange(T, device = dev)[None, :, None] < lens[:, None, None])  # zero past the valid frames
+	w = (torch.randn(Co, Ci, K, generator = g) / (Ci * K) ** 0.5).to(dev)
+	w_fwd, _ = training._pack(w, Ci, Co, want_dgrad = False)
+	outs = []
+	for skip in (None, (xlen, T, pad)):
+		y = torch.full((B, T, Co), float('nan'), dtype = BF16, device = dev)
+		st = torch.empty(2, Co, device = dev)
+		ops.conv1d_fused([ops.Source(x, w_fwd, Ci, K, 1, pad, T_in = T)], B, T, Co, out_hi = y, stats = st, skip = skip)
+		outs.append((y, st))
+	torch.cuda.synchronize()
+	assert torch.equal(outs[0][0], outs[1][0])
+	assert torch.allclose(outs[0][1], outs[1][1], rtol = 1e-5, atol = 1e-4)  # fp32 atomics: order of the partial sums differs
+	assert bool((outs[1][0][3, 200:] == 0).all())  # utterance 3: 35 valid frames, tiles 2.. are pure padding
+	# with the launch's own temporal mask the skip is implied
+	ym = [torch.empty(B, T, Co, dtype = BF16, device = dev) for _ in range(2)]
+	ops.conv1d_fused([ops.Source(x, w_fwd, Ci, K, 1, pad, T_in = T)], B, T, Co, out_hi = ym[0], xlen = xlen, act = 1)
+	ref = torch.relu(outs[0][0].float()) * (torch.arange(T, device = dev)[None, :, None] < lens[:, None, None])
+	assert torch.equal(ym[0].float(), ref)
+	# weight gradient: both operand orientations
+	dy = torch.randn(B, T, Co, generator = g).to(BF16).to(dev)
+	for a, a_C, bx, b_C, dil, pd, margin in ((dy, Co, x, Ci, 1, pad, pad), (x, Ci, dy, Co, -1, -pad, 0)):
+		full = ops.conv1d_wgrad(a, T, a_C, bx, T, b_C, K, dil, pd)
+		part = ops.conv1d_wgrad(a, T, a_C, bx, T, b_C, K, dil, pd, skip = (xlen, T, margin))
+		assert rel(part, full) < 1e-6, rel(part, full)
+
+
+def test_training_step_same_with_and_without_padding_skip():
+	from convasr_b200 import training
+	dev = torch.device('cuda:0')
+	C = 38
+	sig, xlen, y, ylen = _batch(C)
+	xlen = torch.tensor([1.0, 0.9, 0.4, 0.2])
+	res = []
+	for flag in (False, True):
+		training._SKIP_PADDING = flag
+		try:
+			m, sd = _model(dev, dict(base_width = 32, num_blocks = 1))
+			out = m(sig.to(dev), xlen.to(dev), y = y.to(dev), ylen = torch.tensor([[14], [11], [5], [2]]).to(dev))
+			out['loss'].sum().backward()
+			res.append((out['logits'][0].detach().clone(), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None])))
+		finally:
+			training._SKIP_PADDING = True
+	assert rel(res[1][0], res[0][0]) < 1e-5, rel(res[1][0], res[0][0])  # forward: same numbers (BN statistics via fp32 atomics)
+	assert rel(res[1][1], res[0][1]) < 1e-2, rel(res[1][1], res[0][1])  # run-to-run atomics noise amplified by the backward (see above)
