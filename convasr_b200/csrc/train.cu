@@ -413,12 +413,22 @@ bn_stream_kernel(const StreamArgs p) {
         mbar_wait(&full[s], (uint32_t)(it / p.stages) & 1u);
         const unsigned char* src = smem_raw + (size_t)s * NIN * p.stage_bytes;
         const int row0 = chunk * p.rows_per_chunk;
+        // one division per chunk; the 4 rows of this thread are `lanes` apart, (b, t) advance incrementally
+        int b = (row0 + lane) / p.T, t = (row0 + lane) - b * p.T;
+        int len = p.xlen == nullptr ? p.T : frac_len(__ldg(p.xlen + min(b, p.B - 1)), p.T);
 #pragma unroll
         for (int u = 0; u < kStreamUnits; ++u) {
             const int rr = row0 + u * lanes + lane;
             if (rr >= R) break;
-            const int b = rr / p.T, t = rr - b * p.T;
-            const bool keep = p.xlen == nullptr || t < frac_len(__ldg(p.xlen + b), p.T);
+            if (u > 0) {
+                t += lanes;
+                while (t >= p.T) {
+                    t -= p.T;
+                    ++b;
+                    len = p.xlen == nullptr ? p.T : frac_len(__ldg(p.xlen + b), p.T);
+                }
+            }
+            const bool keep = t < len;
             const size_t unit = (size_t)u * nthreads + tid;
             if (MODE == 1 && !keep) continue;
             float yf[8], o[8];
@@ -488,7 +498,8 @@ bn_stream_kernel(const StreamArgs p) {
 static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& threads, int& grid, size_t& smem) {
     if (ld % 8 != 0 || R <= 0) return false;
     const int vectors = ld / 8;
-    int lanes = (256 + vectors - 1) / vectors;
+    int lanes = 256 / vectors;  // ~256 threads: the kernels are register-heavy, more CTAs per SM beat bigger CTAs
+    if (lanes < 1) lanes = 1;
     while ((vectors * lanes) % 32 != 0) ++lanes;
     threads = vectors * lanes;
     if (threads > kStreamMaxThreads) return false;
@@ -496,11 +507,13 @@ static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& thr
     a.rows_per_chunk = kStreamUnits * lanes;
     a.n_chunks = (R + a.rows_per_chunk - 1) / a.rows_per_chunk;
     a.stage_bytes = kStreamUnits * threads * 16;
-    int stages = (int)((100 * 1024) / ((size_t)n_inputs * a.stage_bytes));
+    // ~48 KB of stages per CTA: 3-4 CTAs per SM (ncu: with 2 fat CTAs the SM idled on LDS / fixed-latency waits at
+    // 52 % issue utilisation); bytes in flight per SM stay ~150-190 KB
+    int stages = (int)((48 * 1024) / ((size_t)n_inputs * a.stage_bytes));
     a.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
     smem = (size_t)a.stages * n_inputs * a.stage_bytes + 8 * a.stages;
     if (smem < (size_t)threads * 64) smem = (size_t)threads * 64;  // the reduction scratch of the reduce pass
-    grid = a.n_chunks < 148 * 2 ? a.n_chunks : 148 * 2;
+    grid = 0;  // sized by stream_launch from the occupancy of the instantiation
     return true;
 }
 
@@ -512,7 +525,20 @@ static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, siz
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
-    bn_stream_kernel<MODE><<<grid, threads, smem, stream>>>(a);
+    // persistent grid = exactly one wave: resident CTAs per SM for this (threads, smem), cached
+    static int cache_threads[8], cache_smem[8], cache_per_sm[8], n_cache = 0;
+    int per_sm = 0;
+    for (int i = 0; i < n_cache; ++i)
+        if (cache_threads[i] == threads && cache_smem[i] == (int)smem) per_sm = cache_per_sm[i];
+    if (per_sm == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_stream_kernel<MODE>, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        if (n_cache < 8) { cache_threads[n_cache] = threads; cache_smem[n_cache] = (int)smem; cache_per_sm[n_cache] = per_sm; ++n_cache; }
+    }
+    (void)grid;
+    const int g = a.n_chunks < 148 * per_sm ? a.n_chunks : 148 * per_sm;
+    bn_stream_kernel<MODE><<<g, threads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
