@@ -47,13 +47,20 @@ def load():
 	# the reference modules are imported by bare name; keep them out of the way of the drop-in
 	# modules of the same names by importing under a private prefix
 	saved_path = list(sys.path)
-	saved_modules = {n: sys.modules.get(n) for n in ('models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers', 'shaping', 'transcripts')}
+	saved_modules = {n: sys.modules.get(n) for n in ('models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers', 'shaping', 'transcripts', 'datasets', 'optimizers', 'audio', 'utils', 'text_processing')}
 	for n in saved_modules:
 		sys.modules.pop(n, None)
 	sys.path.insert(0, REFERENCE_DIR)
 	try:
 		for n in ('shaping', 'transcripts', 'models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers'):
 			_CACHE[n] = importlib.import_module(n)
+		try:  # the batch feed's collate_fn (datasets.py:305-332); pulls in text_processing / audio / utils
+			import warnings
+			with warnings.catch_warnings():
+				warnings.simplefilter('ignore')
+				_CACHE['datasets'] = importlib.import_module('datasets')
+		except Exception:
+			_CACHE['datasets'] = None
 	finally:
 		sys.path[:] = saved_path
 		for n, m in saved_modules.items():

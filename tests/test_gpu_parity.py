@@ -340,3 +340,29 @@ def test_grouped_conv_relu_kernel(dev, C_in, C_out, groups, k):
 		assert got.shape == (B, T, ld_out)
 		assert rel(got[:, :, :C_out].permute(0, 2, 1), ref) < tol, (tier, rel(got[:, :, :C_out].permute(0, 2, 1), ref))
 		assert float(got[:, :, C_out:].abs().max()) == 0.0 if ld_out > C_out else True
+
+
+def test_device_feeder_prefetch(dev):
+	"""feed.DeviceFeeder: batches arrive on the GPU unchanged and in order while the next upload is already in
+	flight on the copy stream; pinned staging buffers are recycled (train.py:745)."""
+	from convasr_b200 import feed
+	from oracle import make_golden
+	pool = feed.PinnedPool()
+	name, items, multiple = make_golden.feed_batches()[0]
+	want = [feed.collate(items[k:] + items[:k], multiple) for k in range(4)]  # 4 different batches (rotations)
+
+	def host_batches():
+		for k in range(4):
+			yield feed.collate(items[k:] + items[:k], multiple, pool = pool)
+
+	feeder = feed.DeviceFeeder(host_batches(), dev, pool = pool)
+	n = 0
+	for (meta, s, x, xlen, y, ylen), ref_b in zip(feeder, want):
+		assert x.is_cuda and x.dtype == torch.int16 and xlen.dtype == torch.float32
+		_ = (x.float() * 2).sum()  # some work on the consumer stream
+		for got, exp in ((x, ref_b[2]), (xlen, ref_b[3]), (y, ref_b[4]), (ylen, ref_b[5])):
+			assert torch.equal(got.cpu(), exp)
+		assert [m['example_id'] for m in meta] == [m['example_id'] for m in ref_b[0]]
+		n += 1
+	assert n == 4 and feeder.bytes_uploaded == sum(t.numel() * t.element_size() for b in want for t in b[2:])
+	assert sum(len(v) for v in pool.free.values()) >= 4  # staging buffers came back

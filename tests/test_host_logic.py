@@ -145,3 +145,43 @@ def test_training_path_matches_oracle_on_cpu_modules(golden):
 			logits = m.decoder(x)[0]
 		rel = float((logits - c['logits']).norm() / c['logits'].norm())
 		assert rel < 1e-4, (c['model'], rel)
+
+
+# ------------------------------------------------------------------------------------------ batch feed
+def test_collate_matches_reference_collate_fn(golden):
+	"""feed.collate == AudioTextDataset.collate_fn (datasets.py:305-332) on the items oracle/make_golden.py fed the
+	reference: same shapes, dtypes (int16 PCM stays int16), zero padding to the time multiple, fp32 length fractions,
+	speaker padding; also through the recycling pool (buffers come back dirty and must be re-initialised)."""
+	from convasr_b200 import feed
+	from oracle import make_golden
+	pool = feed.PinnedPool(pin = False)
+	for rep in range(2):
+		for (name, items, multiple), c in zip(make_golden.feed_batches(), golden('feed')['cases']):
+			assert name == c['name']
+			meta, s, x, xlen, y, ylen = feed.collate(items, time_padding_multiple = multiple, pool = pool)
+			assert [m['example_id'] for m in meta] == [m['example_id'] for m in c['meta']]
+			for got, want in ((s, c['s']), (x, c['x']), (xlen, c['xlen']), (y, c['y']), (ylen, c['ylen'])):
+				assert got.dtype == want.dtype and got.shape == want.shape and torch.equal(got, want), name
+			pool.give(s, x, xlen, y, ylen)
+			for t in (s, x, xlen, y, ylen):
+				t.fill_(7)  # poison what went back to the pool
+	# batch mode: fields arrive as lists and are zipped first (datasets.py:307-308)
+	name, items, multiple = make_golden.feed_batches()[0]
+	a = feed.collate(items, multiple)
+	b = feed.collate(list(map(list, zip(*items))), multiple, batch_mode = True)
+	assert all(torch.equal(u, v) for u, v in zip(a[1:], b[1:]))
+
+
+@pytest.mark.reference
+def test_collate_matches_live_reference():
+	import types
+	from convasr_b200 import feed
+	from oracle import make_golden, reference_shim
+	ref = reference_shim.load()
+	if ref.datasets is None:
+		pytest.skip('reference datasets module not importable here')
+	for name, items, multiple in make_golden.feed_batches():
+		fake_self = types.SimpleNamespace(mode = ref.datasets.AudioTextDataset.DEFAULT_MODE, time_padding_multiple = multiple)
+		theirs = ref.datasets.AudioTextDataset.collate_fn(fake_self, items)
+		ours = feed.collate(items, multiple)
+		assert all(torch.equal(a, b) and a.dtype == b.dtype for a, b in zip(ours[1:], theirs[1:])), name
