@@ -19,7 +19,9 @@ BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
 
 value  = whole-job audio-seconds / second with the PCM already resident in HBM (CUDA events).
 e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM + targets
-         -> H2D, the step, D2H of the per-utterance loss (and the greedy ids for inference).
+         -> H2D through convasr_b200.feed.DeviceFeeder (every step uploads its own batch; the copy of step
+         i+1 overlaps the compute of step i), the step, D2H of the per-utterance loss (and the greedy
+         ids for inference).
 N > 1  = per-GPU batch fixed (weak scaling); time = max over ranks.
 --impl reference = the CPU oracle port of the reference path (torch CPU ops, all host threads) on a
          bounded sample of the same workload.
@@ -223,6 +225,10 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	sig_pin, xlen_pin, y_pin, ylen_pin = [t.pin_memory() for t in (sig, xlen, y, ylen)]
 	sig_d, xlen_d, y_d, ylen_d = [t.to(dev) for t in (sig, xlen, y, ylen)]
 	flush = torch.empty(256 << 20, dtype = torch.uint8, device = dev)
+	# e2e leg: the public batch feed (convasr_b200/feed.py) -- every step uploads its own pinned host batch; the copy of
+	# step i+1 is issued on a copy stream while step i computes (the timed region still contains one full H2D per step)
+	from convasr_b200 import feed as feed_mod
+	feeder = iter(feed_mod.DeviceFeeder(((None, None, sig_pin, xlen_pin, y_pin, ylen_pin) for _ in range(steps + 16)), dev))
 	Fr = sig.shape[1] // 80 + 1
 	flops_fwd, t_out = conv_flops_per_step(model, B, Fr)
 	first = model.backbone[0].conv[0][0]
@@ -255,7 +261,8 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			return run[0](sig_d, xlen_d, y_d, ylen_d)
 
 		def step_e2e():
-			per_utt = run[0](*[t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)])
+			_, _, s, xl, yy, yl = next(feeder)  # this step's H2D was issued on the copy stream during the previous step
+			per_utt = run[0](s, xl, yy, yl)
 			return per_utt.detach().cpu()
 
 		d2h = B * 4
@@ -275,7 +282,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 			return nll
 
 		def step_e2e():
-			s, xl, yy, yl = [t.to(dev, non_blocking = True) for t in (sig_pin, xlen_pin, y_pin, ylen_pin)]
+			_, _, s, xl, yy, yl = next(feeder)
 			out = model(s, xl, y = yy, ylen = yl)
 			return out['loss'].cpu(), out['log_probs'][0]._convasr_argmax.cpu()
 
