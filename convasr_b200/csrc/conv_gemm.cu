@@ -574,14 +574,25 @@ static int encode_map_3d(CUtensorMap* map, const void* base, uint64_t d0, uint64
     return 0;
 }
 
-static int pick_block_n(int C_out, int epilogue) {
+static int pick_block_n(int C_out, int epilogue, long long m_tiles, int num_sms) {
     if (epilogue == CAB_EPI_LOGSOFTMAX) return ((C_out + 15) / 16) * 16;
-    // fewest N tiles first, then least padding; multiples of 32 so the epilogue works in
-    // 32-column TMEM loads.
-    const int n_tiles = (C_out + kMaxBlockN - 1) / kMaxBlockN;
-    int bn = (C_out + n_tiles - 1) / n_tiles;
-    bn = ((bn + 31) / 32) * 32;
-    return bn;
+    // N tile (multiple of 32: the epilogue works in 32-column TMEM loads).  A k-step costs ~(block_n + 96)
+    // (MMA time grows with block_n, the A-tile load and the per-step latencies do not) and the persistent
+    // grid needs ceil(tiles / #SMs) rounds: large batches end up with the fewest, widest tiles (256 -> 1x256,
+    // 640 -> 3x224, 896 -> 4x224), small batches (B = 8: 32 M tiles for 148 SMs) split N further so that
+    // every SM gets a tile.
+    int best_bn = 0;
+    double best_cost = 0.0;
+    const int min_tiles = (C_out + kMaxBlockN - 1) / kMaxBlockN;
+    for (int n_tiles = min_tiles; n_tiles <= min_tiles * 8; ++n_tiles) {
+        int bn = (C_out + n_tiles - 1) / n_tiles;
+        bn = ((bn + 31) / 32) * 32;
+        if (bn < 64 && n_tiles > min_tiles) break;
+        const long long tiles = m_tiles * ((C_out + bn - 1) / bn);
+        const double cost = (double)((tiles + num_sms - 1) / num_sms) * (bn + 96);
+        if (best_bn == 0 || cost < best_cost * 0.98) { best_bn = bn; best_cost = cost; }
+    }
+    return best_bn;
 }
 
 extern std::atomic<int64_t> g_launch_count;
@@ -604,7 +615,14 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     p.B = ep->B;
     p.T_out = ep->T_out;
     p.C_out = ep->C_out;
-    int bn = ep->block_n > 0 ? ep->block_n : pick_block_n(ep->C_out, ep->epilogue);
+    static int sms_for_tiling = 0;
+    if (sms_for_tiling == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms_for_tiling, cudaDevAttrMultiProcessorCount, dev);
+        if (sms_for_tiling <= 0) sms_for_tiling = 148;
+    }
+    int bn = ep->block_n > 0 ? ep->block_n : pick_block_n(ep->C_out, ep->epilogue, (long long)ep->B * ((ep->T_out + kBlockM - 1) / kBlockM), sms_for_tiling);
     CAB_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= kMaxBlockN, "block_n=%d must be a multiple of 16 in [16,256]", bn);
     if (ep->epilogue == CAB_EPI_ACT_BF16) {
         CAB_CHECK_ARG(bn % 32 == 0, "block_n=%d must be a multiple of 32 for the bf16 epilogue", bn);

@@ -81,8 +81,10 @@ class DeviceFeeder:
 	"""Iterates host batches `(meta, s, x, xlen, y, ylen)` and yields them with x, xlen, y, ylen on the GPU
 	(train.py:745), uploading batch i+1 on a dedicated copy stream while the caller computes on batch i.
 
-	The consumer's stream waits on the copy's event (no host synchronisation); device buffers are handed to
-	the caching allocator with `record_stream`, pinned host buffers go back to `pool` once their copy is done."""
+	Device memory is a ring of `depth + 1` slots that are reused (no allocator traffic in steady state): the upload
+	into a slot waits, on the copy stream, for the event the consumer's stream recorded when it asked for the batch
+	AFTER the one that last lived in that slot; the consumer's stream waits for the copy's event.  No host
+	synchronisation on the data path; pinned host buffers go back to `pool` once their copy has completed."""
 
 	def __init__(self, batches, device, pool = None, depth = 2):
 		self.it = iter(batches)
@@ -90,8 +92,17 @@ class DeviceFeeder:
 		self.pool = pool
 		self.depth = max(1, depth)
 		self.copy_stream = torch.cuda.Stream(device = self.device)
+		self.slots = [dict(buffers = [None] * 4, free = None) for _ in range(self.depth + 1)]
+		self.n_uploaded = 0
 		self.queue = []
 		self.bytes_uploaded = 0
+
+	def _slot_view(self, slot, k, host):
+		nbytes = host.numel() * host.element_size()
+		buf = slot['buffers'][k]
+		if buf is None or buf.numel() < nbytes:
+			buf = slot['buffers'][k] = torch.empty(max(256, 1 << (nbytes - 1).bit_length()) if nbytes > 0 else 256, dtype = torch.uint8, device = self.device)
+		return buf[:nbytes].view(host.dtype).view(host.shape)
 
 	def _upload_next(self):
 		try:
@@ -99,24 +110,37 @@ class DeviceFeeder:
 		except StopIteration:
 			return False
 		host = (x, xlen, y, ylen)
+		slot = self.slots[self.n_uploaded % len(self.slots)]
+		self.n_uploaded += 1
 		with torch.cuda.stream(self.copy_stream):
-			dev = tuple(t.to(self.device, non_blocking = True) for t in host)
+			if slot['free'] is not None:
+				self.copy_stream.wait_event(slot['free'])  # the consumer is done with the batch that lived here
+			dev = tuple(self._slot_view(slot, k, t) for k, t in enumerate(host))
+			for d, h in zip(dev, host):
+				d.copy_(h, non_blocking = True)
 			done = torch.cuda.Event()
 			done.record(self.copy_stream)
 		self.bytes_uploaded += sum(t.numel() * t.element_size() for t in host)
-		self.queue.append((meta, s, dev, host, done))
+		self.queue.append((meta, s, dev, host, done, slot))
 		return True
 
 	def __iter__(self):
 		while len(self.queue) < self.depth and self._upload_next():
 			pass
+		previous = None
 		while self.queue:
-			meta, s, dev, host, done = self.queue.pop(0)
-			torch.cuda.current_stream(self.device).wait_event(done)
+			meta, s, dev, host, done, slot = self.queue.pop(0)
+			consumer = torch.cuda.current_stream(self.device)
+			if previous is not None:
+				# everything the caller enqueued for the previous batch precedes this point of its stream
+				previous['free'] = torch.cuda.Event()
+				previous['free'].record(consumer)
+			consumer.wait_event(done)
 			for t in dev:
-				t.record_stream(torch.cuda.current_stream(self.device))
+				t.record_stream(consumer)  # the slot's memory was allocated on the copy stream; matters only if a slot is ever re-grown
 			self._upload_next()  # goes out while the caller works on `dev`
 			if self.pool is not None:
-				done.synchronize()  # already complete in steady state: this batch was uploaded `depth` steps ago
+				done.synchronize()  # complete in steady state: this batch was uploaded `depth` steps ago
 				self.pool.give(*host)
+			previous = slot
 			yield (meta, s) + dev
