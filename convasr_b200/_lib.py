@@ -34,6 +34,10 @@ class ConvEpilogue(ctypes.Structure):
 	]
 
 
+class PackItem(ctypes.Structure):
+	_fields_ = [('w', c_void_p), ('fwd', c_void_p), ('dgrad', c_void_p), ('Co', c_i32), ('Ci', c_i32), ('K', c_i32), ('ci_ld', c_i32), ('co_ld', c_i32)]
+
+
 ACT_NONE, ACT_RELU, ACT_HARDTANH, ACT_LEAKY_RELU = 0, 1, 2, 3
 EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
 MAX_CONV_SOURCES = 18
@@ -57,6 +61,7 @@ SIGNATURES = {
 	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
 							c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p, c_void_p],
 	'cab_pack_weight': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+	'cab_pack_weights_batched': [ctypes.POINTER(PackItem), c_int, c_void_p],
 	'cab_unpack_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
 	'cab_bct_to_btc': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 	'cab_optimizer_step': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

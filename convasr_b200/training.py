@@ -80,6 +80,22 @@ def _pack(w, ci_ld, co_ld, want_dgrad):
 	return fwd, dgr
 
 
+def _pack_all(specs):
+	"""specs: [(w fp32 [Co, Ci, K], ci_ld, co_ld, want_dgrad)] -> [(fwd bf16 [K, Co, ci_ld], dgrad bf16 [K, Ci, co_ld] or None)]
+	in ONE launch (cab_pack_weights_batched)"""
+	out, items = [], (_lib.PackItem * len(specs))()
+	for i, (w, ci_ld, co_ld, want_dgrad) in enumerate(specs):
+		Co, Ci, K = w.shape
+		fwd = torch.zeros(K, Co, ci_ld, dtype = BF16, device = w.device) if ci_ld != Ci else torch.empty(K, Co, ci_ld, dtype = BF16, device = w.device)
+		dgr = None
+		if want_dgrad:
+			dgr = torch.zeros(K, Ci, co_ld, dtype = BF16, device = w.device) if co_ld != Co else torch.empty(K, Ci, co_ld, dtype = BF16, device = w.device)
+		items[i] = _lib.PackItem(w.data_ptr(), fwd.data_ptr(), dgr.data_ptr() if dgr is not None else None, Co, Ci, K, ci_ld, co_ld)
+		out.append((fwd, dgr))
+	_lib.check(_lib.load().cab_pack_weights_batched(items, len(specs), ops._stream()), 'cab_pack_weights_batched')
+	return out
+
+
 def _bn_finalize(sums, n_rows, layer):
 	"""sums: fp32 [2, co_alloc] accumulated by the conv epilogue -> [scale, shift, mean, invstd] + running stats"""
 	bn = layer.bn
@@ -108,6 +124,11 @@ class NativeStack(torch.autograd.Function):
 		T = holder['n_frames']
 		x, x_T = feats, T
 		saved = []
+		# bf16 operand copies of every stride-1 conv weight and of the decoder, in one launch
+		dec = model.decoder[0]
+		plain = [li for li, L in enumerate(layers) if L.stride != 2]
+		packed_w = _pack_all([(layers[li].conv.weight.detach(), layers[li].ci_alloc, layers[li].co_alloc, li > 0) for li in plain] + [(dec.weight.detach(), engine._ceil_to(dec.in_channels, 64), engine._ceil_to(dec.out_channels, 64), True)])
+		packed_w, (w_dec, w_dec_dgr) = dict(zip(plain, packed_w[:-1])), packed_w[-1]
 		for li, L in enumerate(layers):
 			w = L.conv.weight
 			if L.stride == 2:
@@ -120,7 +141,7 @@ class NativeStack(torch.autograd.Function):
 				skip = None
 			else:
 				skip = None
-				w_fwd, w_dgr = _pack(w.detach(), L.ci_alloc, L.co_alloc, want_dgrad = li > 0)
+				w_fwd, w_dgr = packed_w[li]
 				src = ops.Source(x, w_fwd, L.ci_alloc, L.k, L.dil, L.pad, T_in = x_T)
 				T_out = x_T + 2 * L.pad - L.dil * (L.k - 1)
 				geom = ('plain', L.k, L.pad)
@@ -145,9 +166,7 @@ class NativeStack(torch.autograd.Function):
 			saved.append((x, x_T, y, T_out, ss, w_dgr, geom))
 			x, x_T = out, T_out
 		torch._foreach_add_([L.bn.num_batches_tracked for L in layers], 1)
-		dec = model.decoder[0]
 		C = dec.out_channels
-		w_dec, w_dec_dgr = _pack(dec.weight.detach(), engine._ceil_to(dec.in_channels, 64), engine._ceil_to(C, 64), want_dgrad = True)
 		logits = torch.empty(B, C, x_T, dtype = torch.float32, device = x.device)
 		log_probs = torch.empty_like(logits)
 		argmax = torch.empty(B, x_T, dtype = torch.int32, device = x.device)

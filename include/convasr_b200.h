@@ -185,6 +185,14 @@ int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, in
  * [K,Ci,ld]) into the parameter layout. */
 int cab_pack_weight(const float* w, int Co, int Ci, int K, void* fwd, int ci_ld, void* dgrad, int co_ld,
                     cab_stream_t stream);
+/* the same for up to 32 weights in one launch (all layers of a model at the start of a training step) */
+typedef struct {
+    const float* w;  /* fp32 [Co, Ci, K] */
+    void* fwd;       /* bf16 [K, Co, ci_ld] or NULL */
+    void* dgrad;     /* bf16 [K, Ci, co_ld] (taps flipped) or NULL */
+    int32_t Co, Ci, K, ci_ld, co_ld;
+} cab_pack_item_t;
+int cab_pack_weights_batched(const cab_pack_item_t* items_host, int n_items, cab_stream_t stream);
 int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad,
                      int accumulate, cab_stream_t stream);
 /* fp32 [B,C,T] (gradient w.r.t. the logits) -> bf16 channels-last [B,T,ld]; class_sums (fp32 [C],

@@ -408,3 +408,20 @@ def test_training_step_same_with_and_without_padding_skip():
 			training._SKIP_PADDING = True
 	assert rel(res[1][0], res[0][0]) < 1e-3, rel(res[1][0], res[0][0])  # forward: same numbers up to the order of the fp32 atomics behind the BN statistics (measured 1e-5)
 	assert rel(res[1][1], res[0][1]) < 1e-2, rel(res[1][1], res[0][1])  # run-to-run atomics noise amplified by the backward (see above)
+
+
+def test_batched_weight_pack_equals_per_layer_pack():
+	from convasr_b200 import training
+	dev = torch.device('cuda:0')
+	g = torch.Generator().manual_seed(2)
+	shapes = [(256, 64, 11), (384, 256, 11), (896, 768, 29), (1024, 896, 1), (38, 1024, 1), (70, 50, 5)]
+	ws = [torch.randn(*s, generator = g).to(dev) for s in shapes]
+	specs = [(w, (w.shape[1] + 63) // 64 * 64, (w.shape[0] + 63) // 64 * 64, i != 0) for i, w in enumerate(ws)]
+	batched = training._pack_all(specs)
+	for (w, ci_ld, co_ld, want_dgrad), (fwd, dgr) in zip(specs, batched):
+		fwd1, dgr1 = training._pack(w, ci_ld, co_ld, want_dgrad)
+		assert torch.equal(fwd, fwd1) and (dgr is None) == (dgr1 is None) and (dgr is None or torch.equal(dgr, dgr1))
+		Co, Ci, K = w.shape
+		assert torch.equal(fwd[:, :, :Ci], w.permute(2, 0, 1).to(BF16))
+		if dgr is not None:
+			assert torch.equal(dgr[:, :, :Co], w.flip(2).permute(2, 1, 0).to(BF16))
