@@ -619,8 +619,11 @@ JasperNetBigInplace = _jasper_family('JasperNetBigInplace', 'models.py:1430-1442
 
 def entropy(log_probs, lengths = None, dim = 1, eps = 1e-9, sum = True, keepdim = False):
 	"""models.py:645-658.  The default reduction runs the fused native kernel."""
-	if dim == 1 and sum and not keepdim and log_probs.ndim == 3 and log_probs.is_cuda and eps == 1e-9:
+	if not log_probs.is_cuda:
+		raise RuntimeError('convasr_b200: entropy() runs on CUDA tensors only (there is no CPU fallback)')
+	if dim == 1 and sum and not keepdim and log_probs.ndim == 3 and eps == 1e-9:
 		return ops.entropy(log_probs, lengths)[0]
+	# non-default reductions (other dim / keepdim / per-frame output): same formula on the GPU, unfused
 	e = -(log_probs.exp() * log_probs).sum(dim = dim, keepdim = keepdim)
 	if lengths is not None:
 		e = e * temporal_mask(e, lengths)
@@ -631,7 +634,9 @@ def entropy(log_probs, lengths = None, dim = 1, eps = 1e-9, sum = True, keepdim 
 
 def weighted_mean_entropy(log_probs, lengths = None, dim = -2, eps = 1e-9, eps_id = -1):
 	"""models.py:661-673"""
-	if dim in (-2, 1) and log_probs.ndim == 3 and log_probs.is_cuda and eps == 1e-9:
+	if not log_probs.is_cuda:
+		raise RuntimeError('convasr_b200: weighted_mean_entropy() runs on CUDA tensors only (there is no CPU fallback)')
+	if dim in (-2, 1) and log_probs.ndim == 3 and eps == 1e-9:
 		return ops.entropy(log_probs, lengths, eps_id = eps_id)[1]
 	prob = log_probs.exp()
 	e = -(prob * log_probs).sum(dim = dim)
