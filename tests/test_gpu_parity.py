@@ -366,3 +366,29 @@ def test_device_feeder_prefetch(dev):
 		n += 1
 	assert n == 4 and feeder.bytes_uploaded == sum(t.numel() * t.element_size() for b in want for t in b[2:])
 	assert sum(len(v) for v in pool.free.values()) >= 4  # staging buffers came back
+
+
+def test_tiny_utterances_in_a_ragged_batch(dev):
+	"""Edge case of a ragged batch: an utterance shorter than one frame hop (one valid frame; every other tile of
+	it is padding and is skipped) must not disturb its neighbours and equals its own stand-alone result; padded
+	frames carry the decoder bias (quirk 6)."""
+	from convasr_b200 import models
+	torch.manual_seed(0)
+	m = models.Wav2Letter(64, [38], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, base_width = 32)
+	shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')}
+	m.load_state_dict(O.synth_state_dict(shapes, seed = 3), strict = False)
+	m = m.to(dev).eval().set_precision('fp32')
+	g = torch.Generator().manual_seed(5)
+	T = 24000
+	sig = (torch.randn(4, T, generator = g) * 3000).round().clamp(-32767, 32767).to(torch.int16)
+	xlen = torch.tensor([1.0, 30 / T, 0.37, 0.5])
+	with torch.no_grad():
+		out = m(sig.to(dev), xlen.to(dev))
+		solo = [m(sig[k:k + 1].to(dev), xlen[k:k + 1].to(dev)) for k in (1, 2)]
+	logits, olen = out['logits'][0], out['olen'][0]
+	assert int(olen[1]) == 1 and bool(torch.isfinite(logits).all())
+	for k, s1 in zip((1, 2), solo):
+		assert rel(logits[k], s1['logits'][0][0]) < 1e-5, k
+		n = int(olen[k])
+		bias = m.decoder[0].bias.detach()
+		assert torch.allclose(logits[k][:, n:], bias[:, None].expand(-1, logits.shape[2] - n), atol = 1e-6)
