@@ -62,7 +62,11 @@ def test_bn_act_mask_forward_backward_kernels():
 		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), 0.0, None, 0, ops._stream()), 'fwd')
 		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
 		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._p(part), ops._stream()), 'bwd')
+		# without the replica scratch the row-walker variant runs: same results
+		sums2 = torch.empty(2, C, device = dev); dy2 = torch.empty_like(yd)
+		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums2), ops._p(dy2), 0.0, None, 0, None, ops._stream()), 'bwd (row walker)')
 		torch.cuda.synchronize()
+		assert rel(sums2, sums) < 1e-5 and rel(dy2.float(), dy.float()) < 1e-3, act_name
 		assert rel(out.float().permute(0, 2, 1), o) < 4e-3, act_name  # bf16 output rounding
 		assert torch.allclose(rm_d.cpu(), rm_ref, atol = 1e-5) and torch.allclose(rv_d.cpu(), rv_ref, rtol = 1e-4, atol = 1e-5)
 		assert rel(sums[0], br.grad) < 1e-4 and rel(sums[1], gr.grad) < 1e-4, act_name
