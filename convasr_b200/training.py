@@ -3,16 +3,21 @@
 What `model.train(); loss.backward()` does in the reference through autograd + cuDNN/ATen
 (ConvBn1d.forward models.py:127-139, train.py:748-774) runs here on this repo's kernels:
 
-  forward, per conv repeat   y = conv(x)                    cab_conv1d_fused   (tcgen05 implicit GEMM)
-                             batch mean / var, running stats cab_bn_batch_stats
-                             x' = act(BN(y)) * mask          cab_bn_act_mask_fwd
+  step start                 bf16 operand copies of all weights cab_pack_weights_batched (one launch)
+  forward, per conv repeat   y = conv(x) + batch sums in the epilogue cab_conv1d_fused (tcgen05 implicit GEMM)
+                             mean / invstd, running stats    cab_bn_finalize
+                             x' = dropout(act(BN(y))) * mask cab_bn_act_mask_fwd (bulk-copy streamed)
   decoder                    logits, log_probs               cab_conv1d_fused   (LOGSOFTMAX epilogue)
   backward, per conv repeat  dz -> (dgamma, dbeta), dy       cab_bn_act_mask_bwd
                              dW = dy (x) x over time         cab_conv1d_wgrad   (tcgen05, MN-major operands)
                              dx = conv(dy, flipped W^T)      cab_conv1d_fused   (same kernel as forward)
+                             all-reduce(dW) on the comm stream parallel.GradSync (data-parallel replicas)
+
+On ragged batches the three GEMMs leave out tiles that lie entirely in an utterance's padding (the
+previous layer's mask makes the inputs exact zeros there; masked gradient rows are never read).
 
 Activations are bf16 channels-last, parameters stay fp32 masters (bf16 operand copies are re-packed
-every step by cab_pack_weight), all gradients are fp32.  Supported topologies: dense (non-separable)
+every step), all gradients are fp32.  Supported topologies: dense (non-separable)
 blocks without residual branches -- the Wav2Letter family, with or without dropout (dropout masks come
 from a counter-based generator of this repo, not from torch's Philox stream); anything else keeps using
 the ATen path in models.JasperNet._forward_training.
