@@ -185,3 +185,33 @@ def test_collate_matches_live_reference():
 		theirs = ref.datasets.AudioTextDataset.collate_fn(fake_self, items)
 		ours = feed.collate(items, multiple)
 		assert all(torch.equal(a, b) and a.dtype == b.dtype for a, b in zip(ours[1:], theirs[1:])), name
+
+
+# ------------------------------------------------------------------------------------------ bench contract
+def test_bench_reference_arm_prints_the_contract_line():
+	"""`bench.py --impl reference` (the CPU oracle port timed on the host cores) prints ONE JSON line with the
+	keys the driver reads; runs without a GPU."""
+	import json
+	import os
+	import subprocess
+	import sys
+	ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--cpu-sample-batch', '2', '--workload', 'wav2letter_char_fwd_ctc_B8x10s_fp32'], capture_output = True, text = True, timeout = 600, env = dict(os.environ, CUDA_VISIBLE_DEVICES = ''))
+	assert out.returncode == 0, out.stderr[-2000:]
+	lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+	assert len(lines) == 1
+	d = json.loads(lines[0])
+	assert d['impl'] == 'reference' and d['metric'] == 'audio_seconds_per_second' and d['unit'] == 'audio-s/s'
+	assert d['higher_is_better'] is True and d['value'] > 0 and d['gpu_launches'] == 0
+	assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+	assert d['e2e'] == dict(value = d['value'], unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0)
+	assert d['config']['workload'] == 'wav2letter_char_fwd_ctc_B8x10s_fp32'
+
+
+def test_native_training_coverage_by_model_class():
+	"""training.supported(): the dense, residual-free families train on the native kernels, everything else takes the
+	documented ATen path."""
+	from convasr_b200 import models, training
+	native = {name for name in ALL_MODELS if training.supported(getattr(models, name)(64, [38], **(dict(base_width = 128) if 'Separable' in name else dict(base_width = 16))))}
+	assert 'Wav2Letter' in native and all(n.startswith('Wav2Letter') for n in native), native
+	assert not any('Jasper' in n for n in native)
