@@ -329,14 +329,14 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	torch.cuda.synchronize()
 	assert bool(torch.isfinite(nll).all()), 'synthetic targets must admit an alignment'
 	sampler = ClockSampler(local_rank)
-	if rank == 0 and full:
+	if rank == 0:
 		sampler.start()
 	barrier()
 	t_wall0 = time.time()
 	ms = timed(step_device, steps)
 	barrier()
 	t_wall1 = time.time()
-	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 and full else None
+	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 	result = dict(ms = ms, ms_e2e = None)
 	roofline = None
 	if full:
@@ -453,7 +453,7 @@ def main():
 		for name2 in SECONDARY_WORKLOADS:
 			r2 = measure(name2, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
 			ms2, = reduce_max([r2['ms']])
-			also[name2] = dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, lengths = r2['config']['lengths'], valid_audio_fraction = r2['valid_fraction'], step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'])
+			also[name2] = dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, lengths = r2['config']['lengths'], valid_audio_fraction = r2['valid_fraction'], step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'], clocks = r2['clocks'])
 	if rank == 0:
 		audio_s = r['B'] * r['seconds'] * world
 		line = dict(
