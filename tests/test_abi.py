@@ -53,3 +53,20 @@ def test_cpu_tensors_are_rejected_loudly():
 	m = models.Wav2Letter(64, [38], base_width = 8).eval()
 	with pytest.raises(RuntimeError, match = 'no CPU fallback'):
 		m(torch.zeros(1, 64, 32))
+
+
+def test_ctypes_table_matches_header_prototypes():
+	"""every prototype's parameter count equals the ctypes argtypes the Python side binds (the table is kept by hand);
+	the structs passed by pointer have the sizes the header's layouts imply"""
+	from convasr_b200 import _lib
+	src = open(os.path.join(ROOT, 'include', 'convasr_b200.h')).read()
+	src = re.sub(r'/\*.*?\*/', '', src, flags = re.S)
+	protos = dict(re.findall(r'\bint\s+(cab_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', src, flags = re.S))
+	for name, argtypes in _lib.SIGNATURES.items():
+		assert name in protos, name
+		params = [p for p in protos[name].split(',') if p.strip() and p.strip() != 'void']
+		assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+	assert ctypes.sizeof(_lib.PackItem) == 48  # 3 pointers + 5 int32, padded to 8
+	assert _lib.ConvEpilogue.skip_frac.offset == _lib.ConvEpilogue.stats.offset + 8
+	assert _lib.ConvEpilogue.skip_margin.offset == _lib.ConvEpilogue.skip_frac.offset + 12
+	assert ctypes.sizeof(_lib.ConvEpilogue) == _lib.ConvEpilogue.skip_frac.offset + 16
