@@ -448,7 +448,7 @@ def main():
 	r = measure(args.workload, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = rank == 0 and world == 1 and not args.no_cpu_baseline, full = True)
 	ms, ms_e2e = reduce_max([r['ms'], r['ms_e2e']])
 	also = None
-	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD:
+	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD and world == 1:  # the scaling runs (N > 1) measure the headline workload only
 		also = {}
 		for name2 in SECONDARY_WORKLOADS:
 			r2 = measure(name2, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
