@@ -167,14 +167,20 @@ def _activation(y, act):
 	raise ValueError(act)
 
 
-def _bn_eval(y, sd, prefix, eps = 1e-5, training = False):
+def _bn_eval(y, sd, prefix, eps = 1e-5, training = False, stats_out = None):
 	"""nn.BatchNorm1d (models.py:112-113): eval mode uses the running statistics; training mode the
 	biased batch statistics over all B*t positions (padded frames included -- the mask comes after the
-	activation, models.py:135-138).  Absent keys = already fused (Identity)."""
+	activation, models.py:135-138) and moves the running statistics with momentum 0.1 (running_var with the
+	unbiased batch variance); `stats_out` receives the updated buffers.  Absent keys = already fused (Identity)."""
 	if prefix + '.running_mean' not in sd:
 		return y
 	if training:
-		return F.batch_norm(y, None, None, sd[prefix + '.weight'], sd[prefix + '.bias'], True, 0.1, eps)
+		rm = rv = None
+		if stats_out is not None:
+			rm, rv = sd[prefix + '.running_mean'].detach().clone().float(), sd[prefix + '.running_var'].detach().clone().float()
+			stats_out[prefix + '.running_mean'], stats_out[prefix + '.running_var'] = rm, rv
+			stats_out[prefix + '.num_batches_tracked'] = sd[prefix + '.num_batches_tracked'] + 1
+		return F.batch_norm(y, rm, rv, sd[prefix + '.weight'], sd[prefix + '.bias'], True, 0.1, eps)
 	g, b = sd[prefix + '.weight'], sd[prefix + '.bias']
 	m, v = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
 	return (y - m[None, :, None]) / torch.sqrt(v[None, :, None] + eps) * g[None, :, None] + b[None, :, None]
@@ -192,7 +198,7 @@ def _round_bf16(t):
 	return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
 
 
-def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False, round_bf16 = False):
+def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False, round_bf16 = False, stats_out = None):
 	"""JasperNet.forward models.py:303-317 (backbone, decoder, log_softmax) in eval mode.
 
 	x: normalised features [B, C, F].  Returns (logits list, log_probs list, olen list)."""
@@ -219,14 +225,14 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 				y = F.conv1d(y.relu(), sd[p + '.2.weight'], sd.get(p + '.2.bias'))
 			else:
 				y = rb(F.conv1d(x, rb(w), sd.get(p + '.0.bias'), stride = stride, padding = pad, dilation = dil))
-			y = _bn_eval(y, sd, f'backbone.{i}.bn.{j}', training = training)
+			y = _bn_eval(y, sd, f'backbone.{i}.bn.{j}', training = training, stats_out = stats_out)
 			if j == reps - 1:  # residuals join on the last repeat only (models.py:129-133)
 				assert n_res == len(res) or not residual
 				for r, rx in enumerate(res[:n_res] if residual else []):
 					pr = f'backbone.{i}.conv_residual.{r}'
 					if pr + '.weight' in sd:
 						ry = F.conv1d(rx, sd[pr + '.weight'], sd.get(pr + '.bias'))
-						ry = _bn_eval(ry, sd, f'backbone.{i}.bn_residual.{r}', training = training)
+						ry = _bn_eval(ry, sd, f'backbone.{i}.bn_residual.{r}', training = training, stats_out = stats_out)
 					else:  # 'flat' residual: Identity (models.py:117,121)
 						ry = rx
 					y = y + ry
@@ -244,6 +250,13 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 		else:
 			res = []
 	logits = [F.conv1d(x, rb(sd['decoder.0.weight']), sd['decoder.0.bias'])]  # models.py:26
+	if 'decoder.1.0.conv.0.0.weight' in sd:  # Decoder(type = 'bpe') models.py:27-33: two ConvBn1d(k = 15, relu, no lengths -> no mask)
+		h = x
+		for m in range(2):
+			w = sd[f'decoder.1.{m}.conv.0.0.weight']
+			h = F.conv1d(h, w, sd.get(f'decoder.1.{m}.conv.0.0.bias'), padding = w.shape[-1] // 2)
+			h = _bn_eval(h, sd, f'decoder.1.{m}.bn.0', training = training, stats_out = stats_out).relu()
+		logits.append(h)
 	log_probs = [F.log_softmax(l, dim = 1).to(torch.float32) for l in logits]  # :316
 	olen = [output_lengths(l.shape[-1], xlen) if xlen is not None else torch.full((len(l), ), l.shape[-1], dtype = torch.long) for l in logits]  # :317
 	return logits, log_probs, olen
@@ -461,11 +474,21 @@ def greedy_generate(tokenizer, ids, output_lengths = None, time_stamps = None, b
 
 
 def entropy(log_probs, lengths = None, eps = 1e-9):
+	"""models.py:645-658 (dim = 1, sum = True)"""
 	e = -(log_probs.exp() * log_probs).sum(dim = 1)
 	if lengths is None:
 		return e.mean(dim = -1)
 	e = e * (torch.arange(e.shape[-1])[None] < lengths[:, None])
 	return e.sum(dim = -1) / (eps + lengths.type_as(log_probs))
+
+
+def margin(log_probs):
+	"""models.py:676-677: `torch.sub(*probs.topk(2, dim = 1).values)` unpacks the BATCH dimension, so it is only
+	defined for B == 2 and returns top2(utt 0) - top2(utt 1) [2, T]; any other B raises TypeError.  Kept as is."""
+	vals = log_probs.exp().topk(2, dim = 1).values
+	if vals.shape[0] != 2:
+		raise TypeError(f'sub() takes 2 positional arguments but {vals.shape[0]} were given')
+	return vals[0] - vals[1]
 
 
 def weighted_mean_entropy(log_probs, lengths = None, eps = 1e-9, eps_id = -1):
@@ -505,6 +528,22 @@ def synth_state_dict(shapes, seed = 0):
 		else:
 			sd[k] = torch.randn(shape, generator = g)
 	return sd
+
+
+def smooth_regime(sd, seed = 0):
+	"""Exactness-harness weights: BatchNorm shifts of the BACKBONE moved to the middle of hardtanh(0, 20)'s linear
+	range (beta ~ 10, gamma in [0.5, 1.5] => 6.6 sigma from either kink), so that no activation gate can flip between
+	two implementations.  Every nonlinearity of the reference has a kink; in TRAIN mode a gate that flips changes the
+	gradient by O(1 / sqrt(elements)) -- measured here: the fp32 CPU oracle vs the reference itself differ by 1.7e-2 in
+	the full-depth Wav2Letter gradients (3 flips out of 59 k elements at conv layer 15) while every forward quantity
+	agrees to 3e-5.  In this regime the conv -> batch-stat BN -> mask chain is smooth, and kernel-chain exactness at
+	full depth can be asserted at 1e-3."""
+	g = torch.Generator().manual_seed(seed)
+	out = dict(sd)
+	for k, v in sd.items():
+		if k.startswith('backbone.') and '.bn' in k and k.endswith('.bias'):
+			out[k] = 10.0 + 0.1 * torch.randn(v.shape, generator = g)
+	return out
 
 
 # --------------------------------------------------------------------------------------------

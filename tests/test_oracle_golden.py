@@ -111,3 +111,101 @@ def test_oracle_against_live_reference():
 	ylen = torch.tensor([9, 5])
 	al_ref = ref.ctc.alignment(lp.permute(2, 0, 1), y, olen[0], ylen, blank = 37)
 	assert torch.equal(O.ctc_alignment(lp.permute(2, 0, 1), y, olen[0], ylen, 37), al_ref)
+
+
+# ------------------------------------------------------------------------------------------ train mode
+def golden_state_dict(c):
+	sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
+	if c['kwargs'].get('smooth'):
+		sd = O.smooth_regime(sd, seed = c['seed'])
+	assert abs(sum(float(v.double().abs().sum()) for v in sd.values() if v.is_floating_point()) - c['checksum']) < 1e-6 * c['checksum']
+	return sd
+
+
+def oracle_train_step(c, **kw):
+	"""the oracle's TRAIN-mode forward + autograd backward on a golden case -> (logits, loss[B], grads, stats)"""
+	sd = golden_state_dict(c)
+	leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone()) for k, v in sd.items()}
+	over = {k: v for k, v in c['kwargs'].items() if k in ('groups', )}
+	stats = {}
+	logits, log_probs, olen = O.model_forward(leaf, c['signal'], c['xlen'], model = c['model'], training = True, stats_out = stats, **over, **kw)
+	C = c['num_classes']
+	nll = O.ctc_loss_torch(log_probs[0].permute(2, 0, 1), c['y'][:, 0], olen[0], c['ylen'][:, 0], C - 1)
+	nll.mean().backward()  # == (loss / ylen * ylen).mean(), train.py:754-755
+	grads = {k: v.grad for k, v in leaf.items() if v.is_floating_point() and v.requires_grad and v.grad is not None}
+	return logits[0].detach(), nll.detach() / c['ylen'][:, 0], grads, stats
+
+
+def check_grads_against_golden(grads, golden_grads, tol, what = ''):
+	"""golden gradients are strided samples + norms (oracle/make_golden.py: compress_grad).  Returns (total rel error,
+	worst per-tensor rel error).  Tensors whose true gradient is zero (a conv bias in front of a batch-statistics
+	BatchNorm) hold rounding noise in the reference too: they are judged against the largest tensor's scale."""
+	assert set(grads) == set(golden_grads), set(grads) ^ set(golden_grads)
+	gmax = max(float(gg['sample'].double().norm()) for gg in golden_grads.values())
+	worst, tot_d, tot_n = 0.0, 0.0, 0.0
+	for k, gg in golden_grads.items():
+		g = grads[k].detach().cpu().flatten()
+		assert tuple(grads[k].shape) == gg['shape'], k
+		s = g[::gg['stride']]
+		d = float((s.double() - gg['sample'].double()).norm())
+		n = float(gg['sample'].double().norm())
+		tot_d += d * d
+		tot_n += n * n
+		e = d / max(n, 1e-3 * gmax)
+		worst = max(worst, e)
+		assert e < tol, (what, k, e)
+		assert abs(float(g.double().norm()) - gg['norm']) <= tol * max(gg['norm'], 1e-3 * gmax), (what, k)
+	total = (tot_d / tot_n)**0.5
+	assert total < tol, (what, total)
+	return total, worst
+
+
+def test_train_mode_oracle_matches_reference_golden(golden):
+	"""TRAIN mode (batch-statistics BN, autograd) of every golden family: logits, loss, all gradients, BN running stats"""
+	g = golden('train')
+	for c in g['cases']:
+		logits, loss, grads, stats = oracle_train_step(c)
+		assert rel(logits, c['logits']) < 1e-4, (c['model'], rel(logits, c['logits']))
+		assert torch.allclose(loss, c['loss'], rtol = 1e-4, atol = 1e-4), c['model']
+		# a hardtanh / relu gate that flips between two fp32 implementations moves the gradient by O(1 / sqrt(elements)):
+		# the kinked full-depth cases are bounded loosely, the shallow and the smooth-regime ones tightly (O.smooth_regime)
+		deep_kinked = not c['kwargs'].get('smooth') and c['kwargs'].get('num_blocks', 5) > 1
+		total, worst = check_grads_against_golden(grads, c['grads'], 5e-2 if deep_kinked else 1e-3, c['model'])
+		print(c['model'], c['kwargs'], 'oracle vs reference: total grad rel', total, 'worst tensor', worst)
+		for k, v in c['stats'].items():
+			assert k in stats, k
+			if k.endswith('num_batches_tracked'):
+				assert int(stats[k]) == int(v)
+			else:
+				assert torch.allclose(stats[k], v, rtol = 1e-4, atol = 1e-5), k
+
+
+def test_misc_golden_novograd_uncertainty_bpe(golden):
+	g = golden('misc')
+	for c in g['novograd']:
+		params = [p.clone() for p in c['p0']]
+		state = [{} for _ in params]
+		for st in c['steps']:
+			O.novograd_step(params, st['grads'], state, lr = c['lr'], betas = c['betas'], weight_decay = c['weight_decay'], dampening = c['dampening'])
+			for p, q in zip(params, st['params']):
+				assert torch.allclose(p, q, rtol = 1e-6, atol = 1e-7)
+	for c in g['uncertainty']:
+		lp, lens = c['log_probs'], c['lengths']
+		assert torch.allclose(O.entropy(lp, lens), c['entropy'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(O.entropy(lp, None), c['entropy_nolen'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(O.weighted_mean_entropy(lp, lens, eps_id = lp.shape[1] - 1), c['wme'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(O.weighted_mean_entropy(lp, None, eps_id = lp.shape[1] - 1), c['wme_nolen'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(O.margin(lp[:2]), c['margin'], rtol = 1e-6, atol = 1e-7)
+		with pytest.raises(TypeError):
+			O.margin(torch.cat([lp, lp])[:3])
+	c = g['bpe']
+	sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
+	logits, log_probs, olen = O.model_forward(sd, c['signal'], c['xlen'], model = c['model'])
+	assert len(logits) == 2
+	loss = 0
+	for h in range(2):
+		assert torch.equal(olen[h], c['olen'][h])
+		assert rel(logits[h], c['logits'][h]) < 1e-4 and rel(log_probs[h], c['log_probs'][h]) < 1e-4
+		C = c['num_classes'][h]
+		loss = loss + O.ctc_loss_torch(log_probs[h].permute(2, 0, 1), c['y'][:, h], olen[h], c['ylen'][:, h], C - 1) / c['ylen'][:, 0]  # models.py:323: every head / ylen[:, 0]
+	assert torch.allclose(loss, c['loss'], rtol = 1e-3, atol = 1e-3)
