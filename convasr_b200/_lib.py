@@ -35,12 +35,19 @@ class ConvEpilogue(ctypes.Structure):
 
 
 class PackItem(ctypes.Structure):
-	_fields_ = [('w', c_void_p), ('fwd', c_void_p), ('dgrad', c_void_p), ('Co', c_i32), ('Ci', c_i32), ('K', c_i32), ('ci_ld', c_i32), ('co_ld', c_i32)]
+	_fields_ = [('w', c_void_p), ('fwd', c_void_p), ('dgrad', c_void_p), ('fwd_lo', c_void_p), ('dgrad_lo', c_void_p), ('Co', c_i32), ('Ci', c_i32), ('K', c_i32), ('ci_ld', c_i32), ('co_ld', c_i32), ('mode', c_i32), ('pad', c_i32)]
+
+
+class BnBranch(ctypes.Structure):
+	_fields_ = [('y', c_void_p), ('y_lo', c_void_p), ('ss', c_void_p)]
 
 
 ACT_NONE, ACT_RELU, ACT_HARDTANH, ACT_LEAKY_RELU = 0, 1, 2, 3
 EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
 MAX_CONV_SOURCES = 18
+MAX_BN_BRANCHES = 12
+PACK_MAX_ITEMS = 32
+ABI_VERSION = 2
 
 # name -> argtypes; every function returns int except the three introspection calls
 BN_SUM_REPLICAS = 8  # CAB_BN_SUM_REPLICAS
@@ -52,22 +59,30 @@ SIGNATURES = {
 						c_void_p, c_void_p, c_void_p],
 	'cab_conv1d_fused': [ctypes.POINTER(ConvSource), c_int, ctypes.POINTER(ConvEpilogue), c_void_p],
 	'cab_conv1d_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-						c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p],
+						c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
 	'cab_bn_batch_stats': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_void_p],
 	'cab_bn_finalize': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
-	'cab_bn_act_mask_fwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_float,
+	'cab_bn_act_mask_fwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_float,
 							c_void_p, c_i64, c_void_p],
-	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
-							c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p, c_void_p],
+	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+							c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i64, c_int, c_void_p, c_void_p],
+	'cab_bn_multi_act_mask_fwd': [ctypes.POINTER(BnBranch), c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+								c_float, c_void_p, c_i64, c_void_p],
+	'cab_act_mask_bwd_dz': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+							c_float, c_void_p, c_i64, c_void_p],
 	'cab_pack_weight': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
 	'cab_pack_weights_batched': [ctypes.POINTER(PackItem), c_int, c_void_p],
-	'cab_unpack_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
-	'cab_bct_to_btc': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+	'cab_unpack_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+	'cab_bct_to_btc': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
 	'cab_optimizer_step': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-							c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p],
-	'cab_grouped_conv1d_relu': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
-								c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p],
+							c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
+	'cab_grouped_conv1d': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+								c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+	'cab_grouped_conv1d_wgrad': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+								c_void_p, c_void_p, c_void_p],
+	'cab_bn_act_mask_fwd_stats': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
+								c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p],
 	'cab_log_softmax_argmax': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 	'cab_log_softmax_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
 	'cab_ctc_loss_fwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -94,13 +109,19 @@ def load():
 	if _LIB is not None:
 		return _LIB
 	path = lib_path()
-	if not os.path.exists(path):
+	if path == _build.LIB_PATH and _build.needs_build():
+		# missing, or older than its sources: rebuild (under a file lock; concurrent ranks wait and then load the result)
 		try:
 			_build.build()
 		except Exception as e:
-			raise RuntimeError(
-				f'convasr_b200: native library {path} is missing and could not be built ({e}); there is no fallback path'
-			) from e
+			if not os.path.exists(path):
+				raise RuntimeError(
+					f'convasr_b200: native library {path} is missing and could not be built ({e}); there is no fallback path'
+				) from e
+			# no compiler on this machine (a GPU box running a snapshot): the shipped library is used as is; an ABI
+			# mismatch is caught below
+	elif not os.path.exists(path):
+		raise RuntimeError(f'convasr_b200: native library {path} is missing; there is no fallback path')
 	lib = ctypes.CDLL(path)
 	for name, argtypes in SIGNATURES.items():
 		fn = getattr(lib, name)
@@ -110,8 +131,8 @@ def load():
 		fn = getattr(lib, name)
 		fn.argtypes = []
 		fn.restype = restype
-	if lib.cab_abi_version() != 1:
-		raise RuntimeError(f'convasr_b200: ABI version mismatch ({lib.cab_abi_version()} != 1)')
+	if lib.cab_abi_version() != ABI_VERSION:
+		raise RuntimeError(f'convasr_b200: ABI version mismatch ({lib.cab_abi_version()} != {ABI_VERSION}): stale {path}? rebuild with python -m convasr_b200.build --force')
 	_LIB = lib
 	return lib
 

@@ -24,17 +24,43 @@ def _nvcc():
 	return cand if os.path.exists(cand) else 'nvcc'
 
 
+HASH_PATH = LIB_PATH + '.srchash'
+
+
+def source_hash():
+	"""content hash of everything the library is built from (mtimes do not survive a snapshot copy to a GPU box)"""
+	import hashlib
+	h = hashlib.sha256()
+	for d in [os.path.join(CSRC, s) for s in SOURCES + HEADERS]:
+		h.update(open(d, 'rb').read())
+	h.update(' '.join(NVCC_FLAGS).encode())
+	return h.hexdigest()
+
+
 def needs_build():
-	if not os.path.exists(LIB_PATH):
+	if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
 		return True
-	lib_mtime = os.path.getmtime(LIB_PATH)
-	deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-	return any(os.path.getmtime(d) > lib_mtime for d in deps)
+	return open(HASH_PATH).read().strip() != source_hash()
 
 
 def build(force = False, verbose = False):
+	"""Compile and link under an exclusive file lock: ranks of one torchrun that all find the library stale take
+	turns, the first one builds (objects and the .so go to temporary names, then os.replace), the others see a
+	fresh library when they get the lock."""
+	import fcntl
 	if not force and not needs_build():
 		return LIB_PATH
+	with open(os.path.join(PKG_DIR, '.build.lock'), 'w') as lock:
+		fcntl.flock(lock, fcntl.LOCK_EX)
+		try:
+			if not force and not needs_build():
+				return LIB_PATH
+			return _build_locked(verbose)
+		finally:
+			fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
 	objs = []
 	procs = []
 	for src in SOURCES:
@@ -54,10 +80,14 @@ def build(force = False, verbose = False):
 			sys.stderr.write(f'--- {src} ---\n{out}\n')
 	if failed:
 		raise RuntimeError('convasr_b200: nvcc compilation failed')
-	link = [_nvcc(), '-shared', '-o', LIB_PATH, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
+	tmp = LIB_PATH + f'.tmp{os.getpid()}'
+	link = [_nvcc(), '-shared', '-o', tmp, *objs, '-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
 	res = subprocess.run(link, stdout = subprocess.PIPE, stderr = subprocess.STDOUT, text = True)
 	if res.returncode != 0:
 		raise RuntimeError('convasr_b200: link failed\n' + res.stdout)
+	os.replace(tmp, LIB_PATH)
+	with open(HASH_PATH, 'w') as f:
+		f.write(source_hash())
 	return LIB_PATH
 
 

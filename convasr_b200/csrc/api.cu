@@ -24,14 +24,14 @@ void set_last_error(const char* fmt, ...) {
 // output channels; weights stay in L1.
 int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in, int ld_in, const float* wgt,
                       const float* bias, int C_out, int groups, int k, int pad_left, void* out, void* out_lo,
-                      int out_T_rows, int ld_out, cudaStream_t stream);
+                      int out_T_rows, int ld_out, int relu, cudaStream_t stream);
 constexpr int kGcFrames = 8;
 __global__ void __launch_bounds__(256)
 grouped_conv_relu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo, int T,
                          int T_rows, int C_in, int ld_in, const float* __restrict__ w,
                          const float* __restrict__ bias, int C_out, int groups, int K, int pad,
                          __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int out_T_rows,
-                         int ld_out) {
+                         int ld_out, int relu) {
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kGcFrames;
     const int cin_g = C_in / groups, cout_g = C_out / groups;
@@ -72,7 +72,7 @@ grouped_conv_relu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat1
             const int t = t0 + i;
             if (t < T) {
                 const size_t o = ((size_t)b * out_T_rows + t) * ld_out + co;
-                const float v = fmaxf(acc[i], 0.f);
+                const float v = relu ? fmaxf(acc[i], 0.f) : acc[i];
                 const __nv_bfloat16 h = __float2bfloat16_rn(v);
                 out[o] = h;
                 if (out_lo) out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -89,24 +89,24 @@ extern "C" int cab_abi_version(void) { return CAB_ABI_VERSION; }
 extern "C" const char* cab_last_error(void) { return g_err; }
 extern "C" int64_t cab_launch_count(void) { return g_launch_count.load(); }
 
-extern "C" int cab_grouped_conv1d_relu(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in,
-                                       int ld_in, const float* wgt, const float* bias, int C_out, int groups,
-                                       int k, int pad_left, void* out, void* out_lo, int out_T_rows, int ld_out,
-                                       cab_stream_t stream_) {
+extern "C" int cab_grouped_conv1d(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in,
+                                  int ld_in, const float* wgt, const float* bias, int C_out, int groups,
+                                  int k, int pad_left, void* out, void* out_lo, int out_T_rows, int ld_out, int relu,
+                                  cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(act && wgt && out, "null pointer argument");
     CAB_CHECK_ARG(groups > 0 && C_in % groups == 0 && C_out % groups == 0, "channels not divisible by groups");
     CAB_CHECK_ARG(T_rows >= T && out_T_rows >= T, "row allocation smaller than T");
     CAB_CHECK_ARG(ld_in >= C_in && ld_out >= C_out, "row pitch smaller than channel count");
     {
-        const int rc = grouped_conv_fast(act, act_lo, B, T, T_rows, C_in, ld_in, wgt, bias, C_out, groups, k, pad_left, out, out_lo, out_T_rows, ld_out, stream);
+        const int rc = grouped_conv_fast(act, act_lo, B, T, T_rows, C_in, ld_in, wgt, bias, C_out, groups, k, pad_left, out, out_lo, out_T_rows, ld_out, relu, stream);
         if (rc <= 0) return rc;  // launched (0) or failed (< 0); 1 = shape not covered by the FFMA2 kernel
     }
     dim3 grid((T + kGcFrames - 1) / kGcFrames, B);
     grouped_conv_relu_kernel<<<grid, 256, 0, stream>>>(
         static_cast<const __nv_bfloat16*>(act), static_cast<const __nv_bfloat16*>(act_lo), T, T_rows, C_in, ld_in, wgt,
         bias, C_out, groups, k, pad_left, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
-        out_T_rows, ld_out);
+        out_T_rows, ld_out, relu);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

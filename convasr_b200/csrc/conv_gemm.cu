@@ -363,17 +363,24 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                     }
 #undef CAB_EPI_CALL
                     if (p.stats != nullptr) {
-                        // BatchNorm batch statistics of what was just stored (bf16-rounded), valid rows only
+                        // BatchNorm batch statistics of what was just stored (bf16-rounded; hi + lo in the split
+                        // tier), valid rows only
                         float xs[32], xq[32];
                         const uint4* mine = reinterpret_cast<const uint4*>(st_hi + row * 64);
+                        const uint4* mine_lo = reinterpret_cast<const uint4*>(st_lo + row * 64);
                         const int sw = (row >> 1) & 3;
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
                             const uint4 w4 = mine[qd ^ sw];
                             const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+                            uint4 l4 = make_uint4(0, 0, 0, 0);
+                            if (has_lo) l4 = mine_lo[qd ^ sw];
+                            const uint32_t wl[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                                float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                                const float2 fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[j]));
+                                f.x += fl.x; f.y += fl.y;
                                 const float f0 = row_ok ? f.x : 0.f, f1 = row_ok ? f.y : 0.f;
                                 xs[qd * 8 + 2 * j] = f0; xs[qd * 8 + 2 * j + 1] = f1;
                                 xq[qd * 8 + 2 * j] = f0 * f0; xq[qd * 8 + 2 * j + 1] = f1 * f1;

@@ -45,6 +45,12 @@ struct GroupedArgs {
     __nv_bfloat16* out_lo;
     int B, T, T_rows, C_in, ld_in, C_out, ld_out, out_T_rows, groups, pad;
     int tiles_per_utt, n_items, parts, cols_max;
+    int relu;           // 1: + bias, ReLU (forward of the separable pair); 0: plain grouped conv (its input gradient)
+    const __nv_bfloat16* dy;     // wgrad: gradient w.r.t. the grouped conv's output [B, T_rows_dy, ld_dy]
+    const __nv_bfloat16* dy_lo;
+    int ld_dy, dy_T_rows;
+    float* dw;          // wgrad: fp32 [C_out][cin_g][K], zeroed by the host wrapper
+    float* db;          // wgrad: fp32 [C_out] or null
 };
 
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, bool valid) {
@@ -169,7 +175,7 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
 #pragma unroll
             for (int i = 0; i < kGcTT; ++i) {
                 if (i < n_t) {
-                    const float v = live ? fmaxf(acc[i].x + acc[i].y, 0.f) : 0.f;  // padding channels: zeros (the pointwise GEMM contracts over them)
+                    const float v = live ? (p.relu ? fmaxf(acc[i].x + acc[i].y, 0.f) : acc[i].x + acc[i].y) : 0.f;  // padding channels: zeros (the pointwise GEMM contracts over them)
                     const __nv_bfloat16 h = __float2bfloat16_rn(v);
                     o_hi[i * p.ld_out] = h;
                     if (HAS_LO && o_lo) o_lo[i * p.ld_out] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -178,6 +184,17 @@ grouped_conv_ffma2_kernel(const GroupedArgs p) {
         }
         __syncthreads();  // everybody is done with tile `buf` before the next iteration refills it
     }
+}
+
+static int gc_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 static size_t grouped_smem_bytes(int cin_g, int K, int cols_max, bool has_lo) {
@@ -208,7 +225,7 @@ static int launch_grouped(const GroupedArgs& a, int n_cb, cudaStream_t stream) {
 // returns 1 when this shape is not covered (caller runs the generic kernel), 0 on launch, < 0 on error
 int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in, int ld_in, const float* wgt,
                       const float* bias, int C_out, int groups, int k, int pad_left, void* out, void* out_lo,
-                      int out_T_rows, int ld_out, cudaStream_t stream) {
+                      int out_T_rows, int ld_out, int relu, cudaStream_t stream) {
     if (ld_in % 8 != 0 || C_in % groups != 0 || C_out % groups != 0) return 1;
     const int cin_g = C_in / groups, cout_g = C_out / groups;
     const int n_cb = (ld_out + kGcCo - 1) / kGcCo;
@@ -230,11 +247,11 @@ int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_r
     a.x = static_cast<const __nv_bfloat16*>(act); a.x_lo = static_cast<const __nv_bfloat16*>(act_lo); a.w = wgt; a.bias = bias;
     a.out = static_cast<__nv_bfloat16*>(out); a.out_lo = static_cast<__nv_bfloat16*>(out_lo);
     a.B = B; a.T = T; a.T_rows = T_rows; a.C_in = C_in; a.ld_in = ld_in; a.C_out = C_out; a.ld_out = ld_out; a.out_T_rows = out_T_rows;
-    a.groups = groups; a.pad = pad_left; a.cols_max = cols_max;
+    a.groups = groups; a.pad = pad_left; a.cols_max = cols_max; a.relu = relu;
     a.tiles_per_utt = (T + kGcTile - 1) / kGcTile;
     a.n_items = B * a.tiles_per_utt;
     // one wave: every CTA must be resident at once (2 per SM), a 297th CTA would run alone afterwards
-    int parts = (148 * ctas_per_sm) / n_cb;
+    int parts = (gc_num_sms() * ctas_per_sm) / n_cb;
     parts = parts < 1 ? 1 : parts;
     a.parts = parts < a.n_items ? parts : a.n_items;
     switch (k) {
@@ -255,4 +272,201 @@ int grouped_conv_fast(const void* act, const void* act_lo, int B, int T, int T_r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Weight / bias gradient of the grouped conv (training of the separable blocks; in the reference this is autograd's
+// grouped cudnn wgrad behind loss.backward(), train.py:770-774):
+//   dW[co, j, k] = sum_{b,t} dy[b, t, co] * x[b, t + k - pad, g(co) * cin_g + j],   db[co] = sum_{b,t} dy[b, t, co]
+// Same tiling as the forward kernel (CTA = 64 output channels x a persistent loop over (utterance, 64-frame) tiles, x tile
+// and dy tile staged with cp.async, double buffered).  thread = (output channel, input-channel pair jp, frame-strip
+// class): it keeps the K accumulators (float2: even / odd input channel) of its (co, jp) in registers for the whole
+// life of the CTA, slides a register window of x over each 16-frame strip, and adds its partial sums to dW with fp32
+// atomics once at the end (a few thousand per CTA, spread over all weights).
+// ---------------------------------------------------------------------------------------
+template <int K, bool HAS_LO>
+__global__ void __launch_bounds__(kGcThreads, 1)
+grouped_conv_wgrad_kernel(const GroupedArgs p) {
+    constexpr int kRows = kGcTile + K - 1;
+    constexpr int kWin = kGcTT + K - 1;
+    constexpr int NT = HAS_LO ? 2 : 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int tile_bytes = kRows * kGcMaxCols * 2;
+    constexpr int dy_bytes = kGcTile * kGcCo * 2;
+    constexpr int buf_bytes = NT * (tile_bytes + dy_bytes);
+    constexpr int pitch = kGcMaxCols * 2;
+    const int cin_g = p.C_in / p.groups, cout_g = p.C_out / p.groups;
+    const int n_jp = (cin_g + 1) / 2;
+    const int ways = n_jp >= 3 ? 1 : (n_jp == 2 ? 2 : 4);  // frame-strip classes per (co, jp) so that all 4 thread rows work
+    const int tid = threadIdx.x;
+    const int co_l = tid % kGcCo, q = tid / kGcCo;
+    const int jp = q % n_jp, fs = q / n_jp;
+    const bool worker = q < n_jp * ways && jp < n_jp;
+    const int cb = blockIdx.x, part = blockIdx.y;
+    const int co = cb * kGcCo + co_l;
+    const bool live = co < p.C_out && worker;
+    const int co_last = min(cb * kGcCo + kGcCo, p.C_out) - 1;
+    const int ci_first = co_last >= cb * kGcCo ? (cb * kGcCo / cout_g) * cin_g : 0;
+    const int ci_end = co_last >= cb * kGcCo ? (co_last / cout_g + 1) * cin_g + 1 : 8;
+    const int ci_lo = ci_first & ~7;
+    const int cols = ((ci_end - ci_lo + 7) & ~7);
+    const int n_vec = cols / 8;
+    const int col0 = co < p.C_out ? (co / cout_g) * cin_g - ci_lo : 0;
+    const int total_vec = kRows * n_vec;
+    constexpr int dy_vec = kGcTile * kGcCo / 8;  // 16-byte vectors of the dy tile
+
+    auto issue = [&](int item, int buf) {
+        const int b = item / p.tiles_per_utt, t0 = (item - b * p.tiles_per_utt) * kGcTile;
+        const uint32_t base = smem_u32(smem_raw) + buf * buf_bytes;
+#pragma unroll
+        for (int v = 0; v < kGcMaxVec; ++v) {
+            const int idx = tid + v * kGcThreads;
+            if (idx >= total_vec) break;
+            const int r = idx / n_vec, cvec = idx - r * n_vec;
+            const int u = t0 - p.pad + r, ch = ci_lo + cvec * 8;
+            const bool ok = u >= 0 && u < p.T && ch < p.ld_in;
+            const size_t off = ok ? ((size_t)b * p.T_rows + u) * p.ld_in + ch : 0;
+            const uint32_t dst = base + r * pitch + cvec * 16;
+            cp_async_16(dst, p.x + off, ok);
+            if (HAS_LO) cp_async_16(dst + tile_bytes, p.x_lo + off, ok);
+        }
+        const uint32_t dbase = base + NT * tile_bytes;
+#pragma unroll
+        for (int v = 0; v < dy_vec / kGcThreads; ++v) {
+            const int idx = tid + v * kGcThreads;
+            const int r = idx / (kGcCo / 8), cvec = idx - r * (kGcCo / 8);
+            const int t = t0 + r, ch = cb * kGcCo + cvec * 8;
+            const bool ok = t < p.T && ch < p.ld_dy;
+            const size_t off = ok ? ((size_t)b * p.dy_T_rows + t) * p.ld_dy + ch : 0;
+            const uint32_t dst = dbase + r * (kGcCo * 2) + cvec * 16;
+            cp_async_16(dst, p.dy + off, ok);
+            if (HAS_LO) cp_async_16(dst + dy_bytes, p.dy_lo + off, ok);
+        }
+        cp_async_commit();
+    };
+
+    float2 acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+    float bsum = 0.f;
+
+    int item = part, buf = 0;
+    if (item < p.n_items) issue(item, 0);
+    for (; item < p.n_items; item += p.parts, buf ^= 1) {
+        const bool more = item + p.parts < p.n_items;
+        if (more) issue(item + p.parts, buf ^ 1);
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        if (live) {
+            const unsigned char* xt = smem_raw + buf * buf_bytes + col0 * 2 + jp * 4;
+            const unsigned char* dt = smem_raw + buf * buf_bytes + NT * tile_bytes + co_l * 2;
+            for (int s = fs; s < kGcStrips; s += ways) {
+                float d[kGcTT];
+#pragma unroll
+                for (int i = 0; i < kGcTT; ++i) {
+                    const unsigned char* a = dt + (s * kGcTT + i) * (kGcCo * 2);
+                    d[i] = __uint_as_float((uint32_t)*reinterpret_cast<const unsigned short*>(a) << 16);
+                    if (HAS_LO) d[i] += __uint_as_float((uint32_t)*reinterpret_cast<const unsigned short*>(a + dy_bytes) << 16);
+                    if (jp == 0) bsum += d[i];
+                }
+                float2 xw[kWin];
+                const unsigned char* xr = xt + (s * kGcTT) * pitch;
+#pragma unroll
+                for (int m = 0; m < kWin; ++m) {
+                    xw[m] = load_pair<false>(xr + m * pitch);
+                    if (HAS_LO) {
+                        const float2 l = load_pair<false>(xr + tile_bytes + m * pitch);
+                        xw[m].x += l.x;
+                        xw[m].y += l.y;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+#pragma unroll
+                    for (int i = 0; i < kGcTT; ++i) acc[k] = fma2(make_float2(d[i], d[i]), xw[i + k], acc[k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        float* w0 = p.dw + ((size_t)co * cin_g + 2 * jp) * K;
+        const bool odd_ok = 2 * jp + 1 < cin_g;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            atomicAdd(w0 + k, acc[k].x);
+            if (odd_ok) atomicAdd(w0 + K + k, acc[k].y);
+        }
+        if (jp == 0 && p.db != nullptr) atomicAdd(p.db + co, bsum);
+    }
+}
+
+template <int K>
+static int launch_grouped_wgrad(const GroupedArgs& a, int n_cb, cudaStream_t stream) {
+    const bool lo = a.x_lo != nullptr;
+    const size_t smem = (size_t)2 * (lo ? 2 : 1) * ((kGcTile + K - 1) * kGcMaxCols * 2 + kGcTile * kGcCo * 2);
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[lo]) {
+        if (lo) CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_wgrad_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CAB_CHECK_CUDA(cudaFuncSetAttribute(grouped_conv_wgrad_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[lo] = smem;
+    }
+    if (lo) grouped_conv_wgrad_kernel<K, true><<<dim3(n_cb, a.parts), kGcThreads, smem, stream>>>(a);
+    else grouped_conv_wgrad_kernel<K, false><<<dim3(n_cb, a.parts), kGcThreads, smem, stream>>>(a);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 }  // namespace cab
+
+using namespace cab;
+
+extern "C" int cab_grouped_conv1d_wgrad(const void* dy, const void* dy_lo, int dy_T_rows, int ld_dy, const void* x, const void* x_lo,
+                                        int B, int T, int T_rows, int C_in, int ld_in, int C_out, int groups, int k, int pad_left,
+                                        float* dw, float* db, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(dy && x && dw, "null pointer argument");
+    CAB_CHECK_ARG((dy_lo == nullptr) == (x_lo == nullptr), "split-bf16 tier needs both dy_lo and x_lo");
+    CAB_CHECK_ARG(groups > 0 && C_in % groups == 0 && C_out % groups == 0 && ld_in % 8 == 0 && ld_dy % 8 == 0 && ld_dy >= C_out, "bad grouped conv layout");
+    CAB_CHECK_ARG(k % 2 == 1 && pad_left == k / 2, "grouped conv wgrad: odd kernel sizes with 'same' padding only (k=%d pad=%d)", k, pad_left);
+    const int cin_g = C_in / groups, cout_g = C_out / groups;
+    CAB_CHECK_ARG((cin_g + 1) / 2 <= kGcStrips, "grouped conv wgrad: at most %d input channels per group (got %d)", 2 * kGcStrips, cin_g);
+    const int n_cb = (C_out + kGcCo - 1) / kGcCo;
+    int cols_max = 8;
+    for (int cb = 0; cb < n_cb; ++cb) {
+        const int co_last = (cb * kGcCo + kGcCo < C_out ? cb * kGcCo + kGcCo : C_out) - 1;
+        const int ci_first = (cb * kGcCo / cout_g) * cin_g, ci_end = (co_last / cout_g + 1) * cin_g + 1;
+        const int cols = ((ci_end - (ci_first & ~7)) + 7) & ~7;
+        cols_max = cols > cols_max ? cols : cols_max;
+    }
+    CAB_CHECK_ARG(cols_max <= kGcMaxCols && (kGcTile + k - 1) * (cols_max / 8) <= kGcMaxVec * kGcThreads, "grouped conv wgrad: input window of %d channels per 64 outputs is not covered", cols_max);
+    GroupedArgs a{};
+    a.x = static_cast<const __nv_bfloat16*>(x); a.x_lo = static_cast<const __nv_bfloat16*>(x_lo);
+    a.dy = static_cast<const __nv_bfloat16*>(dy); a.dy_lo = static_cast<const __nv_bfloat16*>(dy_lo); a.ld_dy = ld_dy; a.dy_T_rows = dy_T_rows;
+    a.dw = dw; a.db = db;
+    a.B = B; a.T = T; a.T_rows = T_rows; a.C_in = C_in; a.ld_in = ld_in; a.C_out = C_out; a.groups = groups; a.pad = pad_left; a.cols_max = cols_max;
+    a.tiles_per_utt = (T + kGcTile - 1) / kGcTile;
+    a.n_items = B * a.tiles_per_utt;
+    int parts = gc_num_sms() / n_cb;  // one CTA per SM (register-heavy), one wave
+    parts = parts < 1 ? 1 : parts;
+    a.parts = parts < a.n_items ? parts : a.n_items;
+    CAB_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)C_out * cin_g * k, stream));
+    if (db) CAB_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C_out, stream));
+    switch (k) {
+        case 3: return launch_grouped_wgrad<3>(a, n_cb, stream);
+        case 5: return launch_grouped_wgrad<5>(a, n_cb, stream);
+        case 7: return launch_grouped_wgrad<7>(a, n_cb, stream);
+        case 9: return launch_grouped_wgrad<9>(a, n_cb, stream);
+        case 11: return launch_grouped_wgrad<11>(a, n_cb, stream);
+        case 13: return launch_grouped_wgrad<13>(a, n_cb, stream);
+        case 15: return launch_grouped_wgrad<15>(a, n_cb, stream);
+        case 17: return launch_grouped_wgrad<17>(a, n_cb, stream);
+        case 19: return launch_grouped_wgrad<19>(a, n_cb, stream);
+        case 21: return launch_grouped_wgrad<21>(a, n_cb, stream);
+        case 23: return launch_grouped_wgrad<23>(a, n_cb, stream);
+        case 25: return launch_grouped_wgrad<25>(a, n_cb, stream);
+        case 27: return launch_grouped_wgrad<27>(a, n_cb, stream);
+        default: CAB_CHECK_ARG(false, "grouped conv wgrad: kernel size %d has no instantiation (odd 3..27)", k);
+    }
+    return 0;
+}

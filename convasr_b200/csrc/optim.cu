@@ -49,7 +49,8 @@ mt_sumsq_kernel(const long long* __restrict__ grad_ptrs, const long long* __rest
 // state: [0] = step count (as float bits are avoided: int), kept in an int64 device cell
 __global__ void mt_prepare_kernel(const float* __restrict__ sumsq, int n, int mode, float max_norm, float beta2, float eps,
                                   float* __restrict__ ema, float* __restrict__ scale, long long* __restrict__ step_cell,
-                                  int* __restrict__ first_flag, float* __restrict__ total_norm_out) {
+                                  int* __restrict__ first_flag, float* __restrict__ total_norm_out,
+                                  const float* __restrict__ ext_total_norm) {
     __shared__ float s_total;
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += sumsq[i];
@@ -60,17 +61,20 @@ __global__ void mt_prepare_kernel(const float* __restrict__ sumsq, int n, int mo
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
-        s_total = sqrtf(t);
+        // ext_total_norm: the gradient norm over ALL parameter groups (clip_grad_norm_ is global, train.py:776-779)
+        s_total = ext_total_norm ? ext_total_norm[0] : sqrtf(t);
         if (total_norm_out) total_norm_out[0] = s_total;
     }
     __syncthreads();
+    if (mode == 2) return;  // norm only
     const bool first = step_cell[0] == 0;
     // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (total + 1e-6), max = 1)
     const float c = max_norm > 0.f ? fminf(max_norm / (s_total + 1e-6f), 1.f) : 1.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (mode == 1) {  // NovoGrad: EMA of the squared norm of the (clipped) gradient, optimizers.py:77-79
             const float g2 = c * c * sumsq[i];
-            const float e = first ? g2 : ema[i] * beta2 + g2 * (1.f - beta2);
+            // a tensor that joins later (its first gradient) starts its EMA like a first step does: ema == 0 marks it
+            const float e = (first || ema[i] == 0.f) ? g2 : ema[i] * beta2 + g2 * (1.f - beta2);
             ema[i] = e;
             scale[i] = c / sqrtf(e + eps);
         } else {
@@ -139,22 +143,27 @@ extern "C" int cab_optimizer_step(int mode, int n_tensors, const int64_t* param_
                                   float* ws_sumsq, float* ema, float* ws_scale, int64_t* step_cell, int32_t* ws_first,
                                   const float* lr_dev, float momentum, float beta2, float eps, float weight_decay,
                                   float dampening, int nesterov, float max_grad_norm, float* total_norm_out,
-                                  cab_stream_t stream_) {
+                                  const float* ext_total_norm, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    CAB_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (SGD) or 1 (NovoGrad)");
+    CAB_CHECK_ARG(mode >= 0 && mode <= 2, "mode must be 0 (SGD), 1 (NovoGrad) or 2 (gradient norm only)");
     CAB_CHECK_ARG(n_tensors > 0 && n_chunks > 0 && chunk_elems > 0 && chunk_elems % 4 == 0, "bad table sizes");
-    CAB_CHECK_ARG(param_ptrs && grad_ptrs && mom_ptrs && numels && chunk_tensor && chunk_off && ws_sumsq && ws_scale && step_cell && ws_first && lr_dev, "null pointer argument");
-    CAB_CHECK_ARG(mode == 0 || ema != nullptr, "NovoGrad needs the ema state");
+    CAB_CHECK_ARG(grad_ptrs && numels && chunk_tensor && chunk_off && ws_sumsq, "null pointer argument");
+    CAB_CHECK_ARG(mode == 2 ? total_norm_out != nullptr : (param_ptrs && mom_ptrs && ws_scale && step_cell && ws_first && lr_dev), "null pointer argument");
+    CAB_CHECK_ARG(mode != 1 || ema != nullptr, "NovoGrad needs the ema state");
     int launches = 1;
-    const bool need_norm = mode == 1 || max_grad_norm > 0.f || total_norm_out != nullptr;
+    const bool need_norm = mode >= 1 || (max_grad_norm > 0.f && ext_total_norm == nullptr) || total_norm_out != nullptr;
     CAB_CHECK_CUDA(cudaMemsetAsync(ws_sumsq, 0, sizeof(float) * n_tensors, stream));
     if (need_norm) {
         mt_sumsq_kernel<<<n_chunks, kOptThreads, 0, stream>>>(reinterpret_cast<const long long*>(grad_ptrs), reinterpret_cast<const long long*>(numels), chunk_tensor, reinterpret_cast<const long long*>(chunk_off), chunk_elems, ws_sumsq);
         CAB_CHECK_LAUNCH();
         ++launches;
     }
-    mt_prepare_kernel<<<1, 256, 0, stream>>>(ws_sumsq, n_tensors, mode, need_norm ? max_grad_norm : 0.f, beta2, eps, ema, ws_scale, reinterpret_cast<long long*>(step_cell), ws_first, total_norm_out);
+    mt_prepare_kernel<<<1, 256, 0, stream>>>(ws_sumsq, n_tensors, mode, (need_norm || ext_total_norm) ? max_grad_norm : 0.f, beta2, eps, ema, ws_scale, reinterpret_cast<long long*>(step_cell), ws_first, total_norm_out, ext_total_norm);
     CAB_CHECK_LAUNCH();
+    if (mode == 2) {
+        g_launch_count.fetch_add(launches, std::memory_order_relaxed);
+        return 0;
+    }
     mt_update_kernel<<<n_chunks, kOptThreads, 0, stream>>>(reinterpret_cast<const long long*>(param_ptrs), reinterpret_cast<const long long*>(grad_ptrs), reinterpret_cast<const long long*>(mom_ptrs), reinterpret_cast<const long long*>(numels), chunk_tensor, reinterpret_cast<const long long*>(chunk_off), chunk_elems, ws_scale, ws_first, lr_dev, mode, momentum, weight_decay, dampening, nesterov);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(launches + 1, std::memory_order_relaxed);

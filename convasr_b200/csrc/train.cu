@@ -136,11 +136,11 @@ colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float n, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ out /* [4][C]: scale, shift, mean, invstd */) {
+                                   float* __restrict__ out /* [4][C]: scale, shift, mean, invstd */, int sums_ld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float mean = stats[c] / n;
-    const float var = fmaxf(stats[C + c] / n - mean * mean, 0.f);
+    const float var = fmaxf(stats[sums_ld + c] / n - mean * mean, 0.f);
     const float invstd = rsqrtf(var + eps);
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     out[c] = g * invstd;
@@ -341,21 +341,50 @@ struct StreamArgs {
     const __nv_bfloat16* y;
     const __nv_bfloat16* g;    // grad w.r.t. the layer output (backward modes)
     __nv_bfloat16* out;        // forward: activations; apply: grad_y
+    // split-bf16 ("fp32 tier"): every tensor is a (hi, lo) pair, value = hi + lo
+    const __nv_bfloat16* y_lo;
+    const __nv_bfloat16* g_lo;
+    __nv_bfloat16* out_lo;
     const float* ss;           // [4][C] scale, shift, mean, invstd
     const float* xlen;
     float* partials;           // [kBnSumReplicas][2][C]
     float* sums;               // [2][C] totals (written by the apply pass)
     const long long* seed_ptr;
     unsigned long long salt;
+    // forward with the BatchNorm finalize folded in (raw_sums != null): coefficients from the conv epilogue's raw sums
+    const float* raw_sums;     // [2][sums_ld]
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    float* ss_out;             // [4][C], written by CTA 0
+    int sums_ld;
+    float n_rows, eps, momentum;
     float a, bb, drop_p, inv_n;
     int B, T, C, ld, act;
     int vectors, rows_per_chunk, n_chunks, stages, stage_bytes;
 };
 
-template <int MODE>  // 0: forward, 1: backward reduce, 2: backward apply
+__device__ __forceinline__ void add8(float (&f)[8], const uint4& lo) {
+    float l[8];
+    unpack8(lo, l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] += l[e];
+}
+// lo half of a split-bf16 store: what the bf16 rounding of `hi` lost
+__device__ __forceinline__ uint4 pack8_lo(const float (&f)[8], const uint4& hi) {
+    float h[8], r[8];
+    unpack8(hi, h);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = f[e] - h[e];
+    return pack8(r);
+}
+
+template <int MODE, bool SPLIT>  // 0: forward, 1: backward reduce, 2: backward apply
 __global__ void __launch_bounds__(kStreamMaxThreads)
 bn_stream_kernel(const StreamArgs p) {
-    constexpr int NIN = MODE == 0 ? 1 : 2;
+    constexpr int NT = MODE == 0 ? 1 : 2;          // tensors read (y [, g])
+    constexpr int NIN = NT * (SPLIT ? 2 : 1);      // smem planes per stage: y, g, y_lo, g_lo
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)p.stages * NIN * p.stage_bytes);
     const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -373,7 +402,11 @@ bn_stream_kernel(const StreamArgs p) {
         unsigned char* dst = smem_raw + (size_t)s * NIN * p.stage_bytes;
         mbar_expect_tx(&full[s], bytes * NIN);
         bulk_load_1d(dst, p.y + (size_t)row0 * ld, bytes, &full[s]);
-        if (NIN == 2) bulk_load_1d(dst + p.stage_bytes, p.g + (size_t)row0 * ld, bytes, &full[s]);
+        if (NT == 2) bulk_load_1d(dst + p.stage_bytes, p.g + (size_t)row0 * ld, bytes, &full[s]);
+        if (SPLIT) {
+            bulk_load_1d(dst + (size_t)NT * p.stage_bytes, p.y_lo + (size_t)row0 * ld, bytes, &full[s]);
+            if (NT == 2) bulk_load_1d(dst + (size_t)(NT + 1) * p.stage_bytes, p.g_lo + (size_t)row0 * ld, bytes, &full[s]);
+        }
     };
     if (tid == 0)
         for (int s = 0; s < p.stages; ++s)
@@ -385,8 +418,30 @@ bn_stream_kernel(const StreamArgs p) {
     for (int e = 0; e < 8; ++e) {
         const int c = c0 + e;
         const bool ok = c < C;
-        sc[e] = ok ? p.ss[c] : 0.f;
-        sh[e] = ok ? p.ss[C + c] : 0.f;
+        if (MODE == 0 && p.raw_sums != nullptr) {
+            // same arithmetic as bn_finalize_kernel
+            sc[e] = 0.f; sh[e] = 0.f;
+            if (ok) {
+                const float n = p.n_rows;
+                const float mean = p.raw_sums[c] / n;
+                const float var = fmaxf(p.raw_sums[p.sums_ld + c] / n - mean * mean, 0.f);
+                const float invstd = rsqrtf(var + p.eps);
+                const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+                sc[e] = g * invstd;
+                sh[e] = b - mean * g * invstd;
+                if (blockIdx.x == 0 && lane == 0) {
+                    p.ss_out[c] = sc[e];
+                    p.ss_out[C + c] = sh[e];
+                    p.ss_out[2 * C + c] = mean;
+                    p.ss_out[3 * C + c] = invstd;
+                    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+                    if (p.running_var) p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (n / fmaxf(n - 1.f, 1.f));
+                }
+            }
+        } else {
+            sc[e] = ok ? p.ss[c] : 0.f;
+            sh[e] = ok ? p.ss[C + c] : 0.f;
+        }
         acc_s[e] = 0.f; acc_q[e] = 0.f; k0[e] = 0.f; k1[e] = 0.f;
         if (MODE == 2) {
             float m1 = 0.f, m2 = 0.f;
@@ -433,6 +488,7 @@ bn_stream_kernel(const StreamArgs p) {
             if (MODE == 1 && !keep) continue;
             float yf[8], o[8];
             unpack8(*reinterpret_cast<const uint4*>(src + unit * 16), yf);
+            if (SPLIT) add8(yf, *reinterpret_cast<const uint4*>(src + (size_t)NT * p.stage_bytes + unit * 16));
             if (MODE == 0) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = (keep && c0 + e < C) ? act_fwd(fmaf(yf[e], sc[e], sh[e]), p.act, p.a, p.bb) : 0.f;
@@ -443,6 +499,7 @@ bn_stream_kernel(const StreamArgs p) {
             } else {
                 float gf[8];
                 unpack8(*reinterpret_cast<const uint4*>(src + p.stage_bytes + unit * 16), gf);
+                if (SPLIT) add8(gf, *reinterpret_cast<const uint4*>(src + (size_t)(NT + 1) * p.stage_bytes + unit * 16));
                 if (dropping) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) gf[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, p.drop_p) ? gf[e] * inv_keep : 0.f;
@@ -459,7 +516,11 @@ bn_stream_kernel(const StreamArgs p) {
                     }
                 }
             }
-            if (MODE != 1) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.out) + ((size_t)row0 * ld * 2) + unit * 16) = pack8(o);
+            if (MODE != 1) {
+                const uint4 hi = pack8(o);
+                *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.out) + ((size_t)row0 * ld * 2) + unit * 16) = hi;
+                if (SPLIT) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.out_lo) + ((size_t)row0 * ld * 2) + unit * 16) = pack8_lo(o, hi);
+            }
         }
         __syncthreads();  // everybody is done reading stage s
         if (tid == 0 && chunk + p.stages * stride < p.n_chunks) issue(chunk + p.stages * stride, s);
@@ -513,15 +574,27 @@ static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& thr
     a.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
     smem = (size_t)a.stages * n_inputs * a.stage_bytes + 8 * a.stages;
     if (smem < (size_t)threads * 64) smem = (size_t)threads * 64;  // the reduction scratch of the reduce pass
+    if (smem > 220 * 1024) return false;
     grid = 0;  // sized by stream_launch from the occupancy of the instantiation
     return true;
 }
 
-template <int MODE>
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int MODE, bool SPLIT>
 static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, size_t smem, cudaStream_t stream) {
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
@@ -531,14 +604,14 @@ static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, siz
     for (int i = 0; i < n_cache; ++i)
         if (cache_threads[i] == threads && cache_smem[i] == (int)smem) per_sm = cache_per_sm[i];
     if (per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_stream_kernel<MODE>, threads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_stream_kernel<MODE, SPLIT>, threads, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (n_cache < 8) { cache_threads[n_cache] = threads; cache_smem[n_cache] = (int)smem; cache_per_sm[n_cache] = per_sm; ++n_cache; }
     }
     (void)grid;
-    const int g = a.n_chunks < 148 * per_sm ? a.n_chunks : 148 * per_sm;
-    bn_stream_kernel<MODE><<<g, threads, smem, stream>>>(a);
+    const int g = a.n_chunks < num_sms() * per_sm ? a.n_chunks : num_sms() * per_sm;
+    bn_stream_kernel<MODE, SPLIT><<<g, threads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -572,24 +645,39 @@ pack_weight_kernel(const float* __restrict__ w, int Co, int Ci, int K, __nv_bflo
 }
 // All layers in ONE launch: the per-layer grids above are 64-900 blocks of a 17-27 us kernel each (launch /
 // ramp-up bound: 18 launches = 0.5 ms of a 23 ms step for 0.5 GB of traffic).  Tile = 16 co x 32 ci x K.
+// mode 1 = stride-2 conv as a stride-1 conv over frame pairs (engine.pack_taps_stride2): tap kk of the original
+// kernel lands at pair tap dp = floor((kk - pad) / 2) - dp_min, channel block q = (kk - pad) - 2 dp of a
+// [taps2, Co, 2 * ci_alloc] operand (ci_ld = 2 * ci_alloc; unfilled slots stay as the caller zeroed them).
 constexpr int kPackMaxItems = 32;
 struct PackBatch {
     const float* w[kPackMaxItems];
     __nv_bfloat16* fwd[kPackMaxItems];
     __nv_bfloat16* dgr[kPackMaxItems];
+    __nv_bfloat16* fwd_lo[kPackMaxItems];
+    __nv_bfloat16* dgr_lo[kPackMaxItems];
     int Co[kPackMaxItems], Ci[kPackMaxItems], K[kPackMaxItems], ci_ld[kPackMaxItems], co_ld[kPackMaxItems];
+    int mode[kPackMaxItems], pad[kPackMaxItems];
     int tile_start[kPackMaxItems + 1];
     int n;
 };
+__device__ __forceinline__ int floordiv2(int j) { return j >= 0 ? j / 2 : -((1 - j) / 2); }
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t idx, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[idx] = h;
+    if (lo) lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const PackBatch pb) {
     extern __shared__ float tile[];  // [16 co][32 ci * K + 1]
     int item = 0;
     while (item + 1 < pb.n && (int)blockIdx.x >= pb.tile_start[item + 1]) ++item;
     const int Co = pb.Co[item], Ci = pb.Ci[item], K = pb.K[item], ci_ld = pb.ci_ld[item], co_ld = pb.co_ld[item];
+    const int mode = pb.mode[item], pad = pb.pad[item];
     const float* __restrict__ w = pb.w[item];
     __nv_bfloat16* __restrict__ fwd = pb.fwd[item];
     __nv_bfloat16* __restrict__ dgr = pb.dgr[item];
+    __nv_bfloat16* __restrict__ fwd_lo = pb.fwd_lo[item];
+    __nv_bfloat16* __restrict__ dgr_lo = pb.dgr_lo[item];
     const int local = blockIdx.x - pb.tile_start[item];
     const int n_ci_tiles = (Ci + 31) / 32;
     const int co0 = (local / n_ci_tiles) * 16, ci0 = (local % n_ci_tiles) * 32;
@@ -601,24 +689,42 @@ pack_weights_batched_kernel(const PackBatch pb) {
         for (int i = threadIdx.x; i < ci_n * K; i += 32) tile[co * pitch + i] = src[i];
     }
     __syncthreads();
+    const int dp_min = floordiv2(-pad);
     for (int i = tid; i < 16 * 32 * K; i += 256) {
         const int k = i / 512, r = i - k * 512;
         int ci = r % 32, co = r / 32;  // forward operand: ci fastest
-        if (fwd && ci < ci_n && co < co_n) fwd[((size_t)k * Co + co0 + co) * ci_ld + ci0 + ci] = __float2bfloat16_rn(tile[co * pitch + ci * K + k]);
+        if (fwd && ci < ci_n && co < co_n) {
+            const float v = tile[co * pitch + ci * K + k];
+            if (mode == 0) {
+                store_split(fwd, fwd_lo, ((size_t)k * Co + co0 + co) * ci_ld + ci0 + ci, v);
+            } else {
+                const int j = k - pad, dp = floordiv2(j), q = j - 2 * dp;
+                store_split(fwd, fwd_lo, ((size_t)(dp - dp_min) * Co + co0 + co) * ci_ld + q * (ci_ld / 2) + ci0 + ci, v);
+            }
+        }
         co = r % 16; ci = r / 16;      // dgrad operand: co fastest, taps flipped
-        if (dgr && ci < ci_n && co < co_n) dgr[((size_t)(K - 1 - k) * Ci + ci0 + ci) * co_ld + co0 + co] = __float2bfloat16_rn(tile[co * pitch + ci * K + k]);
+        if (dgr && ci < ci_n && co < co_n) store_split(dgr, dgr_lo, ((size_t)(K - 1 - k) * Ci + ci0 + ci) * co_ld + co0 + co, tile[co * pitch + ci * K + k]);
     }
 }
 
 // packed gradient fp32 [K, M, ld] -> fp32 [Co, Ci, K]; transposed = packed is [K, Ci, Co]
+// transposed = 2: packed is the stride-2 pair layout [taps2, Co, ld] of pack mode 1 (`pair_pad` = the conv's padding,
+// channel block q starts at q * (pair_ci_alloc))
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int K, int Co, int Ci, int ld, int transposed,
-                                    float* __restrict__ grad, int accumulate) {
+                                    float* __restrict__ grad, int accumulate, int pair_pad, int pair_ci_alloc) {
     const size_t n = (size_t)Co * Ci * K;
+    const int dp_min = floordiv2(-pair_pad);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
         const int ci = (int)((i / K) % Ci);
         const int co = (int)(i / ((size_t)K * Ci));
-        const float v = transposed ? packed[((size_t)k * Ci + ci) * ld + co] : packed[((size_t)k * Co + co) * ld + ci];
+        float v;
+        if (transposed == 2) {
+            const int j = k - pair_pad, dp = floordiv2(j), q = j - 2 * dp;
+            v = packed[((size_t)(dp - dp_min) * Co + co) * ld + q * pair_ci_alloc + ci];
+        } else {
+            v = transposed ? packed[((size_t)k * Ci + ci) * ld + co] : packed[((size_t)k * Co + co) * ld + ci];
+        }
         grad[i] = accumulate ? grad[i] + v : v;
     }
 }
@@ -626,7 +732,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int K, int
 // fp32 [B, C, T] -> bf16 channels-last [B, T, ld] (zero padded channels) + per-class sums over (b, t)
 __global__ void __launch_bounds__(256)
 bct_to_btc_kernel(const float* __restrict__ x, int B, int C, int T, int ld, __nv_bfloat16* __restrict__ out,
-                  float* __restrict__ csum) {
+                  __nv_bfloat16* __restrict__ out_lo, float* __restrict__ csum) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -643,7 +749,117 @@ bct_to_btc_kernel(const float* __restrict__ x, int B, int C, int T, int ld, __nv
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int t = t0 + i, c = c0 + tx;
-        if (t < T && c < ld) out[((size_t)b * T + t) * ld + c] = __float2bfloat16_rn(tile[tx][i]);
+        if (t < T && c < ld) store_split(out, out_lo, ((size_t)b * T + t) * ld + c, tile[tx][i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Residual topologies (models.py:129-133: on the last repeat of a block every residual source goes through its own
+// 1x1 conv + BatchNorm and is ADDED before the activation; 'flat' residuals are added as they are):
+//   forward : out = mask(dropout(act(sum_i (scale_i * y_i + shift_i))))       bn_multi_fwd_kernel
+//   backward: dz = g * act'(.) * mask * dropout, gate taken from `out`         act_bwd_dz_kernel
+//             then every BatchNorm branch is the plain single-input backward on (y_i, dz) with act = none
+// Row walkers (a thread owns one 16-byte channel vector and walks rows): these run on the last repeat of a block only.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxBranches = CAB_MAX_BN_BRANCHES;
+struct MultiArgs {
+    const __nv_bfloat16* y[kMaxBranches];
+    const __nv_bfloat16* y_lo[kMaxBranches];
+    const float* ss[kMaxBranches];  // [4][C] or null (identity branch)
+    int n;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+bn_multi_fwd_kernel(const MultiArgs m, int B, int T, int C, int ld, int act, float a, float bb, const float* __restrict__ xlen,
+                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, float drop_p,
+                    const long long* __restrict__ seed_ptr, unsigned long long salt, int kRowsPerBlock) {
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    if (c0 >= ld) return;
+    const int R = B * T;
+    const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+    const unsigned long long seed = drop_p > 0.f ? (unsigned long long)seed_ptr[0] + salt * 0xD1B54A32D192ED03ULL : 0ull;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+        const int b = r / T, t = r - b * T;
+        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
+        float z[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) z[e] = 0.f;
+        if (keep) {
+            for (int i = 0; i < m.n; ++i) {
+                float f[8];
+                unpack8(*reinterpret_cast<const uint4*>(m.y[i] + (size_t)r * ld + c0), f);
+                if (SPLIT) add8(f, *reinterpret_cast<const uint4*>(m.y_lo[i] + (size_t)r * ld + c0));
+                const float* ss = m.ss[i];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c0 + e;
+                    if (c < C) z[e] += ss ? fmaf(f[e], __ldg(ss + c), __ldg(ss + C + c)) : f[e];
+                }
+            }
+        }
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (keep && c0 + e < C) ? act_fwd(z[e], act, a, bb) : 0.f;
+        if (drop_p > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = dropout_keep(seed, (unsigned long long)r * ld + c0 + e, drop_p) ? o[e] * inv_keep : 0.f;
+        }
+        const uint4 hi = pack8(o);
+        *reinterpret_cast<uint4*>(out + (size_t)r * ld + c0) = hi;
+        if (SPLIT) *reinterpret_cast<uint4*>(out_lo + (size_t)r * ld + c0) = pack8_lo(o, hi);
+    }
+}
+
+// dz = g * act'(z) * mask * dropout with the gate read off the stored output: relu / leaky z > 0 <=> out > 0;
+// hardtanh a < z < b <=> a < out * (1 - p) < b (a kept element is act(z) / (1 - p)); dropped or masked elements get 0
+template <bool SPLIT>
+__global__ void __launch_bounds__(256)
+act_bwd_dz_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ out_lo,
+                  const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ g_lo, int B, int T, int C, int ld,
+                  int act, float a, float bb, const float* __restrict__ xlen, __nv_bfloat16* __restrict__ dz,
+                  __nv_bfloat16* __restrict__ dz_lo, float drop_p, const long long* __restrict__ seed_ptr,
+                  unsigned long long salt, int kRowsPerBlock) {
+    const int cv = blockIdx.x * 32 + threadIdx.x;
+    const int c0 = cv * 8;
+    if (c0 >= ld) return;
+    const int R = B * T;
+    const int r0 = blockIdx.y * kRowsPerBlock, r1 = min(R, r0 + kRowsPerBlock);
+    const unsigned long long seed = drop_p > 0.f ? (unsigned long long)seed_ptr[0] + salt * 0xD1B54A32D192ED03ULL : 0ull;
+    const float inv_keep = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, keep_p = 1.f - drop_p;
+    for (int r = r0 + threadIdx.y; r < r1; r += kRowLanes) {
+        const int b = r / T, t = r - b * T;
+        const bool keep = xlen == nullptr || t < frac_len(__ldg(xlen + b), T);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = 0.f;
+        if (keep) {
+            float of[8], gf[8];
+            unpack8(*reinterpret_cast<const uint4*>(out + (size_t)r * ld + c0), of);
+            unpack8(*reinterpret_cast<const uint4*>(g + (size_t)r * ld + c0), gf);
+            if (SPLIT) {
+                add8(of, *reinterpret_cast<const uint4*>(out_lo + (size_t)r * ld + c0));
+                add8(gf, *reinterpret_cast<const uint4*>(g_lo + (size_t)r * ld + c0));
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (c0 + e >= C) continue;
+                float gate;
+                const float v = of[e] * keep_p;
+                if (act == CAB_ACT_RELU) gate = v > 0.f ? 1.f : 0.f;
+                else if (act == CAB_ACT_HARDTANH) gate = (v > a && v < bb) ? 1.f : 0.f;
+                else if (act == CAB_ACT_LEAKY_RELU) gate = v > 0.f ? 1.f : a;
+                else gate = 1.f;
+                float d = gf[e] * gate;
+                if (drop_p > 0.f) d = dropout_keep(seed, (unsigned long long)r * ld + c0 + e, drop_p) ? d * inv_keep : 0.f;
+                o[e] = d;
+            }
+        }
+        const uint4 hi = pack8(o);
+        *reinterpret_cast<uint4*>(dz + (size_t)r * ld + c0) = hi;
+        if (SPLIT) *reinterpret_cast<uint4*>(dz_lo + (size_t)r * ld + c0) = pack8_lo(o, hi);
     }
 }
 
@@ -651,7 +867,7 @@ bct_to_btc_kernel(const float* __restrict__ x, int B, int C, int T, int ld, __nv
 
 using namespace cab;
 
-#define GRID_1D(n, per) (int)(((n) / (per) + 255) / 256 > 148 * 8 ? 148 * 8 : (((n) / (per) + 255) / 256 < 1 ? 1 : ((n) / (per) + 255) / 256))
+#define GRID_1D(n, per) (int)(((n) / (per) + 255) / 256 > (size_t)num_sms() * 8 ? (size_t)num_sms() * 8 : (((n) / (per) + 255) / 256 < 1 ? 1 : ((n) / (per) + 255) / 256))
 
 extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta, float eps,
                                   float momentum, float* running_mean, float* running_var, float* ws_sums /*[2][C]*/,
@@ -664,7 +880,7 @@ extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, co
     dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
     colstats_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), R, C, ld, ws_sums, rpb);
     CAB_CHECK_LAUNCH();
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_sums, C, (float)R, gamma, beta, eps, momentum, running_mean, running_var, out_ss);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws_sums, C, (float)R, gamma, beta, eps, momentum, running_mean, running_var, out_ss, C);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return 0;
@@ -674,30 +890,35 @@ extern "C" int cab_bn_finalize(const float* sums, int n_rows, int C, const float
                                float momentum, float* running_mean, float* running_var, float* out_ss, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(sums && out_ss && n_rows > 0 && C > 0, "bad arguments");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, (float)n_rows, gamma, beta, eps, momentum, running_mean, running_var, out_ss);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(sums, C, (float)n_rows, gamma, beta, eps, momentum, running_mean, running_var, out_ss, C);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
-extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
-                                   const float* xlen_frac, void* out, float dropout_p, const int64_t* seed, int64_t salt,
-                                   cab_stream_t stream_) {
+extern "C" int cab_bn_act_mask_fwd(const void* y, const void* y_lo, const float* ss, int B, int T, int C, int ld, int act,
+                                   float act_a, float act_b, const float* xlen_frac, void* out, void* out_lo, float dropout_p,
+                                   const int64_t* seed, int64_t salt, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && ss && out, "null pointer argument");
+    CAB_CHECK_ARG((y_lo == nullptr) == (out_lo == nullptr), "split-bf16 tier needs both y_lo and out_lo");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
     CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    const bool split = y_lo != nullptr;
     StreamArgs sa{};
     int threads, grid_s;
     size_t smem;
-    if (stream_geometry(B * T, ld, 1, sa, threads, grid_s, smem)) {
+    if (stream_geometry(B * T, ld, split ? 2 : 1, sa, threads, grid_s, smem)) {
         sa.y = static_cast<const __nv_bfloat16*>(y); sa.out = static_cast<__nv_bfloat16*>(out); sa.ss = ss; sa.xlen = xlen_frac;
+        sa.y_lo = static_cast<const __nv_bfloat16*>(y_lo); sa.out_lo = static_cast<__nv_bfloat16*>(out_lo);
         sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
         sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
-        CAB_CHECK_CUDA(stream_launch<0>(sa, threads, grid_s, smem, stream));
+        if (split) CAB_CHECK_CUDA((stream_launch<0, true>(sa, threads, grid_s, smem, stream)));
+        else CAB_CHECK_CUDA((stream_launch<0, false>(sa, threads, grid_s, smem, stream)));
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
         return 0;
     }
+    CAB_CHECK_ARG(!split, "split-bf16 BatchNorm forward: row pitch ld=%d not covered by the streamed kernel", ld);
     const int rpb = rows_per_block_for(B * T, ld);
     dim3 grid((ld / 8 + 31) / 32, (B * T + rpb - 1) / rpb), block(32, kRowLanes);
     bn_act_mask_fwd_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
@@ -706,39 +927,125 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T,
     return 0;
 }
 
-extern "C" int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld, int act,
-                                   float act_a, float act_b, const float* xlen_frac, float* sums /*[2][C]: dbeta, dgamma*/,
-                                   void* grad_y, float dropout_p, const int64_t* seed, int64_t salt, float* ws_partials,
-                                   cab_stream_t stream_) {
+extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const float* raw_sums, int sums_ld, int n_rows,
+                                         const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                                         float* running_var, float* out_ss, int B, int T, int C, int ld, int act, float act_a,
+                                         float act_b, const float* xlen_frac, void* out, void* out_lo, float dropout_p,
+                                         const int64_t* seed, int64_t salt, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(y && raw_sums && out_ss && out && n_rows > 0 && sums_ld >= C, "bad arguments");
+    CAB_CHECK_ARG((y_lo == nullptr) == (out_lo == nullptr), "split-bf16 tier needs both y_lo and out_lo");
+    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
+    CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    const bool split = y_lo != nullptr;
+    StreamArgs sa{};
+    int threads, grid_s;
+    size_t smem;
+    if (!stream_geometry(B * T, ld, split ? 2 : 1, sa, threads, grid_s, smem)) {
+        // row pitch not covered by the streamed kernel: finalize, then the row walker
+        bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(raw_sums, C, (float)n_rows, gamma, beta, eps, momentum, running_mean, running_var, out_ss, sums_ld);
+        CAB_CHECK_LAUNCH();
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return cab_bn_act_mask_fwd(y, y_lo, out_ss, B, T, C, ld, act, act_a, act_b, xlen_frac, out, out_lo, dropout_p, seed, salt, stream_);
+    }
+    sa.y = static_cast<const __nv_bfloat16*>(y); sa.out = static_cast<__nv_bfloat16*>(out); sa.ss = nullptr; sa.xlen = xlen_frac;
+    sa.y_lo = static_cast<const __nv_bfloat16*>(y_lo); sa.out_lo = static_cast<__nv_bfloat16*>(out_lo);
+    sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
+    sa.raw_sums = raw_sums; sa.sums_ld = sums_ld; sa.gamma = gamma; sa.beta = beta; sa.running_mean = running_mean; sa.running_var = running_var;
+    sa.ss_out = out_ss; sa.n_rows = (float)n_rows; sa.eps = eps; sa.momentum = momentum;
+    sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+    if (split) CAB_CHECK_CUDA((stream_launch<0, true>(sa, threads, grid_s, smem, stream)));
+    else CAB_CHECK_CUDA((stream_launch<0, false>(sa, threads, grid_s, smem, stream)));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
+                                   int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
+                                   float* sums /*[2][C]: dbeta, dgamma*/, void* grad_y, void* grad_y_lo, float dropout_p,
+                                   const int64_t* seed, int64_t salt, int frozen, float* ws_partials, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
     CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    const bool split = y_lo != nullptr;
+    CAB_CHECK_ARG(split == (grad_out_lo != nullptr) && split == (grad_y_lo != nullptr), "split-bf16 tier needs y_lo, grad_out_lo and grad_y_lo together");
     {
         StreamArgs sa{};
         int threads, grid_s;
         size_t smem;
-        if (ws_partials != nullptr && stream_geometry(B * T, ld, 2, sa, threads, grid_s, smem)) {
+        if (ws_partials != nullptr && stream_geometry(B * T, ld, split ? 4 : 2, sa, threads, grid_s, smem)) {
             sa.y = static_cast<const __nv_bfloat16*>(y); sa.g = static_cast<const __nv_bfloat16*>(grad_out);
-            sa.out = static_cast<__nv_bfloat16*>(grad_y); sa.ss = ss; sa.xlen = xlen_frac; sa.partials = ws_partials; sa.sums = sums;
+            sa.y_lo = static_cast<const __nv_bfloat16*>(y_lo); sa.g_lo = static_cast<const __nv_bfloat16*>(grad_out_lo);
+            sa.out = static_cast<__nv_bfloat16*>(grad_y); sa.out_lo = static_cast<__nv_bfloat16*>(grad_y_lo);
+            sa.ss = ss; sa.xlen = xlen_frac; sa.partials = ws_partials; sa.sums = sums;
             sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
-            sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.inv_n = 1.f / (float)(B * T);
+            sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.inv_n = frozen ? 0.f : 1.f / (float)(B * T);  // frozen: grad_y = scale * dz
             sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
             CAB_CHECK_CUDA(cudaMemsetAsync(ws_partials, 0, sizeof(float) * kBnSumReplicas * 2 * C, stream));
-            CAB_CHECK_CUDA(stream_launch<1>(sa, threads, grid_s, smem, stream));
-            CAB_CHECK_CUDA(stream_launch<2>(sa, threads, grid_s, smem, stream));
+            if (split) {
+                CAB_CHECK_CUDA((stream_launch<1, true>(sa, threads, grid_s, smem, stream)));
+                CAB_CHECK_CUDA((stream_launch<2, true>(sa, threads, grid_s, smem, stream)));
+            } else {
+                CAB_CHECK_CUDA((stream_launch<1, false>(sa, threads, grid_s, smem, stream)));
+                CAB_CHECK_CUDA((stream_launch<2, false>(sa, threads, grid_s, smem, stream)));
+            }
             g_launch_count.fetch_add(2, std::memory_order_relaxed);
             return 0;
         }
     }
+    CAB_CHECK_ARG(!split, "split-bf16 BatchNorm backward needs ws_partials and a row pitch the streamed kernel covers (ld=%d)", ld);
     CAB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
     const int R = B * T, rpb = rows_per_block_for(R, ld);
     dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
     bn_act_bwd_reduce_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
     CAB_CHECK_LAUNCH();
-    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
+    bn_act_bwd_apply_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const __nv_bfloat16*>(grad_out), ss, sums, frozen ? 0.f : 1.f / (float)R, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(grad_y), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_bn_multi_act_mask_fwd(const cab_bn_branch_t* branches, int n_branches, int B, int T, int C, int ld, int act,
+                                         float act_a, float act_b, const float* xlen_frac, void* out, void* out_lo,
+                                         float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(branches && out && n_branches >= 1 && n_branches <= kMaxBranches, "n_branches=%d out of [1,%d]", n_branches, kMaxBranches);
+    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
+    CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    const bool split = out_lo != nullptr;
+    MultiArgs m{};
+    m.n = n_branches;
+    for (int i = 0; i < n_branches; ++i) {
+        CAB_CHECK_ARG(branches[i].y != nullptr && (!split || branches[i].y_lo != nullptr), "branch %d: null pointer", i);
+        m.y[i] = static_cast<const __nv_bfloat16*>(branches[i].y);
+        m.y_lo[i] = static_cast<const __nv_bfloat16*>(branches[i].y_lo);
+        m.ss[i] = branches[i].ss;
+    }
+    const int R = B * T, rpb = rows_per_block_for(R, ld);
+    dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
+    if (split) bn_multi_fwd_kernel<true><<<grid, block, 0, stream>>>(m, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
+    else bn_multi_fwd_kernel<false><<<grid, block, 0, stream>>>(m, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(out), nullptr, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_act_mask_bwd_dz(const void* out, const void* out_lo, const void* grad_out, const void* grad_out_lo, int B, int T,
+                                   int C, int ld, int act, float act_a, float act_b, const float* xlen_frac, void* dz, void* dz_lo,
+                                   float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(out && grad_out && dz, "null pointer argument");
+    CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
+    CAB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && (dropout_p == 0.f || seed != nullptr), "bad dropout arguments");
+    const bool split = dz_lo != nullptr;
+    CAB_CHECK_ARG(!split || (out_lo && grad_out_lo), "split-bf16 tier needs out_lo and grad_out_lo");
+    const int R = B * T, rpb = rows_per_block_for(R, ld);
+    dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
+    if (split) act_bwd_dz_kernel<true><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(out_lo), static_cast<const __nv_bfloat16*>(grad_out), static_cast<const __nv_bfloat16*>(grad_out_lo), B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(dz_lo), dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
+    else act_bwd_dz_kernel<false><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), nullptr, static_cast<const __nv_bfloat16*>(grad_out), nullptr, B, T, C, ld, act, act_a, act_b, xlen_frac, static_cast<__nv_bfloat16*>(dz), nullptr, dropout_p, reinterpret_cast<const long long*>(seed), (unsigned long long)salt, rpb);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -769,8 +1076,12 @@ extern "C" int cab_pack_weights_batched(const cab_pack_item_t* items, int n, cab
         const cab_pack_item_t& it = items[i];
         CAB_CHECK_ARG(it.w && (it.fwd || it.dgrad) && it.Co > 0 && it.Ci > 0 && it.K > 0, "item %d: bad arguments", i);
         CAB_CHECK_ARG((!it.fwd || it.ci_ld >= it.Ci) && (!it.dgrad || it.co_ld >= it.Co), "item %d: bad pitch", i);
+        CAB_CHECK_ARG((!it.fwd_lo || it.fwd) && (!it.dgrad_lo || it.dgrad), "item %d: lo output without its hi output", i);
         pb.w[i] = it.w; pb.fwd[i] = static_cast<__nv_bfloat16*>(it.fwd); pb.dgr[i] = static_cast<__nv_bfloat16*>(it.dgrad);
+        pb.fwd_lo[i] = static_cast<__nv_bfloat16*>(it.fwd_lo); pb.dgr_lo[i] = static_cast<__nv_bfloat16*>(it.dgrad_lo);
         pb.Co[i] = it.Co; pb.Ci[i] = it.Ci; pb.K[i] = it.K; pb.ci_ld[i] = it.ci_ld; pb.co_ld[i] = it.co_ld;
+        pb.mode[i] = it.mode; pb.pad[i] = it.pad;
+        CAB_CHECK_ARG(it.mode == 0 || (it.mode == 1 && it.dgrad == nullptr && it.ci_ld % 2 == 0 && it.ci_ld / 2 >= it.Ci), "item %d: bad stride-2 pair packing arguments", i);
         pb.tile_start[i] = tiles;
         tiles += ((it.Co + 15) / 16) * ((it.Ci + 31) / 32);
         max_k = it.K > max_k ? it.K : max_k;
@@ -790,23 +1101,25 @@ extern "C" int cab_pack_weights_batched(const cab_pack_item_t* items, int n, cab
     return 0;
 }
 
-extern "C" int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad, int accumulate, cab_stream_t stream_) {
+extern "C" int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad, int accumulate,
+                                int pair_pad, int pair_ci_alloc, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(packed && grad, "null pointer argument");
+    CAB_CHECK_ARG(transposed >= 0 && transposed <= 2, "transposed=%d", transposed);
     const size_t n = (size_t)Co * Ci * K;
-    unpack_wgrad_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(packed, K, Co, Ci, ld, transposed, grad, accumulate);
+    unpack_wgrad_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(packed, K, Co, Ci, ld, transposed, grad, accumulate, pair_pad, pair_ci_alloc);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
-extern "C" int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, float* class_sums, cab_stream_t stream_) {
+extern "C" int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, void* out_lo, float* class_sums, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(x && out, "null pointer argument");
     CAB_CHECK_ARG(ld >= C, "bad pitch");
     if (class_sums) CAB_CHECK_CUDA(cudaMemsetAsync(class_sums, 0, sizeof(float) * C, stream));
     dim3 grid((T + 31) / 32, (ld + 31) / 32, B);
-    bct_to_btc_kernel<<<grid, 256, 0, stream>>>(x, B, C, T, ld, static_cast<__nv_bfloat16*>(out), class_sums);
+    bct_to_btc_kernel<<<grid, 256, 0, stream>>>(x, B, C, T, ld, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), class_sums);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

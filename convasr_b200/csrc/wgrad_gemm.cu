@@ -272,7 +272,7 @@ using namespace cab;
 extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total, const void* bx, int b_T,
                                 int b_T_rows, int b_ld, int N_total, int B, int taps, int dilation, int pad_left,
                                 float* out, int out_ld, int n_splits, const float* skip_frac, int skip_T, int skip_margin,
-                                cab_stream_t stream_) {
+                                int accumulate_into, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(a && bx && out, "null pointer argument");
     CAB_CHECK_ARG(B > 0 && a_T > 0 && b_T > 0 && taps > 0 && dilation != 0, "bad shape");
@@ -325,8 +325,9 @@ extern "C" int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, 
     p.out = out; p.out_ld = out_ld;
     CAB_CHECK_ARG(skip_frac == nullptr || (skip_T > 0 && skip_margin >= 0), "bad skip_T=%d / skip_margin=%d", skip_T, skip_margin);
     p.skip_frac = skip_frac; p.skip_T = skip_T; p.skip_margin = skip_margin;
-    p.accumulate = n_splits > 1 ? 1 : 0;
-    if (p.accumulate) CAB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)taps * M_total * out_ld, stream));
+    // accumulate_into: add to what `out` already holds (the hi*lo + lo*hi partial products of the split-bf16 tier)
+    p.accumulate = (n_splits > 1 || accumulate_into) ? 1 : 0;
+    if (p.accumulate && !accumulate_into) CAB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)taps * M_total * out_ld, stream));
     const int grid = p.n_items < num_sms ? p.n_items : num_sms;
     wg::wgrad_umma_kernel<<<grid, wg::kNumThreads, wg::kSmemBytes, stream>>>(p);
     CAB_CHECK_LAUNCH();

@@ -130,7 +130,11 @@ class _Launch:
 class StackPlan:
 	"""Packed weights + launch list for backbone and decoder of one model, one precision tier."""
 
+	_epochs = 0
+
 	def __init__(self, model, fp32_tier):
+		StackPlan._epochs += 1
+		self.epoch = StackPlan._epochs  # monotonically increasing identity (id() can be reused after a plan is freed)
 		self.fp32_tier = fp32_tier
 		self.blocks = []  # list of list of _Launch (one list per ConvBn1d)
 		self.residual_mode = model.residual

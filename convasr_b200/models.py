@@ -9,9 +9,9 @@ fused log-mel frontend, masked instance norm, one tcgen05 implicit-GEMM launch p
 repeat with BatchNorm folded and residual/activation/mask in the epilogue, the decoder 1x1
 fused with log_softmax + argmax, and the CTC loss.
 
-Training mode (`model.train()`) keeps the same module tree differentiable through ATen ops on
-the GPU (conv/BN backward are not native yet, see DESIGN.md "not built yet") with the native
-frontend, log_softmax and CTC loss.  There is no CPU path: tensors must be CUDA tensors.
+Training mode (`model.train()`) runs forward AND backward of the same module tree on this repo's kernels
+(convasr_b200/training.py: batch-statistics BatchNorm, residual / dense / separable topologies, dgrad, wgrad);
+there is no ATen / cuDNN path and no CPU path: tensors must be CUDA tensors.
 
 Reference sites are cited per class (paths relative to the reference root).
 """
@@ -219,8 +219,7 @@ def relu_dropout(x, p = 0, inplace = False, training = False):
 
 class ConvBn1d(nn.Module):
 	"""models.py:80-151.  Sub-module names (`conv`, `bn`, `conv_residual`, `bn_residual`) fix the
-	state_dict keys.  `forward` here is the differentiable ATen path used in training mode; in eval
-	mode JasperNet.forward bypasses it and launches the fused kernel plan instead."""
+	state_dict keys; JasperNet.forward launches the fused kernel plan (eval) or the native training graph."""
 
 	def __init__(
 		self, num_channels, kernel_size, stride = 1, dropout = 0, groups = 1, num_channels_residual: typing.List = [],
@@ -240,16 +239,7 @@ class ConvBn1d(nn.Module):
 		self.temporal_mask = temporal_mask
 
 	def forward(self, x, lengths_fraction = None, residual: typing.List = []):
-		last = len(self.conv) - 1
-		for i, (conv, bn) in enumerate(zip(self.conv, self.bn)):
-			extra = []
-			if i == last:
-				assert len(self.conv_residual) == len(self.bn_residual) == len(residual)
-				extra = [rbn(rconv(r)) for rconv, rbn, r in zip(self.conv_residual, self.bn_residual, residual)]
-			x = self.activation(bn(conv(x)), residual = extra)
-			if self.temporal_mask and lengths_fraction is not None:
-				x = x * temporal_mask(x, compute_output_lengths(x, lengths_fraction))
-		return x
+		raise NotImplementedError('convasr_b200: ConvBn1d is a parameter container; it runs as part of JasperNet.forward (fused launches in eval mode, convasr_b200/training.py in training mode)')
 
 	def fuse_conv_bn_eval(self):
 		"""models.py:141-151: fold each BatchNorm into the conv before it and replace it by Identity
@@ -380,7 +370,9 @@ class JasperNet(nn.Module):
 
 	def _get_plan(self):
 		prec = self._active_precision()
-		sig = (prec, engine.params_signature(self.backbone), engine.params_signature(self.decoder))
+		# _state_epoch: bumped by everything that writes parameters / running statistics through raw pointers without
+		# touching a tensor version (native training forward, CUDA-graph replays of a training step)
+		sig = (prec, getattr(self, '_state_epoch', 0), engine.params_signature(self.backbone), engine.params_signature(self.decoder))
 		if self._plan is None or self._plan[0] != sig:
 			with torch.no_grad():
 				self._plan = (sig, engine.StackPlan(self, fp32_tier = prec == 'fp32'))
@@ -405,11 +397,10 @@ class JasperNet(nn.Module):
 			if self.frontend is not None:
 				x = self.frontend(x, xlen = xlen)
 			from . import training
-			if getattr(self, 'native_training', True) and training.supported(self):
-				logits, log_probs = training.forward_training(self, x, xlen)  # conv/BN forward + backward on this repo's kernels
-			else:
-				logits = self._forward_training(x, xlen)
-				log_probs = [ops.log_softmax_dim1(l) for l in logits]
+			why = training.unsupported_reason(self)
+			if why is not None:
+				raise NotImplementedError(f'convasr_b200: training of this module tree is not built ({why}); there is no ATen / cuDNN fallback')
+			logits, log_probs = training.forward_training(self, x, xlen)  # conv/BN forward + backward on this repo's kernels
 		else:
 			logits, log_probs = self._forward_native(x, xlen)
 		olen = [compute_output_lengths(l, xlen) for l in logits]
@@ -435,7 +426,7 @@ class JasperNet(nn.Module):
 
 	def _graphed_raw(self, x, xlen):
 		plan = self._get_plan()
-		key = (tuple(x.shape), x.dtype, xlen is not None, id(plan), x.device.index)
+		key = (tuple(x.shape), x.dtype, xlen is not None, plan.epoch, x.device.index)
 		entry = self._graphs.get(key)
 		if entry is None:
 			if len(self._graphs) >= self._graphs_max:
@@ -490,26 +481,6 @@ class JasperNet(nn.Module):
 		norm_xlen = xlen if (nf is not None and nf.temporal_mask) else None
 		hi, lo, _ = ops.instnorm_pack(feats, norm_xlen, nf.eps if nf is not None else -1.0, F_pad = F_pad, C_pad = C_pad, want_lo = plan.fp32_tier, normalize = nf is not None)
 		return plan.run(engine._Act(hi, lo, Fr, C), xlen)
-
-	def _forward_training(self, feats, xlen):
-		# differentiable ATen path (see module docstring); same op order as models.py:296-315
-		if self.normalize_features is not None:
-			nf = self.normalize_features
-			_, _, feats = ops.instnorm_pack(feats, xlen if nf.temporal_mask else None, nf.eps, want_f32 = True)
-		x = feats.to(self.decoder[0].weight.dtype)
-		residual = []
-		n = len(self.backbone)
-		for i, block in enumerate(self.backbone):
-			x = block(x, residual = residual, lengths_fraction = xlen)
-			if i >= n - self.num_epilogue_modules - 1:
-				residual = []
-			elif self.residual == 'dense':
-				residual = residual + [x]
-			elif self.residual:
-				residual = [x]
-			else:
-				residual = []
-		return self.decoder(x)
 
 	# -- reference utility surface --------------------------------------------------------
 	def freeze(self, backbone = 0, decoder0 = False, frontend = False):
@@ -705,21 +676,12 @@ def data_parallel_and_autocast(model, optimizer = None, data_parallel = True, op
 
 
 def distributed_data_parallel_and_autocast(model, local_rank, optimizer = None, opt_level = None, synchronize_bn = False, **kwargs):
-	"""models.py:755-765: SyncBatchNorm (optional) + data parallelism over NCCL / NVLink.  Topologies
-	the native training step covers are returned UNWRAPPED with a parallel.GradSync attached (parameters
-	broadcast from rank 0; the native backward all-reduces each layer's gradient as soon as it exists);
-	everything else gets torch's DistributedDataParallel."""
-	training = model.training
-	from . import parallel, training as native_training
-	if not synchronize_bn and next(model.parameters()).is_cuda and native_training.supported(model):
-		if opt_level not in (None, '', 'O0'):
-			model.set_precision('bf16')
-		return parallel.attach_grad_sync(model), optimizer
+	"""models.py:755-765: data parallelism over NCCL / NVLink.  The model is returned UNWRAPPED with a
+	parallel.GradSync attached (parameters broadcast from rank 0; the native backward all-reduces each layer's
+	gradient as soon as it exists, overlapped with the rest of the backward)."""
+	from . import parallel
 	if synchronize_bn:
-		model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+		raise NotImplementedError('convasr_b200: synchronize_bn is not built (BatchNorm statistics stay per rank, the reference default, train.py:1054)')
 	if opt_level not in (None, '', 'O0'):
-		master_module(model).set_precision('bf16')
-	on_cuda = next(model.parameters()).is_cuda
-	model = nn.parallel.DistributedDataParallel(model, device_ids = [local_rank], output_device = local_rank) if on_cuda else nn.parallel.DistributedDataParallel(model)
-	model.train(training)
-	return model, optimizer
+		model.set_precision('bf16')
+	return parallel.attach_grad_sync(model), optimizer

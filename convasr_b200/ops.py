@@ -155,35 +155,58 @@ def conv1d_fused(
 	_lib.check(rc, 'cab_conv1d_fused')
 
 
-def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0, skip = None):
+def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0, skip = None, out = None):
 	"""out[tap, m, n] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dilation - pad_left, n]  (fp32 [taps, M, N_ld]);
-	skip = (frac [B], T, margin): frames t >= ceil(frac[b]*T) + margin only contribute zeros and are left out"""
+	skip = (frac [B], T, margin): frames t >= ceil(frac[b]*T) + margin only contribute zeros and are left out;
+	out given: the products are ADDED to it (partial products of the split-bf16 tier)"""
 	_need_cuda(a, bx)
 	assert a.dtype == BF16 and bx.dtype == BF16 and a.is_contiguous() and bx.is_contiguous()
 	B = a.shape[0]
 	out_ld = (N_total + 3) // 4 * 4
-	out = torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
+	accumulate = out is not None
+	if out is None:
+		out = torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
 	rc = _lib.load().cab_conv1d_wgrad(
 		_p(a), a_T, a.shape[1], a.shape[2], M_total, _p(bx), b_T, bx.shape[1], bx.shape[2], N_total, B, taps, dilation, pad_left,
 		_p(out), out_ld, n_splits, _p(skip[0]) if skip is not None else None, int(skip[1]) if skip is not None else 0,
-		int(skip[2]) if skip is not None else 0, _stream()
+		int(skip[2]) if skip is not None else 0, int(accumulate), _stream()
 	)
 	_lib.check(rc, 'cab_conv1d_wgrad')
 	return out  # [taps, M_total, ld >= N_total]; columns past N_total are padding
 
 
-def grouped_conv1d_relu(act, T, C_in, wgt, bias, groups, pad_left, ld_out = None, act_lo = None, want_lo = False):
+def grouped_conv1d(act, T, C_in, wgt, bias, groups, pad_left, ld_out = None, act_lo = None, want_lo = False, relu = True, T_out = None):
+	"""grouped conv (+ bias + ReLU): bf16 channels-last [B, T_rows, ld_in] -> [B, T, ld_out]; T frames in and out"""
 	_need_cuda(act, act_lo, wgt, bias)
 	B, T_rows, ld_in = act.shape
 	C_out, _, k = wgt.shape
+	assert T_out is None or T_out == T, 'grouped conv keeps the frame count (odd kernel, same padding)'
 	out = torch.empty(B, T, ld_out or C_out, dtype = BF16, device = act.device)
 	out_lo = torch.empty_like(out) if want_lo else None
-	rc = _lib.load().cab_grouped_conv1d_relu(
-		_p(act), _p(act_lo), B, T, T_rows, C_in, ld_in, _p(wgt), _p(bias), C_out, groups, k, pad_left, _p(out), _p(out_lo),
-		out.shape[1], out.shape[2], _stream()
+	rc = _lib.load().cab_grouped_conv1d(
+		_p(act), _p(act_lo if want_lo else None), B, T, T_rows, C_in, ld_in, _p(wgt), _p(bias), C_out, groups, k, pad_left, _p(out), _p(out_lo),
+		out.shape[1], out.shape[2], int(bool(relu)), _stream()
 	)
-	_lib.check(rc, 'cab_grouped_conv1d_relu')
+	_lib.check(rc, 'cab_grouped_conv1d')
 	return out, out_lo
+
+
+def grouped_conv1d_relu(act, T, C_in, wgt, bias, groups, pad_left, ld_out = None, act_lo = None, want_lo = False):
+	return grouped_conv1d(act, T, C_in, wgt, bias, groups, pad_left, ld_out = ld_out, act_lo = act_lo, want_lo = want_lo, relu = True)
+
+
+def grouped_conv1d_wgrad(dy, T, x, x_T, C_in, C_out, groups, k, pad_left, db = None):
+	"""dy, x: engine._Act-like (hi, lo) bf16 channels-last; returns dW fp32 [C_out, C_in / groups, k]; db (fp32 [C_out]) is filled"""
+	_need_cuda(dy.hi, x.hi)
+	assert T == x_T
+	B = dy.hi.shape[0]
+	dw = torch.empty(C_out, C_in // groups, k, dtype = torch.float32, device = dy.hi.device)
+	rc = _lib.load().cab_grouped_conv1d_wgrad(
+		_p(dy.hi), _p(dy.lo), dy.hi.shape[1], dy.hi.shape[2], _p(x.hi), _p(x.lo if dy.lo is not None else None), B, T, x.hi.shape[1], C_in, x.hi.shape[2], C_out, groups, k, pad_left,
+		_p(dw), _p(db), _stream()
+	)
+	_lib.check(rc, 'cab_grouped_conv1d_wgrad')
+	return dw
 
 
 # ------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ extern "C" {
 
 typedef void* cab_stream_t; /* cudaStream_t */
 
-#define CAB_ABI_VERSION 1
+#define CAB_ABI_VERSION 2
 
 int cab_abi_version(void);
 const char* cab_last_error(void);
@@ -143,11 +143,12 @@ int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
  *   with n_splits > 1 partial sums are reduced in L2 (the call zeroes `out` first).
  *   skip_frac (or NULL): frames t >= ceil(skip_frac[b]*skip_T) + skip_margin of utterance b contribute
  *   exact zeros (one operand is zero there: ragged batch padding) and are left out of the contraction.
+ *   accumulate_into != 0: the products are ADDED to what `out` holds (split-bf16 tier: hi*hi, then hi*lo, lo*hi).
  * ------------------------------------------------------------------------------------- */
 int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total, const void* bx,
                      int b_T, int b_T_rows, int b_ld, int N_total, int B, int taps, int dilation,
                      int pad_left, float* out, int out_ld, int n_splits, const float* skip_frac, int skip_T,
-                     int skip_margin, cab_stream_t stream);
+                     int skip_margin, int accumulate_into, cab_stream_t stream);
 
 /* Training-mode BatchNorm1d + activation + temporal mask around the conv GEMMs
  * (nn.BatchNorm1d(momentum, eps) inside ConvBn1d.forward, models.py:112-113,127-139):
@@ -172,14 +173,48 @@ int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* 
 int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* out_ss,
                     cab_stream_t stream);
-int cab_bn_act_mask_fwd(const void* y, const float* ss, int B, int T, int C, int ld, int act, float act_a,
-                        float act_b, const float* xlen_frac, void* out, float dropout_p,
-                        const int64_t* seed, int64_t salt, cab_stream_t stream);
-int cab_bn_act_mask_bwd(const void* y, const void* grad_out, const float* ss, int B, int T, int C, int ld,
-                        int act, float act_a, float act_b, const float* xlen_frac, float* sums,
-                        void* grad_y, float dropout_p, const int64_t* seed, int64_t salt,
+/* *_lo: NULL, or the bf16 residual halves of the split-bf16 "fp32" tier (value = hi + lo) -- all of a call's
+ * tensors together. */
+int cab_bn_act_mask_fwd(const void* y, const void* y_lo, const float* ss, int B, int T, int C, int ld, int act,
+                        float act_a, float act_b, const float* xlen_frac, void* out, void* out_lo,
+                        float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream);
+/* frozen != 0: the BatchNorm is in eval mode inside a training model (model.freeze, models.py:328-339): it
+ * normalised with its running statistics, so grad_y = scale * dz without the batch-statistics terms. */
+int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo,
+                        const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
+                        const float* xlen_frac, float* sums, void* grad_y, void* grad_y_lo, float dropout_p,
+                        const int64_t* seed, int64_t salt, int frozen,
                         float* ws_partials /* fp32 [CAB_BN_SUM_REPLICAS][2][C] scratch, or NULL */,
                         cab_stream_t stream);
+/* cab_bn_finalize + cab_bn_act_mask_fwd in one launch: every CTA derives the coefficients of its channels from
+ * the raw sums of the conv epilogue (raw_sums: fp32 [2][sums_ld]); CTA 0 also writes out_ss and moves the
+ * running statistics. */
+int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const float* raw_sums, int sums_ld, int n_rows,
+                              const float* gamma, const float* beta, float eps, float momentum,
+                              float* running_mean, float* running_var, float* out_ss, int B, int T, int C,
+                              int ld, int act, float act_a, float act_b, const float* xlen_frac, void* out,
+                              void* out_lo, float dropout_p, const int64_t* seed, int64_t salt,
+                              cab_stream_t stream);
+/* Residual topologies (ConvBn1d.forward models.py:129-133, ResidualActivation.forward :357-371): on the last
+ * repeat of a block every residual source passes its own 1x1 conv + BatchNorm and is added before the
+ * activation ('flat' residuals are added unchanged: ss == NULL).
+ *   cab_bn_multi_act_mask_fwd: out = mask(dropout(act(sum_i (scale_i * y_i + shift_i))))
+ *   cab_act_mask_bwd_dz      : dz = grad_out * act'(z) * mask * dropout, the gate read off the stored `out`;
+ *                              each BatchNorm branch then runs cab_bn_act_mask_bwd(y_i, dz, act = NONE). */
+#define CAB_MAX_BN_BRANCHES 12
+typedef struct {
+    const void* y;    /* bf16 [B, T, ld] branch input (conv output) */
+    const void* y_lo; /* NULL or its split-bf16 residual */
+    const float* ss;  /* [4][C] scale, shift, mean, invstd -- or NULL for an identity branch */
+} cab_bn_branch_t;
+int cab_bn_multi_act_mask_fwd(const cab_bn_branch_t* branches_host, int n_branches, int B, int T, int C, int ld,
+                              int act, float act_a, float act_b, const float* xlen_frac, void* out,
+                              void* out_lo, float dropout_p, const int64_t* seed, int64_t salt,
+                              cab_stream_t stream);
+int cab_act_mask_bwd_dz(const void* out, const void* out_lo, const void* grad_out, const void* grad_out_lo,
+                        int B, int T, int C, int ld, int act, float act_a, float act_b,
+                        const float* xlen_frac, void* dz, void* dz_lo, float dropout_p, const int64_t* seed,
+                        int64_t salt, cab_stream_t stream);
 /* fp32 [Co,Ci,K] -> bf16 tap-major [K,Co,ci_ld] (forward operand) and/or [K,Ci,co_ld] with flipped
  * taps (dgrad operand); and the inverse for a packed fp32 gradient ([K,Co,ld] or, transposed,
  * [K,Ci,ld]) into the parameter layout. */
@@ -190,21 +225,32 @@ typedef struct {
     const float* w;  /* fp32 [Co, Ci, K] */
     void* fwd;       /* bf16 [K, Co, ci_ld] or NULL */
     void* dgrad;     /* bf16 [K, Ci, co_ld] (taps flipped) or NULL */
+    void* fwd_lo;    /* NULL, or the split-bf16 residual of fwd */
+    void* dgrad_lo;  /* NULL, or the split-bf16 residual of dgrad */
     int32_t Co, Ci, K, ci_ld, co_ld;
+    int32_t mode;    /* 0: plain; 1: stride-2 conv as a stride-1 conv over frame pairs -- fwd is
+                        [ (K + 1) / 2 + (pad odd), Co, ci_ld = 2 * ci_alloc ] zero-initialised by the caller,
+                        tap kk -> pair tap floor((kk - pad) / 2) - floor(-pad / 2), channel block (kk - pad) mod 2 */
+    int32_t pad;     /* mode 1: the strided conv's padding */
 } cab_pack_item_t;
 int cab_pack_weights_batched(const cab_pack_item_t* items_host, int n_items, cab_stream_t stream);
+/* transposed: 0 packed = [K, Co, ld]; 1 packed = [K, Ci, ld]; 2 packed = the stride-2 pair layout of pack mode 1
+ * (pair_pad = the conv's padding, pair_ci_alloc = channels per pair half) */
 int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad,
-                     int accumulate, cab_stream_t stream);
+                     int accumulate, int pair_pad, int pair_ci_alloc, cab_stream_t stream);
 /* fp32 [B,C,T] (gradient w.r.t. the logits) -> bf16 channels-last [B,T,ld]; class_sums (fp32 [C],
  * optional) receives the sums over (b,t) = the decoder bias gradient. */
-int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, float* class_sums,
+int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, void* out_lo, float* class_sums,
                    cab_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * section 8f "next" #3: multi-tensor optimizer step with gradient-norm clipping folded in.
  *   mode 0: torch.optim.SGD(momentum, dampening, weight_decay, nesterov)   (train.py:657-662)
  *   mode 1: NovoGrad (optimizers.py:66-90); `momentum` = beta1, `dampening` != 0 = the dampening flag
- *   max_grad_norm > 0: torch.nn.utils.clip_grad_norm_ (train.py:776-779) applied first.
+ *   mode 2: gradient norm only -- total_norm_out = ||all gradients of the table||, nothing is updated
+ *   max_grad_norm > 0: torch.nn.utils.clip_grad_norm_ (train.py:776-779) applied first; the norm is this
+ *   table's own, or *ext_total_norm (device fp32) when given -- clipping is global over all parameter groups,
+ *   so a multi-group optimizer first runs mode 2 over every parameter and passes the result to each group.
  *   Tensors are described by DEVICE tables: param/grad/momentum pointers (int64 [n]), element counts
  *   (int64 [n]) and a flat chunk list (tensor index int32 [n_chunks], element offset int64
  *   [n_chunks], chunk_elems elements per chunk, multiple of 4).  ema: fp32 [n] NovoGrad state.
@@ -218,16 +264,23 @@ int cab_optimizer_step(int mode, int n_tensors, const int64_t* param_ptrs, const
                        float* ws_sumsq, float* ema, float* ws_scale, int64_t* step_cell, int32_t* ws_first,
                        const float* lr_dev, float momentum, float beta2, float eps, float weight_decay,
                        float dampening, int nesterov, float max_grad_norm, float* total_norm_out,
-                       cab_stream_t stream);
+                       const float* ext_total_norm, cab_stream_t stream);
 
-/* grouped Conv1d + bias + ReLU of the separable blocks (models.py:50-64): bf16 channels-last
+/* grouped Conv1d (+ bias + ReLU when relu != 0) of the separable blocks (models.py:50-64): bf16 channels-last
  * in [B, T_rows, ld_in] / out [B, out_T_rows, ld_out] (channels C_out..ld_out-1 are zeroed),
- * weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1.
- * act_lo / out_lo: NULL, or the bf16 residual halves of the split-bf16 "fp32" tier. */
-int cab_grouped_conv1d_relu(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in,
-                            int ld_in, const float* wgt, const float* bias, int C_out, int groups,
-                            int k, int pad_left, void* out, void* out_lo, int out_T_rows, int ld_out,
-                            cab_stream_t stream);
+ * weight fp32 [C_out, C_in/groups, k] (PyTorch layout), stride 1, dilation 1, T frames in and out.
+ * act_lo / out_lo: NULL, or the bf16 residual halves of the split-bf16 "fp32" tier.
+ * relu == 0 with in-group transposed, tap-flipped weights is the conv's input gradient (training). */
+int cab_grouped_conv1d(const void* act, const void* act_lo, int B, int T, int T_rows, int C_in,
+                       int ld_in, const float* wgt, const float* bias, int C_out, int groups,
+                       int k, int pad_left, void* out, void* out_lo, int out_T_rows, int ld_out, int relu,
+                       cab_stream_t stream);
+/* training: weight / bias gradient of that grouped conv (autograd's grouped wgrad behind loss.backward(),
+ * train.py:770-774):  dw[co, j, k] = sum_{b,t} dy[b,t,co] * x[b, t + k - pad, g(co)*cin_g + j]  (fp32 [C_out, C_in/groups, k],
+ * zeroed by the call), db[co] = sum_{b,t} dy[b,t,co] (fp32 [C_out] or NULL).  Odd k with pad = k / 2. */
+int cab_grouped_conv1d_wgrad(const void* dy, const void* dy_lo, int dy_T_rows, int ld_dy, const void* x,
+                             const void* x_lo, int B, int T, int T_rows, int C_in, int ld_in, int C_out,
+                             int groups, int k, int pad_left, float* dw, float* db, cab_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * A10 (+A13/A14 argmax): log_softmax over the class dim of [B, C, T] (models.py:316) fused

@@ -198,7 +198,7 @@ def _round_bf16(t):
 	return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
 
 
-def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False, round_bf16 = False, stats_out = None):
+def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride1 = 2, groups = 1, num_epilogue = 2, dtype = torch.float32, training = False, round_bf16 = False, stats_out = None, frozen_blocks = 0):
 	"""JasperNet.forward models.py:303-317 (backbone, decoder, log_softmax) in eval mode.
 
 	x: normalised features [B, C, F].  Returns (logits list, log_probs list, olen list)."""
@@ -210,7 +210,9 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 	x = rb(x)
 	n_blocks = _count(sd, 'backbone.{}.')
 	res = []
+	train_all = training
 	for i in range(n_blocks):
+		training = train_all and i >= frozen_blocks  # model.freeze(backbone = N) pins the BatchNorms of the first N blocks to eval (models.py:328-339)
 		reps = _count(sd, 'backbone.%d.conv.{}.' % i)
 		n_res = _count(sd, 'backbone.%d.conv_residual.{}.' % i) if residual else 0
 		for j in range(reps):
@@ -249,6 +251,7 @@ def conv_stack_forward(sd, x, xlen, act, residual, dilation, mask = True, stride
 			res = [x]
 		else:
 			res = []
+	training = train_all
 	logits = [F.conv1d(x, rb(sd['decoder.0.weight']), sd['decoder.0.bias'])]  # models.py:26
 	if 'decoder.1.0.conv.0.0.weight' in sd:  # Decoder(type = 'bpe') models.py:27-33: two ConvBn1d(k = 15, relu, no lengths -> no mask)
 		h = x

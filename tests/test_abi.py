@@ -15,7 +15,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_surface():
 	syms = declared_symbols()
-	for name in ['cab_frontend_logmel', 'cab_instnorm_pack', 'cab_conv1d_fused', 'cab_grouped_conv1d_relu', 'cab_log_softmax_argmax', 'cab_log_softmax_bwd',
+	for name in ['cab_frontend_logmel', 'cab_instnorm_pack', 'cab_conv1d_fused', 'cab_grouped_conv1d', 'cab_grouped_conv1d_wgrad', 'cab_bn_multi_act_mask_fwd', 'cab_act_mask_bwd_dz', 'cab_bn_act_mask_fwd_stats', 'cab_log_softmax_argmax', 'cab_log_softmax_bwd',
 				'cab_ctc_loss_fwd', 'cab_ctc_loss_bwd', 'cab_ctc_alignment', 'cab_topk_ids', 'cab_greedy_collapse', 'cab_entropy', 'cab_last_error', 'cab_abi_version', 'cab_launch_count']:
 		assert name in syms
 
@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 	for name in declared_symbols():
 		assert hasattr(lib, name), f'{name} declared in the header but not exported'
 	loaded = _lib.load()
-	assert loaded.cab_abi_version() == 1
+	assert loaded.cab_abi_version() == _lib.ABI_VERSION == 2
 	# the ctypes table binds exactly the declared compute entry points
 	assert sorted(_lib.SIGNATURES) == sorted(s for s in declared_symbols() if s not in _lib.INTROSPECTION)
 
@@ -66,7 +66,8 @@ def test_ctypes_table_matches_header_prototypes():
 		assert name in protos, name
 		params = [p for p in protos[name].split(',') if p.strip() and p.strip() != 'void']
 		assert len(params) == len(argtypes), (name, len(params), len(argtypes))
-	assert ctypes.sizeof(_lib.PackItem) == 48  # 3 pointers + 5 int32, padded to 8
+	assert ctypes.sizeof(_lib.PackItem) == 72  # 5 pointers + 7 int32, padded to 8
+	assert ctypes.sizeof(_lib.BnBranch) == 24
 	assert _lib.ConvEpilogue.skip_frac.offset == _lib.ConvEpilogue.stats.offset + 8
 	assert _lib.ConvEpilogue.skip_margin.offset == _lib.ConvEpilogue.skip_frac.offset + 12
 	assert ctypes.sizeof(_lib.ConvEpilogue) == _lib.ConvEpilogue.skip_frac.offset + 16

@@ -1,14 +1,15 @@
 """Native training step (conv/BN forward with batch statistics + dgrad/wgrad/BN backward on this
 repo's kernels) against CPU fp32 references.
 
-Precision note.  The native training path keeps activations and operand copies of the weights in
-bf16 (fp32 accumulation, fp32 BatchNorm arithmetic, fp32 gradients).  A randomly initialised
-Wav2Letter in TRAINING mode is a chaotic map: batch-statistics BatchNorm renormalises every layer
-and a perturbation grows ~1.17x per conv layer (measured with a CPU bf16 emulation: 0.3 % after
-layer 1, 10 % after layer 19, for any bf16 implementation, including the reference's own apex/O2
-path).  Parity is therefore pinned (a) per kernel at tight tolerances on identical inputs,
-(b) end to end on a 6-conv-layer Wav2Letter against the oracle with the same bf16 rounding points
-at the BASELINE bf16 bar (2e-2), and (c) on the full 19-layer model by loss and gradient direction.
+Precision note.  Two tiers (model.set_precision): 'fp32' keeps every activation, gradient activation and operand
+copy as a split-bf16 (hi, lo) pair with three accumulated MMA passes -- the exactness harness, pinned against the
+reference's own TRAIN-mode outputs (tests/golden/train.pt) at 1e-3; 'bf16' is the speed tier: a randomly initialised
+Wav2Letter in TRAINING mode amplifies a perturbation ~1.2x per conv layer (batch-statistics BatchNorm renormalises
+every layer), so its end-to-end error is reported as a measured number next to the fp32-tier one.  Independently of
+precision, every nonlinearity of the reference has a kink and a gate that flips between two implementations moves the
+gradient by O(1 / sqrt(elements)) -- the reference vs its own fp32 CPU restatement differ by 1.7e-2 at full depth for
+that reason alone (tests/test_oracle_golden.py); full-depth exactness is therefore asserted on the smooth-regime case
+(oracle.smooth_regime) and on the shallow / residual / dense cases where no gate sits within rounding of a kink.
 """
 import pytest
 import torch
@@ -59,12 +60,12 @@ def test_bn_act_mask_forward_backward_kernels():
 		_lib.check(lib.cab_bn_batch_stats(ops._p(yd), B, T, C, C, ops._p(gamma_d), ops._p(beta_d), 1e-5, 0.1, ops._p(rm_d), ops._p(rv_d), ops._p(ws), ops._p(ss), ops._stream()), 'stats')
 		out = torch.empty_like(yd)
 		xl = xlen.to(dev)
-		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), 0.0, None, 0, ops._stream()), 'fwd')
+		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), None, ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), None, 0.0, None, 0, ops._stream()), 'fwd')
 		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
-		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), 0.0, None, 0, ops._p(part), ops._stream()), 'bwd')
+		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), None, ops._p(go_d), None, ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), None, 0.0, None, 0, 0, ops._p(part), ops._stream()), 'bwd')
 		# without the replica scratch the row-walker variant runs: same results
 		sums2 = torch.empty(2, C, device = dev); dy2 = torch.empty_like(yd)
-		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums2), ops._p(dy2), 0.0, None, 0, None, ops._stream()), 'bwd (row walker)')
+		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), None, ops._p(go_d), None, ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums2), ops._p(dy2), None, 0.0, None, 0, 0, None, ops._stream()), 'bwd (row walker)')
 		torch.cuda.synchronize()
 		assert rel(sums2, sums) < 1e-5 and rel(dy2.float(), dy.float()) < 1e-3, act_name
 		assert rel(out.float().permute(0, 2, 1), o) < 4e-3, act_name  # bf16 output rounding
@@ -91,7 +92,7 @@ def test_dropout_in_bn_act_kernels():
 	outs = []
 	for salt in (3, 3, 4):
 		out = torch.empty_like(yd)
-		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(out), p, ops._p(seed), salt, ops._stream()), 'fwd')
+		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), None, ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(out), None, p, ops._p(seed), salt, ops._stream()), 'fwd')
 		outs.append(out.float().permute(0, 2, 1).cpu())
 	assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])  # deterministic in (seed, salt)
 	# reference without dropout
@@ -106,7 +107,7 @@ def test_dropout_in_bn_act_kernels():
 	mask = torch.where(pos, (outs[0] != 0).float(), torch.ones_like(z)) / (1 - p)  # where z ~ 0 the mask is irrelevant
 	(z * mask).backward(go)
 	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
-	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), ops._p(go_d), ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), p, ops._p(seed), 3, ops._p(part), ops._stream()), 'bwd')
+	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), None, ops._p(go_d), None, ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), None, p, ops._p(seed), 3, 0, ops._p(part), ops._stream()), 'bwd')
 	torch.cuda.synchronize()
 	assert rel(dy.float().permute(0, 2, 1), yr.grad) < 2e-2
 
@@ -116,7 +117,7 @@ def test_training_step_with_dropout_runs_natively():
 	dev = torch.device('cuda:0')
 	C = 38
 	from convasr_b200 import models
-	m = models.Wav2Letter(64, [C], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0.2, check_time_dim_padded = False, base_width = 32).to(dev).train()
+	m = models.Wav2Letter(64, [C], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0.2, check_time_dim_padded = False, base_width = 32).to(dev).train().set_precision('bf16')
 	assert training.supported(m) and m.backbone[1].activation.dropout == 0.2
 	sig, xlen, y, ylen = [t.to(dev) for t in _batch(C)]
 	losses = []
@@ -153,13 +154,13 @@ def test_wgrad_and_dgrad_kernels_against_cpu_autograd():
 
 
 # ------------------------------------------------------------------------------------------ end to end
-def _model(dev, kwargs, C = 38, seed = 7):
+def _model(dev, kwargs, C = 38, seed = 7, precision = 'bf16'):
 	from convasr_b200 import models, training
 	m = models.Wav2Letter(64, [C], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, **kwargs)
 	shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')}
 	sd = O.synth_state_dict(shapes, seed = seed)
 	m.load_state_dict(sd, strict = False)
-	m = m.to(dev).train()
+	m = m.to(dev).train().set_precision(precision)
 	assert training.supported(m)
 	return m, sd
 
@@ -239,27 +240,6 @@ def test_training_step_full_depth_loss_and_gradient_direction():
 	print('full depth: loss', float(loss), float(ref_loss), 'cos', cos)
 	assert cos > 0.7, cos  # 18 chaotic layers each way at bf16 (see module docstring)
 	assert all(torch.isfinite(named[k].grad).all() for k in keys)
-
-
-def test_native_training_agrees_with_aten_path():
-	"""Same module tree and inputs: native kernels vs the ATen (cuDNN) fallback on the same GPU."""
-	dev = torch.device('cuda:0')
-	C = 38
-	m, sd = _model(dev, dict(base_width = 32, num_blocks = 1))
-	sig, xlen, y, ylen = [t.to(dev) for t in _batch(C)]
-	out = m(sig, xlen, y = y, ylen = ylen)
-	(out['loss'] * ylen[:, 0]).mean().backward()
-	native = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
-	m.load_state_dict(sd, strict = False)  # undo the running-stat update
-	m.zero_grad()
-	m.native_training = False
-	out2 = m(sig, xlen, y = y, ylen = ylen)
-	(out2['loss'] * ylen[:, 0]).mean().backward()
-	assert rel(out['loss'], out2['loss']) < 2e-2
-	tot_n = torch.cat([native[k].flatten() for k in native])
-	tot_a = torch.cat([dict(m.named_parameters())[k].grad.flatten() for k in native])
-	print('native vs ATen fp32 path: total grad rel', rel(tot_n, tot_a))
-	assert rel(tot_n, tot_a) < 0.2  # bf16 native vs fp32 ATen
 
 
 def test_graphed_train_step_equals_eager_step():
@@ -422,10 +402,197 @@ def test_batched_weight_pack_equals_per_layer_pack():
 	ws = [torch.randn(*s, generator = g).to(dev) for s in shapes]
 	specs = [(w, (w.shape[1] + 63) // 64 * 64, (w.shape[0] + 63) // 64 * 64, i != 0) for i, w in enumerate(ws)]
 	batched = training._pack_all(specs)
-	for (w, ci_ld, co_ld, want_dgrad), (fwd, dgr) in zip(specs, batched):
+	for (w, ci_ld, co_ld, want_dgrad), (fwd, dgr, _, _) in zip(specs, batched):
 		fwd1, dgr1 = training._pack(w, ci_ld, co_ld, want_dgrad)
 		assert torch.equal(fwd, fwd1) and (dgr is None) == (dgr1 is None) and (dgr is None or torch.equal(dgr, dgr1))
 		Co, Ci, K = w.shape
 		assert torch.equal(fwd[:, :, :Ci], w.permute(2, 0, 1).to(BF16))
 		if dgr is not None:
 			assert torch.equal(dgr[:, :, :Co], w.flip(2).permute(2, 1, 0).to(BF16))
+
+
+# ------------------------------------------------------------------------------------------ golden-backed (reference TRAIN mode)
+def _golden_model(dev, c, precision):
+	from convasr_b200 import models, training
+	from test_oracle_golden import golden_state_dict
+	kw = {k: v for k, v in c['kwargs'].items() if k not in ('smooth', 'freeze')}
+	m = getattr(models, c['model'])(64, [c['num_classes']], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, **kw)
+	m.load_state_dict(golden_state_dict(c), strict = False)
+	m = m.to(dev).train().set_precision(precision)
+	if c['kwargs'].get('freeze'):
+		m.freeze(backbone = c['kwargs']['freeze'])
+	assert training.unsupported_reason(m) is None, training.unsupported_reason(m)
+	return m
+
+
+def _native_train_step(dev, c, precision):
+	m = _golden_model(dev, c, precision)
+	ylen = c['ylen'].to(dev)
+	out = m(c['signal'].to(dev), c['xlen'].to(dev), y = c['y'].to(dev), ylen = ylen)
+	(out['loss'] * ylen[:, 0]).mean().backward()  # train.py:754-755
+	grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None and not k.startswith('frontend.')}
+	stats = {k: v.detach().cpu() for k, v in m.state_dict().items() if k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))}
+	return out, grads, stats
+
+
+def test_training_step_matches_reference_train_mode_golden(golden, capsys):
+	"""The native training step against the REFERENCE's own train-mode outputs (oracle/make_golden.py: golden_train):
+	logits, per-utterance loss, every parameter gradient, BatchNorm running statistics after the step -- plain, residual,
+	dense, separable, mask-free and frozen-backbone families.  fp32 tier: 1e-3 wherever no activation gate can flip
+	(shallow, residual, dense, small, smooth-regime full depth; the reference vs its own CPU restatement is ~3e-5 there),
+	5e-2 on the two kinked full-depth cases (reference vs its own restatement: 1.6e-2 / 1.1e-2).  bf16 tier: measured and
+	reported, bounded loosely."""
+	from test_oracle_golden import check_grads_against_golden
+	dev = torch.device('cuda:0')
+	report = []
+	for c in golden('train')['cases']:
+		deep_kinked = not c['kwargs'].get('smooth') and c['kwargs'].get('num_blocks', 5) > 1 and c['model'] in ('Wav2Letter', 'JasperNetSeparable')
+		for precision in ('fp32', 'bf16'):
+			out, grads, stats = _native_train_step(dev, c, precision)
+			assert torch.equal(out['olen'][0].cpu(), c['olen'])
+			e_logits = rel(out['logits'][0], c['logits'])
+			e_loss = float(((out['loss'].cpu() - c['loss']).abs() / c['loss'].abs()).max())
+			tol_fwd, tol_grad = (1e-3, 5e-2 if deep_kinked else 1e-3) if precision == 'fp32' else (2e-2 if not deep_kinked else 5e-2, 0.5)
+			assert e_logits < tol_fwd, (c['model'], c['kwargs'], precision, e_logits)
+			assert e_loss < max(tol_fwd, 1e-4) * (1 if precision == 'fp32' else 5), (c['model'], precision, e_loss)
+			total, worst = check_grads_against_golden(grads, c['grads'], tol_grad, (c['model'], precision))
+			for k, v in c['stats'].items():
+				if k.endswith('num_batches_tracked'):
+					assert int(stats[k]) == int(v), k
+				else:
+					assert torch.allclose(stats[k], v, rtol = 2e-3 if precision == 'fp32' else 5e-2, atol = 1e-4 if precision == 'fp32' else 1e-2), (k, precision)
+			report.append(f'{c["model"]:22s} {str(c["kwargs"]):48s} {precision}: logits {e_logits:.2e} loss {e_loss:.2e} grads total {total:.2e} worst tensor {worst:.2e}')
+	with capsys.disabled():
+		print('\nnative training step vs reference TRAIN-mode golden:\n  ' + '\n  '.join(report))
+
+
+def test_multi_branch_bn_kernels_against_autograd():
+	"""cab_bn_multi_act_mask_fwd / cab_act_mask_bwd_dz + per-branch BatchNorm backward == torch autograd of
+	act(BN0(y0) + BN1(y1) + y2) * mask (two BatchNorm branches and an identity branch), both tiers"""
+	import ctypes
+	from convasr_b200 import _lib, ops
+	dev = torch.device('cuda:0')
+	lib = _lib.load()
+	g = torch.Generator().manual_seed(3)
+	B, C, T = 3, 96, 77
+	xlen = torch.tensor([1.0, 0.6, 0.35])
+	for act_name, code, a, b in (('hardtanh', _lib.ACT_HARDTANH, 0.0, 20.0), ('relu', _lib.ACT_RELU, 0.0, 0.0), ('leaky_relu', _lib.ACT_LEAKY_RELU, 0.01, 0.0)):
+		for split in (False, True):
+			q = (lambda t: t) if split else (lambda t: t.to(BF16).float())
+			ys = [q(torch.randn(B, C, T, generator = g) * 2 + torch.randn(1, C, 1, generator = g)) for _ in range(3)]
+			gammas = [torch.rand(C, generator = g) + 0.5 for _ in range(2)]
+			betas = [torch.randn(C, generator = g) + (5.0 if act_name == 'hardtanh' else 0.0) for _ in range(2)]
+			go = q(torch.randn(B, C, T, generator = g))
+			yr = [y.clone().requires_grad_(True) for y in ys]
+			gr, br = [x.clone().requires_grad_(True) for x in gammas], [x.clone().requires_grad_(True) for x in betas]
+			z = F.batch_norm(yr[0], None, None, gr[0], br[0], True, 0.1, 1e-5) + F.batch_norm(yr[1], None, None, gr[1], br[1], True, 0.1, 1e-5) + yr[2]
+			o = O._activation(z, (act_name, a, b) if act_name == 'hardtanh' else (act_name, a) if act_name == 'leaky_relu' else (act_name, ))
+			o = o * O.temporal_mask(T, O.output_lengths(T, xlen))
+			o.backward(go)
+
+			def dv(t):  # [B, C, T] fp32 -> (hi, lo) channels-last on the device
+				x = t.permute(0, 2, 1).contiguous()
+				hi = x.to(BF16)
+				return hi.to(dev), ((x - hi.float()).to(BF16).to(dev) if split else None)
+
+			y_d = [dv(y) for y in ys]
+			go_d = dv(go)
+			xl = xlen.to(dev)
+			sss = []
+			for i in range(2):
+				ws = torch.empty(2, C, device = dev); ss = torch.empty(4, C, device = dev)
+				# statistics from the fp32 values (the conv epilogue accumulates hi + lo in the split tier)
+				yf = (y_d[i][0].float() + (y_d[i][1].float() if split else 0)).reshape(-1, C)
+				sums = torch.stack([yf.sum(0), (yf * yf).sum(0)]).contiguous()
+				gd, bd = gammas[i].to(dev), betas[i].to(dev)
+				_lib.check(lib.cab_bn_finalize(ops._p(sums), B * T, C, ops._p(gd), ops._p(bd), 1e-5, 0.1, None, None, ops._p(ss), ops._stream()), 'finalize')
+				sss.append(ss)
+			branches = [(y_d[0], sss[0]), (y_d[1], sss[1]), (y_d[2], None)]
+			arr = (_lib.BnBranch * 3)(*[_lib.BnBranch(t[0].data_ptr(), t[1].data_ptr() if split else None, s.data_ptr() if s is not None else None) for t, s in branches])
+			out_hi = torch.empty(B, T, C, dtype = BF16, device = dev); out_lo = torch.empty_like(out_hi) if split else None
+			_lib.check(lib.cab_bn_multi_act_mask_fwd(arr, 3, B, T, C, C, code, a, b, ops._p(xl), ops._p(out_hi), ops._p(out_lo), 0.0, None, 0, ops._stream()), 'multi fwd')
+			dz_hi = torch.empty_like(out_hi); dz_lo = torch.empty_like(out_hi) if split else None
+			_lib.check(lib.cab_act_mask_bwd_dz(ops._p(out_hi), ops._p(out_lo), ops._p(go_d[0]), ops._p(go_d[1]), B, T, C, C, code, a, b, ops._p(xl), ops._p(dz_hi), ops._p(dz_lo), 0.0, None, 0, ops._stream()), 'dz')
+			tol = 2e-5 if split else 4e-3
+			val = lambda hi, lo: (hi.float() + (lo.float() if lo is not None else 0)).permute(0, 2, 1)
+			assert rel(val(out_hi, out_lo), o) < tol, (act_name, split, rel(val(out_hi, out_lo), o))
+			assert rel(val(dz_hi, dz_lo), yr[2].grad) < tol, (act_name, split)  # the identity branch receives dz itself
+			part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+			for i in range(2):
+				sums = torch.empty(2, C, device = dev); dy_hi = torch.empty_like(out_hi); dy_lo = torch.empty_like(out_hi) if split else None
+				_lib.check(lib.cab_bn_act_mask_bwd(ops._p(y_d[i][0]), ops._p(y_d[i][1]), ops._p(dz_hi), ops._p(dz_lo), ops._p(sss[i]), B, T, C, C, _lib.ACT_NONE, 0.0, 0.0, None, ops._p(sums), ops._p(dy_hi), ops._p(dy_lo),
+													0.0, None, 0, 0, ops._p(part), ops._stream()), 'branch bwd')
+				torch.cuda.synchronize()
+				assert rel(val(dy_hi, dy_lo), yr[i].grad) < (1e-4 if split else 6e-3), (act_name, split, i, rel(val(dy_hi, dy_lo), yr[i].grad))
+				assert rel(sums[0], br[i].grad) < (1e-4 if split else 5e-3) and rel(sums[1], gr[i].grad) < (1e-4 if split else 5e-3), (act_name, split, i)
+
+
+def test_grouped_conv_training_kernels_against_autograd():
+	"""separable blocks: the grouped conv's weight / bias gradient (cab_grouped_conv1d_wgrad) and input gradient
+	(cab_grouped_conv1d with in-group transposed, tap-flipped weights, no ReLU) vs torch autograd, both tiers"""
+	from convasr_b200 import engine, ops
+	dev = torch.device('cuda:0')
+	g = torch.Generator().manual_seed(4)
+	for (B, T, C_in, C_out, groups, k) in [(3, 150, 64, 96, 32, 11), (2, 90, 256, 384, 128, 13), (2, 70, 96, 96, 32, 25), (2, 65, 224, 224, 32, 5)]:
+		for split in (False, True):
+			q = (lambda t: t) if split else (lambda t: t.to(BF16).float())
+			x = q(torch.randn(B, C_in, T, generator = g)).requires_grad_(True)
+			w = (torch.randn(C_out, C_in // groups, k, generator = g) / (k * C_in / groups)**0.5).requires_grad_(True)
+			bias = torch.randn(C_out, generator = g).requires_grad_(True)
+			y = F.conv1d(x, w, bias, padding = k // 2, groups = groups)
+			dy = q(torch.randn(y.shape, generator = g))
+			y.backward(dy)
+
+			def dv(t, ld):
+				xcl = torch.zeros(t.shape[0], t.shape[2], ld)
+				xcl[:, :, :t.shape[1]] = t.detach().permute(0, 2, 1)
+				hi = xcl.to(BF16)
+				return engine._Act(hi.to(dev), (xcl - hi.float()).to(BF16).to(dev) if split else None, t.shape[2], t.shape[1])
+
+			ld_in, ld_out = engine._ceil_to(C_in, 64), engine._ceil_to(C_out, 64)
+			xd, dyd = dv(x, ld_in), dv(dy, ld_out)
+			db = torch.empty(C_out, device = dev)
+			dw = ops.grouped_conv1d_wgrad(dyd, T, xd, T, C_in, C_out, groups, k, k // 2, db)
+			tol = 2e-5 if split else 1e-5
+			assert rel(dw, w.grad) < tol, (C_in, C_out, k, split, rel(dw, w.grad))
+			assert rel(db, bias.grad) < tol
+			cin_g, cout_g = C_in // groups, C_out // groups
+			wt = w.detach().view(groups, cout_g, cin_g, k).permute(0, 2, 1, 3).flip(3).reshape(C_in, cout_g, k).contiguous().to(dev)
+			dx_hi, dx_lo = ops.grouped_conv1d(dyd.hi, T, C_out, wt, None, groups, k - 1 - k // 2, ld_out = ld_in, act_lo = dyd.lo, want_lo = split, relu = False)
+			dx = dx_hi.float() + (dx_lo.float() if split else 0)
+			assert rel(dx[:, :, :C_in].permute(0, 2, 1), x.grad) < (2e-5 if split else 4e-3), (C_in, C_out, k, split)
+
+
+def test_eval_plan_is_rebuilt_after_graphed_training_steps():
+	"""the native kernels write parameters / running statistics through raw pointers; a CUDA-graph replay
+	runs no Python, so the cached eval plan (folded BN, packed weights) must be invalidated explicitly.  Also: the learning
+	rate a scheduler sets between replays reaches the device cell the replay reads."""
+	from convasr_b200 import optimizers, training
+	dev = torch.device('cuda:0')
+	C = 38
+	m, sd = _model(dev, dict(base_width = 32, num_blocks = 1))
+	sig, xlen, y, ylen = [t.to(dev) for t in _batch(C)]
+	opt = optimizers.SGD([p for p in m.parameters() if p.requires_grad], lr = 1e-2, momentum = 0.9)
+	sched = optimizers.MultiStepLR(opt, gamma = 0.1, milestones = [2])
+	step = training.GraphedTrainStep(m, opt, sig, xlen, y, ylen, warmup = 2)
+
+	def eval_logits():
+		m.eval()
+		with torch.no_grad():
+			lg = m(sig, xlen)['logits'][0].clone()
+		m.train()
+		return lg
+
+	first = eval_logits()
+	w0 = m.backbone[1].conv[0][0].weight.detach().clone()
+	step(sig, xlen, y, ylen)
+	w1 = m.backbone[1].conv[0][0].weight.detach().clone()
+	sched.step(2)  # lr 1e-2 -> 1e-3 from here on
+	step(sig, xlen, y, ylen)
+	w2 = m.backbone[1].conv[0][0].weight.detach().clone()
+	second = eval_logits()
+	assert not torch.equal(first, second), 'eval after graph replays must see the trained weights and moved running statistics'
+	m._plan = None  # a plan built from scratch gives the same numbers as the one the signature refreshed
+	assert torch.equal(second, eval_logits())
+	d1, d2 = float((w1 - w0).norm()), float((w2 - w1).norm())
+	assert d2 < 0.5 * d1, (d1, d2)  # the 10x smaller learning rate took effect inside the replay (momentum carries some of the old step)

@@ -121,30 +121,32 @@ def test_precision_selection():
 	assert m2._active_precision() == 'bf16'
 
 
-def test_training_path_matches_oracle_on_cpu_modules(golden):
-	"""The module tree's own differentiable forward (ConvBn1d.forward) in eval mode equals the
-	oracle's conv stack on CPU for every golden family -- checks topology + residual wiring."""
-	for c in golden('models')['cases']:
-		if c['fused']:
-			continue
-		m = getattr(models, c['model'])(64, [c['num_classes']], dropout = 0., **c['kwargs']).eval()
-		sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
-		m.load_state_dict(sd, strict = False)
-		feats = O.masked_instance_norm(O.frontend_logmel(c['signal'], c['xlen']), c['xlen'])
-		with torch.no_grad():
-			x = feats
-			residual = []
-			for i, block in enumerate(m.backbone):
-				x = block(x, residual = residual, lengths_fraction = c['xlen'])
-				if i >= len(m.backbone) - 3:
-					residual = []
-				elif m.residual == 'dense':
-					residual = residual + [x]
-				elif m.residual:
-					residual = [x]
-			logits = m.decoder(x)[0]
-		rel = float((logits - c['logits']).norm() / c['logits'].norm())
-		assert rel < 1e-4, (c['model'], rel)
+def test_training_graph_wiring_follows_the_reference_forward():
+	"""training._graph: activation ids and residual sources per repeat follow JasperNet.forward (models.py:303-313):
+	residual branches join on the LAST repeat of a block only, 'dense' accumulates every earlier block output, plain
+	residual keeps the previous one, the two epilogue modules (and the block before them feeding forward) get none."""
+	from convasr_b200 import training
+	for name, mode in (('Wav2Letter', False), ('Wav2LetterResidual', True), ('Wav2LetterDense', 'dense'), ('Wav2LetterFlat', 'flat'), ('JasperNetSeparable', 'dense')):
+		kw = dict(base_width = 128, groups = 128) if 'Separable' in name else dict(base_width = 16)
+		m = getattr(models, name)(64, [38], dropout = 0., **kw)
+		reps = training._graph(m)
+		assert [r.in_id for r in reps] == list(range(len(reps))) and [r.out_id for r in reps] == list(range(1, len(reps) + 1))
+		block_out, k = [], 0
+		for i, block in enumerate(m.backbone):
+			n = len(block.conv)
+			for j in range(n):
+				rep = reps[k + j]
+				srcs = [s for s, _, _ in rep.res]
+				if j < n - 1 or not mode or i == 0 or i >= len(m.backbone) - 2:
+					assert srcs == [], (name, i, j)
+				elif mode == 'dense':
+					assert srcs == block_out[:i], (name, i, j, srcs)
+				else:
+					assert srcs == block_out[i - 1:i], (name, i, j, srcs)
+				assert all((c is None) == (mode == 'flat') for _, c, _ in rep.res)
+				assert (rep.grouped is not None) == ('Separable' in name and 0 < i < len(m.backbone) - 2)
+			k += n
+			block_out.append(reps[k - 1].out_id)
 
 
 # ------------------------------------------------------------------------------------------ batch feed
@@ -209,9 +211,12 @@ def test_bench_reference_arm_prints_the_contract_line():
 
 
 def test_native_training_coverage_by_model_class():
-	"""training.supported(): the dense, residual-free families train on the native kernels, everything else takes the
-	documented ATen path."""
+	"""training.unsupported_reason(): every family of the model zoo trains on the native kernels except the in-place /
+	invertible variants (section 8f rank 4) and the instance-norm-with-running-stats class the reference itself cannot run;
+	there is no ATen path to fall back to -- the model raises instead."""
 	from convasr_b200 import models, training
-	native = {name for name in ALL_MODELS if training.supported(getattr(models, name)(64, [38], **(dict(base_width = 128) if 'Separable' in name else dict(base_width = 16))))}
-	assert 'Wav2Letter' in native and all(n.startswith('Wav2Letter') for n in native), native
-	assert not any('Jasper' in n for n in native)
+	reasons = {name: training.unsupported_reason(getattr(models, name)(64, [38], **(dict(base_width = 128) if 'Separable' in name else dict(base_width = 16)))) for name in ALL_MODELS}
+	refused = {n for n, r in reasons.items() if r is not None}
+	assert refused == {'Wav2LetterDenseNoDilationInplace', 'JasperNetBigInplace'}, reasons
+	assert training.unsupported_reason(models.Wav2Letter(64, [38, 120], base_width = 16, decoder_type = 'bpe')) is not None
+	assert not hasattr(models.JasperNet, '_forward_training')
