@@ -145,3 +145,49 @@ def check(rc, what):
 
 def launch_count():
 	return int(load().cab_launch_count())
+
+
+class trace:
+	"""Per-entry-point device timing for bench.py: `with _lib.trace() as t:` wraps every C-ABI call in a pair of CUDA
+	events on the launching (current torch) stream; afterwards t.summary() = {entry point: (calls, total ms)}.
+	Eager launches only (a CUDA-graph replay does not pass through here)."""
+
+	def __init__(self, names = None):
+		self.names = list(names) if names is not None else list(SIGNATURES)
+		self.events = []
+
+	def __enter__(self):
+		import torch
+		lib = load()
+		self._orig = {}
+		for name in self.names:
+			fn = getattr(lib, name)
+			self._orig[name] = fn
+
+			def make(fn, name):
+				def traced(*a):
+					e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
+					e0.record()
+					rc = fn(*a)
+					e1.record()
+					self.events.append((name, e0, e1))
+					return rc
+				return traced
+
+			setattr(lib, name, make(fn, name))
+		return self
+
+	def __exit__(self, *exc):
+		lib = load()
+		for name, fn in self._orig.items():
+			setattr(lib, name, fn)
+		return False
+
+	def summary(self):
+		import torch
+		torch.cuda.synchronize()
+		out = {}
+		for name, e0, e1 in self.events:
+			n, ms = out.get(name, (0, 0.0))
+			out[name] = (n + 1, ms + e0.elapsed_time(e1))
+		return out

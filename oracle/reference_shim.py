@@ -1,7 +1,7 @@
-"""Import the REAL reference (read-only tree at /root/reference) on CPU, with stub modules for
-the dependencies this image lacks.
+"""Import the REAL reference (read-only tree at /root/reference, or its staged copy baseline/_ref on a GPU box),
+with stub modules for the dependencies this image lacks.
 
-TEST INFRASTRUCTURE ONLY, and only usable where /root/reference exists (the build container):
+TEST / BENCH-BASELINE INFRASTRUCTURE ONLY, usable where /root/reference or baseline/_ref exists:
 it is used by oracle/make_golden.py to mint tests/golden/ and by the `reference`-marked tests
 that pin oracle/oracle.py against the reference itself.  Nothing is copied from the reference.
 """
@@ -11,7 +11,33 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get('CONVASR_REFERENCE_DIR', '/root/reference')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_DIR = os.path.join(ROOT, 'baseline', '_ref')  # git-ignored copy made by stage(); travels to the GPU box with the snapshot
+
+
+def _reference_dir():
+	for d in (os.environ.get('CONVASR_REFERENCE_DIR'), '/root/reference', STAGED_DIR):
+		if d and os.path.isfile(os.path.join(d, 'models.py')):
+			return d
+	return '/root/reference'
+
+
+REFERENCE_DIR = _reference_dir()
+
+
+def stage():
+	"""Copy the reference's top-level Python modules, UNMODIFIED, into the git-ignored baseline/_ref/ so that bench.py's
+	reference arm (and the gpu_baseline leg) can run the real reference on the GPU box, where /root/reference does not
+	exist.  Build-container only; nothing under baseline/_ref is tracked."""
+	import shutil
+	src = '/root/reference'
+	if not os.path.isfile(os.path.join(src, 'models.py')):
+		return None
+	os.makedirs(STAGED_DIR, exist_ok = True)
+	for f in sorted(os.listdir(src)):
+		if f.endswith('.py'):
+			shutil.copyfile(os.path.join(src, f), os.path.join(STAGED_DIR, f))
+	return STAGED_DIR
 
 
 def available():
@@ -52,7 +78,7 @@ def load():
 		sys.modules.pop(n, None)
 	sys.path.insert(0, REFERENCE_DIR)
 	try:
-		for n in ('shaping', 'transcripts', 'models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers'):
+		for n in ('shaping', 'transcripts', 'models', 'ctc', 'decoders', 'transcript_generators', 'text_tokenizers', 'optimizers'):
 			_CACHE[n] = importlib.import_module(n)
 		try:  # the batch feed's collate_fn (datasets.py:305-332); pulls in text_processing / audio / utils
 			import warnings

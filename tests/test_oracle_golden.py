@@ -116,8 +116,6 @@ def test_oracle_against_live_reference():
 # ------------------------------------------------------------------------------------------ train mode
 def golden_state_dict(c):
 	sd = O.synth_state_dict(c['shapes'], seed = c['seed'])
-	if c['kwargs'].get('smooth'):
-		sd = O.smooth_regime(sd, seed = c['seed'])
 	assert abs(sum(float(v.double().abs().sum()) for v in sd.values() if v.is_floating_point()) - c['checksum']) < 1e-6 * c['checksum']
 	return sd
 
@@ -130,6 +128,8 @@ def oracle_train_step(c, **kw):
 	leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k and not is_frozen(k) else v.clone()) for k, v in sd.items()}
 	over = {k: v for k, v in c['kwargs'].items() if k in ('groups', )}
 	over['frozen_blocks'] = n_frozen
+	if 'nonlinearity' in c['kwargs']:
+		over['act'] = tuple(c['kwargs']['nonlinearity'])
 	stats = {}
 	logits, log_probs, olen = O.model_forward(leaf, c['signal'], c['xlen'], model = c['model'], training = True, stats_out = stats, **over, **kw)
 	C = c['num_classes']
@@ -171,8 +171,8 @@ def test_train_mode_oracle_matches_reference_golden(golden):
 		assert rel(logits, c['logits']) < 1e-4, (c['model'], rel(logits, c['logits']))
 		assert torch.allclose(loss, c['loss'], rtol = 1e-4, atol = 1e-4), c['model']
 		# a hardtanh / relu gate that flips between two fp32 implementations moves the gradient by O(1 / sqrt(elements)):
-		# the kinked full-depth cases are bounded loosely, the shallow and the smooth-regime ones tightly (O.smooth_regime)
-		deep_kinked = not c['kwargs'].get('smooth') and c['kwargs'].get('num_blocks', 5) > 1
+		# the kinked full-depth cases are bounded loosely, the shallow and the smooth ones tightly (O.SMOOTH_NONLINEARITY)
+		deep_kinked = 'nonlinearity' not in c['kwargs'] and c['kwargs'].get('num_blocks', 5) > 1
 		total, worst = check_grads_against_golden(grads, c['grads'], 5e-2 if deep_kinked else 1e-3, c['model'])
 		print(c['model'], c['kwargs'], 'oracle vs reference: total grad rel', total, 'worst tensor', worst)
 		sd0 = golden_state_dict(c)
