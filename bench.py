@@ -10,21 +10,27 @@ frontend -> instance norm -> 18 conv + batch-statistics BatchNorm + hardtanh + m
 dgrad and wgrad of every conv) -> clip_grad_norm(100) + SGD(momentum 0.9, weight decay 1e-3) update (the
 reference's train.py defaults, train.py:657-662,776-779) as one native multi-tensor step.  The whole step
 runs on this repo's kernels.  N > 1: data-parallel replicas; every layer's weight gradient is
-all-reduced (NCCL) from inside the native backward as soon as it exists, inside the same CUDA graph.
+all-reduced (NCCL) from inside the native backward as soon as it exists, inside the same CUDA graph; after the
+timed steps the replicas' parameters are compared bit for bit ("replicas_identical").
 
-Secondary workloads (reported under "also", selectable with --workload): the same training step on a
-RAGGED batch (xlen ~ U(0.5, 1], SURVEY.md 8d: masks exercised; tiles of pure padding are structural zeros
-and are left out of the GEMMs) and the inference path of the same shape -- eval-mode forward with folded
-BatchNorm (CUDA-graph replay) + CTC loss + CTC gradient.
+"also" (every N): the same training step on a RAGGED batch; the inference path of the same shape (eval forward with
+folded BatchNorm + greedy collapse + CTC loss + CTC gradient); BASELINE configs[4]: the utterance-sharded inference
+sweep, 8192 utterances x 10 s split over the ranks in micro-batches of 256 (no data-path collective).
+N = 1 only: BASELINE configs[0] (C1, with the reference's own CPU time beside it), configs[2] (C3), configs[3] (C4),
+each with its own roofline, and "gpu_baseline": the UNMODIFIED reference (baseline/_ref, cuDNN / ATen / cuFFT) running
+the headline training step on the same GPU.
 
 value  = whole-job audio-seconds / second with the PCM already resident in HBM (CUDA events).
 e2e    = same metric through the public module API with HOST buffers: pinned int16 PCM + targets
          -> H2D through convasr_b200.feed.DeviceFeeder (every step uploads its own batch; the copy of step
          i+1 overlaps the compute of step i), the step, D2H of the per-utterance loss (and the greedy
          ids for inference).
+kernels = per C-ABI entry point: launches, device ms per step (CUDA events around every call of one eager
+         step), algorithmic bytes / FLOPs and the fraction of the measured peak that bounds it.
 N > 1  = per-GPU batch fixed (weak scaling); time = max over ranks.
---impl reference = the CPU oracle port of the reference path (torch CPU ops, all host threads) on a
-         bounded sample of the same workload.
+--impl reference = the UNMODIFIED reference (baseline/_ref or /root/reference: models.py + torch CPU ops, all host
+         threads, its own train-loop body train.py:748-779) on a bounded sample of the same workload; when the
+         staged reference is absent, the oracle port (cpu_baseline.kind says which).
 """
 import argparse
 import json
@@ -49,12 +55,15 @@ WORKLOADS = {
 	'wav2letter_char_train_step_B80x15s_bf16_ragged': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'train', 'ragged'),
 	'wav2letter_char_fwd_ctc_B80x15s_bf16': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer', 'full'),
 	'wav2letter_char_fwd_ctc_B80x15s_bf16_ragged': ('Wav2Letter', 38, 80, 15.0, 'bf16', 'infer', 'ragged'),
-	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer', 'ragged'),
-	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer', 'full'),
-	'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16': ('Wav2Letter', 5000, 64, 15.0, 'bf16', 'infer', 'full'),
+	'wav2letter_char_fwd_ctc_B8x10s_fp32': ('Wav2Letter', 38, 8, 10.0, 'fp32', 'infer', 'ragged'),  # BASELINE configs[0] (C1)
+	'jasper_separable_fwd_ctc_B256x20s_bf16': ('JasperNetSeparable', 38, 256, 20.0, 'bf16', 'infer', 'full'),  # configs[2] (C3)
+	'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16': ('Wav2Letter', 5000, 64, 15.0, 'bf16', 'infer', 'full'),  # configs[3] (C4)
+	'wav2letter_char_infer_sweep_8192x10s_bf16': ('Wav2Letter', 38, 256, 10.0, 'bf16', 'sweep', 'ragged'),  # configs[4] (C5): batch = micro-batch
 }
+SWEEP_UTTERANCES = 8192
 DEFAULT_WORKLOAD = 'wav2letter_char_train_step_B80x15s_bf16'
-SECONDARY_WORKLOADS = ['wav2letter_char_train_step_B80x15s_bf16_ragged', 'wav2letter_char_fwd_ctc_B80x15s_bf16']
+SECONDARY_WORKLOADS = ['wav2letter_char_train_step_B80x15s_bf16_ragged', 'wav2letter_char_fwd_ctc_B80x15s_bf16', 'wav2letter_char_infer_sweep_8192x10s_bf16']
+SINGLE_GPU_WORKLOADS = ['wav2letter_char_fwd_ctc_B8x10s_fp32', 'jasper_separable_fwd_ctc_B256x20s_bf16', 'wav2letter_bpe5000_fwd_ctc_B64x15s_bf16']
 # mean DRAM bytes per launch of the tensor-pipe kernels, from the committed ncu --set full captures
 NCU_DRAM_BYTES_PER_LAUNCH = {
 	'wav2letter_char_train_step_B80x15s_bf16': 131.2e6,  # profiles/r01_train_step_tensor_kernels_ncu_full.csv (56 launches)
@@ -63,13 +72,15 @@ NCU_DRAM_BYTES_PER_LAUNCH = {
 }
 STEP_DESC = {
 	'train': 'frontend+instnorm+18x(conv, batch-stat BN, hardtanh, mask)+decoder/log_softmax+CTC loss+full backward (CTC grad, BN bwd, dgrad, wgrad)+clip_grad_norm+SGD(momentum,wd) update',
-	'infer': 'frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+CTC loss+CTC grad (no conv backward)',
+	'infer': 'frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+greedy CTC collapse+CTC loss+CTC grad (no conv backward)',
+	'sweep': f'{SWEEP_UTTERANCES} utterances sharded over the ranks, micro-batches of 256: frontend+instnorm+conv stack (BN folded)+decoder/log_softmax/argmax+greedy CTC collapse+CTC loss; one pass over the shard',
 }
 SAMPLE_RATE = 8000
 LENGTHS_DESC = {
 	'full': 'xlen = 1: every utterance fills its row (benchmark.py:126 style)',
 	'ragged': 'xlen ~ U(0.5, 1]: ~25 % of each row is padding; value counts PADDED seconds; tiles of pure padding are left out of the GEMMs (structural zeros, exact)',
 }
+FP32_FMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal: 148 SMs x 128 fp32 lanes x 2 FLOP x 1.965 GHz (no measured fp32 peak in MEASURED_PEAKS.json)
 
 
 def synth_batch(B, seconds, C, seed, lengths = 'ragged'):
@@ -102,22 +113,61 @@ def model_shapes(model_name, C):
 
 
 def conv_flops_per_step(model, B, F):
-	"""algorithmic 2*MAC of every conv (real channels, real frames, no padding), SURVEY.md 8(d)"""
+	"""algorithmic 2*MAC of every conv (real channels, real frames, no padding); (dense GEMM flops,
+	grouped-conv flops, output frames)"""
 	import torch.nn as nn
-	total = 0
+	dense, grouped = 0, 0
 	t = F
 	for block in model.backbone:
 		for seq in block.conv:
 			for conv in seq:
 				if isinstance(conv, nn.Conv1d):
 					t = (t + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) // conv.stride[0] + 1
-					total += 2 * B * t * conv.out_channels * (conv.in_channels // conv.groups) * conv.kernel_size[0]
+					fl = 2 * B * t * conv.out_channels * (conv.in_channels // conv.groups) * conv.kernel_size[0]
+					if conv.groups > 1:
+						grouped += fl
+					else:
+						dense += fl
 		for rc in block.conv_residual:
 			if isinstance(rc, nn.Conv1d):
-				total += 2 * B * t * rc.out_channels * rc.in_channels
+				dense += 2 * B * t * rc.out_channels * rc.in_channels
 	d = model.decoder[0]
-	total += 2 * B * t * d.out_channels * d.in_channels
-	return total, t
+	dense += 2 * B * t * d.out_channels * d.in_channels
+	return dense, grouped, t
+
+
+def algorithmic_bytes(model, B, T, t_out, C, kind, L):
+	"""algorithmic HBM bytes per step of the memory-bound entry points (SURVEY.md 8(d) per-unit figures x this batch)"""
+	import torch.nn as nn
+	F = T // 80 + 1
+	out = {
+		'cab_frontend_logmel': B * T * 2 + B * 64 * F * 4,  # int16 PCM in, fp32 log-mel out
+		'cab_instnorm_pack': B * 64 * F * 4 + B * (F + F % 2) * 64 * 2,  # fp32 log-mel in, bf16 channels-last out
+		'cab_ctc_loss_fwd': B * t_out * C * 4 + 2 * B * t_out * (2 * L + 1) * 4,  # log_probs read; alpha and beta written
+		'cab_ctc_loss_bwd': 2 * B * t_out * C * 4 + 2 * B * t_out * (2 * L + 1) * 4,  # log_probs read, grad written; alpha, beta read
+		'cab_greedy_collapse': B * t_out * 4 * 2,
+		'cab_log_softmax_argmax': B * t_out * C * 4 * 2,
+	}
+	if kind == 'train':
+		acts, t, params = 0, F, 0
+		for block in model.backbone:
+			for seq in block.conv:
+				conv = seq[0]
+				t = (t + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) // conv.stride[0] + 1
+				acts += B * t * ((conv.out_channels + 63) // 64 * 64) * 2
+				params += conv.weight.numel()
+		params += model.decoder[0].weight.numel()
+		n_all = sum(p.numel() for p in model.parameters() if p.requires_grad)
+		out.update({
+			'cab_bn_act_mask_fwd_stats': 2 * acts,  # y read, activation written
+			'cab_bn_act_mask_bwd': 5 * acts,  # reduce: y, g read; apply: y, g read, dy written
+			'cab_pack_weights_batched': params * (4 + 2 + 2),  # fp32 master read, forward + dgrad bf16 operands written
+			'cab_unpack_wgrad': params * 8,
+			'cab_optimizer_step': n_all * 20 + n_all * 4,  # p, g, m read + p, m written; g read once more for the norm
+			'cab_log_softmax_bwd': 3 * B * t_out * C * 4,
+			'cab_bct_to_btc': B * t_out * C * 4 + B * t_out * 64 * 2,
+		})
+	return out
 
 
 class ClockSampler:
@@ -166,83 +216,189 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (oracle/ is the checker AND the CPU baseline)
+# reference arms: the UNMODIFIED reference (baseline/_ref staged by __graft_entry__.build(), or /root/reference) through
+# its own public API; the oracle port only when neither exists
 # --------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind):
-	from oracle import oracle as O
+def reference_available():
+	from oracle import reference_shim
+	return reference_shim.available()
+
+
+def reference_model(model_name, C, device, seed_shapes_from = None):
+	"""the reference's own module tree with this bench's seeded weights"""
+	from oracle import oracle as O, reference_shim
+	model = reference_shim.make_model(model_name, (C, ), frontend = True)
+	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
+	model.load_state_dict(O.synth_state_dict(shapes, seed = 0), strict = False)
+	return model.to(device)
+
+
+def reference_step_fn(model, kind, C, tokenizer = None):
+	"""one step of the workload through the reference's public API: its train-loop body (train.py:748-779) or its
+	transcribe flow (forward + GreedyCTCGenerator.generate + loss)"""
+	from oracle import reference_shim
+	ref = reference_shim.load()
 	if kind == 'train':
-		leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
-		logits, log_probs, olen = O.model_forward(leaf, sig, xlen, model = model_name, training = True)
-		loss = O.ctc_loss_torch(log_probs[0].permute(2, 0, 1), y[:, 0], olen[0], ylen[:, 0], C - 1).mean()
-		loss.backward()  # backward through the whole stack, as train.py:770-774
+		model.train()
+		opt = torch.optim.SGD(model.parameters(), lr = 1e-6, momentum = 0.9, weight_decay = 1e-3)  # train.py:657-662 defaults
+
+		def step(sig, xlen, y, ylen):
+			out = model(sig, xlen, y = y, ylen = ylen)
+			loss = (out['loss'] * ylen[:, 0]).mean()  # train.py:754-755
+			loss.backward()
+			torch.nn.utils.clip_grad_norm_(model.parameters(), 100.0, error_if_nonfinite = False)  # train.py:776-779
+			opt.step()
+			opt.zero_grad()
+			return out['loss'].detach()
+		return step
+	model.eval()
+	model.fuse_conv_bn_eval()
+	gen = ref.transcript_generators.GreedyCTCGenerator()
+	tok = tokenizer or ref.text_tokenizers.CharTokenizerLegacy('абвгдеёжзийклмнопрстуфхцчшщъыьэюя')
+
+	def step(sig, xlen, y, ylen):
 		with torch.no_grad():
-			for k, v in leaf.items():
-				if v.is_floating_point() and v.grad is not None:
-					sd[k] = sd[k] - 1e-6 * v.grad  # plain SGD update
-		return loss
-	logits, log_probs, olen = O.model_forward(sd, sig, xlen, model = model_name)
-	lp = log_probs[0].permute(2, 0, 1).detach().requires_grad_(True)
-	loss = O.ctc_loss_torch(lp, y[:, 0], olen[0], ylen[:, 0], C - 1)
-	loss.sum().backward()  # CTC gradient w.r.t. the log-probs: the same work the native step does
-	return loss
+			out = model(sig, xlen, y = y, ylen = ylen)
+			if C == len(tok.idx2char):
+				gen.generate(tok, out['log_probs'][0], begin = torch.zeros(len(sig)), end = torch.ones(len(sig)), output_lengths = out['olen'][0])
+		return out['loss']
+	return step
 
 
-def run_cpu_baseline(model_name, C, seconds, sample_B, steps, warmup, kind, lengths = 'ragged'):
+def port_step_fn(model_name, C, kind):
+	"""fallback when the reference is not staged: the oracle port of the same step"""
 	from oracle import oracle as O
-	torch.set_num_threads(os.cpu_count())
 	shapes = {k: s for k, s in model_shapes(model_name, C).items() if not k.startswith('frontend.')}
 	sd = O.synth_state_dict(shapes, seed = 0)
+
+	def step(sig, xlen, y, ylen):
+		if kind == 'train':
+			leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in sd.items()}
+			logits, log_probs, olen = O.model_forward(leaf, sig, xlen, model = model_name, training = True)
+			loss = O.ctc_loss_torch(log_probs[0].permute(2, 0, 1), y[:, 0], olen[0], ylen[:, 0], C - 1).mean()
+			loss.backward()
+			with torch.no_grad():
+				for k, v in leaf.items():
+					if v.is_floating_point() and v.grad is not None:
+						sd[k] = sd[k] - 1e-6 * v.grad
+			return loss.detach()
+		logits, log_probs, olen = O.model_forward(sd, sig, xlen, model = model_name)
+		lp = log_probs[0].permute(2, 0, 1).detach().requires_grad_(True)
+		loss = O.ctc_loss_torch(lp, y[:, 0], olen[0], ylen[:, 0], C - 1)
+		loss.sum().backward()
+		return loss.detach()
+	return step
+
+
+def run_cpu_reference(name, sample_B, steps, warmup):
+	"""(value audio-s/s, s/step, cpu_baseline dict) of the reference's CPU path on a bounded sample of workload `name`"""
+	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[name]
+	kind = 'infer' if kind == 'sweep' else kind
+	torch.set_num_threads(os.cpu_count())
+	if reference_available():
+		step, src = reference_step_fn(reference_model(model_name, C, 'cpu'), kind, C), 'reference'
+		how = f'UNMODIFIED reference models.py / transcript_generators.py via oracle/reference_shim.py, torch {torch.__version__} CPU ops, fp32'
+	else:
+		step, src = port_step_fn(model_name, C, kind), 'port'
+		how = f'oracle port (reference tree not staged under baseline/_ref): torch {torch.__version__} CPU ops, fp32'
 	sig, xlen, y, ylen = synth_batch(sample_B, seconds, C, seed = 0, lengths = lengths)
 	for _ in range(warmup):
-		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind)
+		step(sig, xlen, y, ylen)
 	t0 = time.perf_counter()
 	for _ in range(steps):
-		cpu_reference_step(sd, model_name, sig, xlen, y, ylen, C, kind)
-	dt = time.perf_counter() - t0
-	return sample_B * seconds * steps / dt, dt / steps
+		step(sig, xlen, y, ylen)
+	dt = (time.perf_counter() - t0) / steps
+	value = sample_B * seconds / dt
+	return value, dt, dict(value = value, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = src, sample = f'{sample_B} x {seconds:g} s utterances per step ({kind} step of {name}), {steps} steps after {warmup} warm-up, {dt:.2f} s/step; {how}')
 
 
-def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline, full):
-	"""one workload on this rank's GPU; `full` adds roofline / e2e / clocks (primary line)"""
-	from convasr_b200 import _lib, models, ops
-	from oracle import oracle as O  # only for the seeded synthetic weights + the cpu_baseline leg
+def run_gpu_baseline(name, dev, steps = 8, warmup = 3):
+	"""the UNMODIFIED reference on the same GPU through stock PyTorch kernels (cuDNN convolutions, ATen BatchNorm / hardtanh /
+	ctc_loss, cuFFT frontend, torch.optim.SGD), eager, fp32 parameters with TF32 convolutions and under bf16 autocast --
+	benchmark.py:116-205 method (synchronize around the timed iterations).  Library kernels: context, not a bench value."""
+	if not reference_available():
+		return dict(unavailable = 'reference tree not staged under baseline/_ref')
 	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[name]
-	config = dict(workload = name, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
-				step = STEP_DESC[kind], parallelism = (f'data-parallel replicas x{world} (per-layer NCCL gradient all-reduce overlapped with the backward)' if kind == 'train' else f'utterance-sharded replicas x{world}'),
-				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
-	cpu_baseline = None
-	if with_cpu_baseline:
-		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
-		v, sec = run_cpu_baseline(model_name, C, seconds, sB, 3, 1, kind, lengths)
-		cpu_baseline = dict(value = v, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, 3 steps after 1 warm-up ({sec:.2f} s/step; oracle port: torch {torch.__version__} CPU ops, {kind} step)')
+	out = dict(what = f'unmodified reference ({model_name}) on {torch.cuda.get_device_name(dev)}: stock PyTorch {torch.__version__} CUDA kernels, eager, {kind} step, batch {B} x {seconds:g} s', unit = 'audio-s/s')
+	sig, xlen, y, ylen = [t.to(dev) for t in synth_batch(B, seconds, C, seed = 1000, lengths = lengths)]
+	sig = sig.float()  # the reference casts int16 itself, but its torch.stft path wants a float signal on CUDA
+	torch.backends.cudnn.benchmark = True
+	for label, autocast in (('fp32_tf32_convs', False), ('bf16_autocast', True)):
+		try:
+			step = reference_step_fn(reference_model(model_name, C, dev), kind, C)
 
+			def run():
+				with torch.autocast('cuda', dtype = torch.bfloat16, enabled = autocast):
+					return step(sig, xlen, y, ylen)
+			for _ in range(warmup):
+				run()
+			torch.cuda.synchronize()
+			t0 = time.perf_counter()
+			for _ in range(steps):
+				run()
+			torch.cuda.synchronize()
+			dt = (time.perf_counter() - t0) / steps
+			out[label] = dict(value = B * seconds / dt, ms_per_step = dt * 1e3)
+		except Exception as e:
+			out[label] = dict(error = repr(e)[:300])
+		torch.cuda.empty_cache()
+	return out
+
+
+# --------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------
+def measure(name, args, rank, world, local_rank, dev, steps, warmup, level):
+	"""one workload on this rank's GPU.  level: 'full' (primary line: + e2e, cpu_baseline, clocks), 'roofline' (value +
+	roofline + kernel table), 'light' (value only)"""
+	from convasr_b200 import _lib, models, ops
+	from oracle import oracle as O  # only for the seeded synthetic weights (outside every timed region)
+	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[name]
+	sweep = kind == 'sweep'
+	config = dict(workload = name, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = precision, kind = kind,
+				step = STEP_DESC[kind], parallelism = (f'data-parallel replicas x{world} (per-layer NCCL gradient all-reduce overlapped with the backward)' if kind == 'train' else f'utterance-sharded replicas x{world} (no data-path collective)'),
+				l2 = 'flushed between timed steps (256 MiB memset)', cuda_graphs = not args.no_cuda_graphs)
 	frontend = models.LogFilterBankFrontend(64, SAMPLE_RATE, .02, .01, 'hann_window')
 	model = getattr(models, model_name)(64, [C], frontend = frontend, dropout = 0., check_time_dim_padded = False)
 	shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith('frontend.')}
 	model.load_state_dict(O.synth_state_dict(shapes, seed = 0), strict = False)
-	model = model.to(dev)
+	model = model.to(dev).set_precision(precision)
 	sig, xlen, y, ylen = synth_batch(B, seconds, C, seed = 1000 + rank, lengths = lengths)
 	sig_pin, xlen_pin, y_pin, ylen_pin = [t.pin_memory() for t in (sig, xlen, y, ylen)]
 	sig_d, xlen_d, y_d, ylen_d = [t.to(dev) for t in (sig, xlen, y, ylen)]
 	flush = torch.empty(256 << 20, dtype = torch.uint8, device = dev)
-	# e2e leg: the public batch feed (convasr_b200/feed.py) -- every step uploads its own pinned host batch; the copy of
-	# step i+1 is issued on a copy stream while step i computes (the timed region still contains one full H2D per step)
 	from convasr_b200 import feed as feed_mod
-	feeder = iter(feed_mod.DeviceFeeder(((None, None, sig_pin, xlen_pin, y_pin, ylen_pin) for _ in range(steps + 16)), dev))
 	Fr = sig.shape[1] // 80 + 1
-	flops_fwd, t_out = conv_flops_per_step(model, B, Fr)
+	flops_fwd, flops_grouped, t_out = conv_flops_per_step(model, B, Fr)
 	first = model.backbone[0].conv[0][0]
 	flops_first = 2 * B * ((Fr + 2 * first.padding[0] - first.kernel_size[0]) // first.stride[0] + 1) * first.out_channels * first.in_channels * first.kernel_size[0]
+	# greedy CTC collapse tables (transcript_generators.py:8-93): blank = last class, the class before it plays the space
+	sil = torch.zeros(C, dtype = torch.uint8, device = dev)
+	sil[C - 1] = sil[C - 2] = 1
+	ws = torch.zeros(C, dtype = torch.uint8, device = dev)
+	ws[C - 2] = 1
+	replicas = None
+
+	def infer_once(s, xl, yy, yl, want_grad):
+		"""eval forward (loss included through the public API) + device part of GreedyCTCGenerator + optionally the CTC gradient"""
+		with torch.no_grad():
+			out = model(s, xl)
+		lp = out['log_probs'][0]
+		tok, frm, cnt = ops.greedy_collapse(lp._convasr_argmax, out['olen'][0], C, C - 1, C - 2, sil, ws, 10)
+		lp = lp.requires_grad_(want_grad)
+		nll = ops.ctc_loss(lp.permute(2, 0, 1), yy[:, 0], out['olen'][0], yl[:, 0], blank = C - 1)
+		if want_grad:
+			nll.sum().backward()  # grad w.r.t. the log-probs/logits only: CTC alpha || beta -> gradient scatter
+		return nll, tok, cnt
 
 	if kind == 'train':
-		from convasr_b200 import training
+		from convasr_b200 import optimizers, training
 		model.train()
-		assert training.supported(model), 'native training path does not cover this topology'
+		assert training.unsupported_reason(model) is None, training.unsupported_reason(model)
 		net = model
 		if world > 1:
-			net, _ = models.distributed_data_parallel_and_autocast(model, local_rank)
+			net, _ = models.distributed_data_parallel_and_autocast(model, local_rank, opt_level = 'O2' if precision == 'bf16' else None)
 		# train.py defaults: SGD(momentum 0.9, weight_decay 1e-3) after clip_grad_norm_(max_norm 100) (train.py:657-662,776-779)
-		from convasr_b200 import optimizers
 		train_params = [p for p in model.parameters() if p.requires_grad]
 		optimizer = optimizers.SGD(train_params, lr = 1e-6, momentum = 0.9, weight_decay = 1e-3)  # native multi-tensor step
 		flops = 3 * flops_fwd - flops_first  # forward + dgrad (all but the first layer) + wgrad
@@ -260,35 +416,63 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 		def step_device():
 			return run[0](sig_d, xlen_d, y_d, ylen_d)
 
-		def step_e2e():
-			_, _, s, xl, yy, yl = next(feeder)  # this step's H2D was issued on the copy stream during the previous step
-			per_utt = run[0](s, xl, yy, yl)
-			return per_utt.detach().cpu()
+		def step_e2e(batch):
+			_, _, s, xl, yy, yl = batch  # this step's H2D was issued on the copy stream during the previous step
+			return run[0](s, xl, yy, yl).detach().cpu()
 
 		d2h = B * 4
-		traced_names = ['conv1d_fused', 'conv1d_wgrad']
+		tensor_entries = ['cab_conv1d_fused', 'cab_conv1d_wgrad']
 		kernel_label = 'conv1d_umma_kernel (forward + dgrad) + wgrad_umma_kernel'
-	else:
-		model.eval().set_precision(precision)
+		audio_per_step = B * seconds
+	elif kind == 'infer':
+		model.eval()
 		flops = flops_fwd
 
 		def step_device():
-			# grad w.r.t. the log-probs/logits only: CTC alpha || beta -> gradient scatter
-			with torch.no_grad():
-				out = model(sig_d, xlen_d)
-			lp = out['log_probs'][0].requires_grad_(True)
-			nll = ops.ctc_loss(lp.permute(2, 0, 1), y_d[:, 0], out['olen'][0], ylen_d[:, 0], blank = C - 1)
-			nll.sum().backward()
+			return infer_once(sig_d, xlen_d, y_d, ylen_d, True)[0]
+
+		def step_e2e(batch):
+			_, _, s, xl, yy, yl = batch
+			out = model(s, xl, y = yy, ylen = yl)
+			tok, frm, cnt = ops.greedy_collapse(out['log_probs'][0]._convasr_argmax, out['olen'][0], C, C - 1, C - 2, sil, ws, 10)
+			return out['loss'].cpu(), tok.cpu(), cnt.cpu()
+
+		d2h = B * 4 + B * t_out * 4 + B * 4
+		tensor_entries = ['cab_conv1d_fused']
+		kernel_label = 'conv1d_umma_kernel'
+		audio_per_step = B * seconds
+	else:  # sweep: this rank's shard of SWEEP_UTTERANCES, resident in HBM, one pass in micro-batches of B
+		model.eval()
+		lo, hi = (SWEEP_UTTERANCES * rank) // world, (SWEEP_UTTERANCES * (rank + 1)) // world
+		n_local = hi - lo
+		T = sig.shape[1]
+		g = torch.Generator(device = dev).manual_seed(2000 + rank)
+		shard = (torch.randn(n_local, T, generator = g, device = dev) * 3000).round().clamp(-32767, 32767).to(torch.int16)
+		shard_xlen = torch.rand(n_local, generator = g, device = dev) * 0.5 + 0.5
+		L = y.shape[2]
+		shard_y = torch.randint(0, C - 1, (n_local, 1, L), generator = g, device = dev)
+		shard_ylen = torch.randint(max(1, L // 3), L + 1, (n_local, 1), generator = g, device = dev)
+		flops = flops_fwd * n_local / B
+
+		def step_device():
+			nll = None
+			for a in range(0, n_local, B):
+				nll = infer_once(shard[a:a + B], shard_xlen[a:a + B], shard_y[a:a + B], shard_ylen[a:a + B], False)[0]
 			return nll
 
-		def step_e2e():
-			_, _, s, xl, yy, yl = next(feeder)
-			out = model(s, xl, y = yy, ylen = yl)
-			return out['loss'].cpu(), out['log_probs'][0]._convasr_argmax.cpu()
+		def step_e2e(batches):
+			res = []
+			for _, _, s, xl, yy, yl in batches:
+				out = model(s, xl, y = yy, ylen = yl)
+				tok, frm, cnt = ops.greedy_collapse(out['log_probs'][0]._convasr_argmax, out['olen'][0], C, C - 1, C - 2, sil, ws, 10)
+				res.append((out['loss'].cpu(), cnt.cpu()))
+			return res
 
-		d2h = B * 4 + B * t_out * 4
-		traced_names = ['conv1d_fused']
+		d2h = n_local * 8
+		tensor_entries = ['cab_conv1d_fused']
 		kernel_label = 'conv1d_umma_kernel'
+		audio_per_step = n_local * seconds
+		steps, warmup = max(1, min(steps, 2)), 1
 
 	def barrier():
 		if world > 1:
@@ -314,8 +498,47 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	step_device()
 	torch.cuda.synchronize()
 	launches_per_step = _lib.launch_count() - l0
-	if config['cuda_graphs'] and kind == 'infer':
-		model.enable_cuda_graphs(True)  # forward = one graph replay; CTC loss/grad stay eager launches
+	kernels, roofline = None, None
+	if level in ('full', 'roofline') and not sweep:
+		# per entry point: CUDA events around every C-ABI call of eager steps, on the launching stream
+		n_prof = min(steps, 3)
+		with _lib.trace() as tr:
+			for _ in range(n_prof):
+				flush.zero_()
+				step_device()
+		summary = tr.summary()
+		peaks = measured_peaks()
+		hbm_peak = peaks['hbm_gbs'] if peaks else 6550.0
+		tf_peak = peaks['bf16_tflops_sustained'] if peaks else 1590.0
+		abytes = algorithmic_bytes(model, B, sig.shape[1], t_out, C, kind, y.shape[2])
+		kernels = []
+		for entry, (calls, ms_total) in sorted(summary.items(), key = lambda kv: -kv[1][1]):
+			ms_step = ms_total / n_prof
+			row = dict(entry = entry, launches_per_step = calls // n_prof, ms_per_step = ms_step)
+			if entry in tensor_entries:
+				row.update(bound = 'tensor')
+			elif entry == 'cab_grouped_conv1d':
+				ach = flops_grouped / (ms_step / 1e3) / 1e12
+				row.update(bound = 'fp32 fma (nominal peak, no measured figure)', achieved = ach, peak = FP32_FMA_PEAK_TFLOPS, unit = 'TFLOP/s', frac = ach / FP32_FMA_PEAK_TFLOPS)
+			elif entry in abytes and ms_step > 0:
+				ach = abytes[entry] / (ms_step / 1e3) / 1e9
+				row.update(bound = 'hbm', algorithmic_bytes = abytes[entry], achieved = ach, peak = hbm_peak, unit = 'GB/s', frac = ach / hbm_peak)
+			kernels.append(row)
+		kern_ms = sum(summary[e][1] for e in tensor_entries if e in summary) / n_prof
+		n_kern = sum(summary[e][0] for e in tensor_entries if e in summary) // n_prof
+		achieved = flops / (kern_ms / 1e3) / 1e12
+		for row in kernels:
+			if row.get('bound') == 'tensor':
+				row.update(note = 'see roofline: all launches of the tensor-pipe entry points together')
+		roofline = dict(
+			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = tf_peak, unit = 'TFLOP/s', frac = achieved / tf_peak,
+			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
+			peak_burst = peaks['bf16_tflops'] if peaks else None, frac_of_burst = (achieved / peaks['bf16_tflops']) if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name),
+			traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed' if name in NCU_DRAM_BYTES_PER_LAUNCH else None,
+			launches_per_step = n_kern, kernel_ms_per_step = kern_ms, algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1
+		)
+	if config['cuda_graphs'] and kind != 'train':
+		model.enable_cuda_graphs(True)  # forward = one graph replay; greedy collapse / CTC loss / grad stay eager launches
 	if config['cuda_graphs'] and kind == 'train':
 		try:
 			run[0] = training.GraphedTrainStep(net, optimizer, sig_d, xlen_d, y_d, ylen_d, max_grad_norm = 100.0)  # whole step = one replay
@@ -337,60 +560,44 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, with_cpu_ba
 	barrier()
 	t_wall1 = time.time()
 	clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-	result = dict(ms = ms, ms_e2e = None)
-	roofline = None
-	if full:
-		# dominant (tensor-pipe) kernels: per-launch CUDA events on the launching stream
-		events = []
-		originals = {n: getattr(ops, n) for n in traced_names}
+	result = dict(ms = ms, ms_e2e = None, steps = steps)
+	if roofline is not None:
+		roofline['share_of_step'] = roofline['kernel_ms_per_step'] / (ms / steps)
+	if kind == 'train' and world > 1:
+		# data-parallel correctness, visible to the driver: after the timed steps every replica must hold bit-identical parameters
+		import torch.distributed as dist
+		flat = torch.cat([p.detach().flatten() for p in model.parameters() if p.requires_grad])
+		digest = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat.view(torch.int32).long().sum().double()])
+		every = [torch.empty_like(digest) for _ in range(world)]
+		dist.all_gather(every, digest)
+		gnorm = optimizer.total_grad_norm.clone() if optimizer.total_grad_norm is not None else torch.zeros(1, device = dev)
+		norms = [torch.empty_like(gnorm) for _ in range(world)]
+		dist.all_gather(norms, gnorm)
+		replicas = dict(identical = all(torch.equal(every[0], e) for e in every[1:]), param_checksum = float(every[0][1]), grad_norm_per_rank = [float(n) for n in norms], grad_norms_identical = all(torch.equal(norms[0], n) for n in norms[1:]))
+		assert replicas['identical'], f'data-parallel replicas diverged: {[e.tolist() for e in every]}'
+	if level == 'full' or (sweep and level != 'light'):
+		# end to end through the public API with host buffers (convasr_b200/feed.py): every step uploads its own pinned host
+		# batch; the copy of step i+1 is issued on a copy stream while step i computes (the timed region contains one full H2D per step)
+		if sweep:
+			host = [t.cpu().pin_memory() for t in (shard, shard_xlen, shard_y, shard_ylen)]
 
-		def make_traced(fn):
-			def traced(*a, **k):
-				e0, e1 = torch.cuda.Event(enable_timing = True), torch.cuda.Event(enable_timing = True)
-				e0.record()
-				r = fn(*a, **k)
-				e1.record()
-				events.append((e0, e1))
-				return r
-			return traced
-
-		for n_, fn in originals.items():
-			setattr(ops, n_, make_traced(fn))
-		model.enable_cuda_graphs(False)  # per-launch events need the eager launch path
-		graphed = run[0] if kind == 'train' else None
-		if kind == 'train':
-			run[0] = run_eager
-		n_prof = min(steps, 5)
-		for _ in range(n_prof):
-			flush.zero_()
-			step_device()
-		torch.cuda.synchronize()
-		for n_, fn in originals.items():
-			setattr(ops, n_, fn)
-		if config['cuda_graphs'] and kind == 'infer':
-			model.enable_cuda_graphs(True)
-		if kind == 'train':
-			run[0] = graphed
-		kern_ms = sum(a.elapsed_time(b) for a, b in events) / n_prof
-		n_kern = len(events) // n_prof
-		# end to end through the public API with host buffers
-		for _ in range(3):
-			step_e2e()
+			def batches():
+				return feed_mod.DeviceFeeder(((None, None) + tuple(t[a:a + B] for t in host) for a in range(0, n_local, B)), dev)
+			step_e2e(batches())
+			barrier()
+			result['ms_e2e'] = timed(lambda: step_e2e(batches()), steps)
+			h2d = sum(t.numel() * t.element_size() for t in host)
+		else:
+			feeder = iter(feed_mod.DeviceFeeder(((None, None, sig_pin, xlen_pin, y_pin, ylen_pin) for _ in range(steps + 8)), dev))
+			for _ in range(3):
+				step_e2e(next(feeder))
+			barrier()
+			result['ms_e2e'] = timed(lambda: step_e2e(next(feeder)), steps)
+			h2d = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen))
 		barrier()
-		result['ms_e2e'] = timed(step_e2e, steps)
-		barrier()
-		peaks = measured_peaks()
-		peak = peaks['bf16_tflops_sustained'] if peaks else 1590.0
-		achieved = flops / (kern_ms / 1e3) / 1e12
-		roofline = dict(
-			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = peak, unit = 'TFLOP/s', frac = achieved / peak,
-			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
-			peak_burst = peaks['bf16_tflops'] if peaks else None, frac_of_burst = (achieved / peaks['bf16_tflops']) if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name), traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed',
-			launches_per_step = n_kern, kernel_ms_per_step = kern_ms,
-			algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1, share_of_step = kern_ms / (ms / steps)
-		)
-	result.update(valid_fraction = float(xlen.mean()), config = config, cpu_baseline = cpu_baseline, clocks = clocks, roofline = roofline, launches = launches_per_step * steps, B = B, seconds = seconds, precision = precision,
-					h2d = sum(t.numel() * t.element_size() for t in (sig, xlen, y, ylen)), d2h = d2h)
+		result['h2d'] = h2d
+	result.update(valid_fraction = float(xlen.mean()), config = config, clocks = clocks, roofline = roofline, kernels = kernels, launches = launches_per_step * steps, audio_per_step = audio_per_step,
+					precision = precision, d2h = d2h, replicas = replicas, kind = kind)
 	del model, flush
 	torch.cuda.empty_cache()
 	return result
@@ -405,7 +612,8 @@ def main():
 	ap.add_argument('--workload', default = DEFAULT_WORKLOAD, choices = sorted(WORKLOADS))
 	ap.add_argument('--no-cpu-baseline', action = 'store_true')
 	ap.add_argument('--no-secondary', action = 'store_true')
-	ap.add_argument('--cpu-sample-batch', type = int, default = 8)
+	ap.add_argument('--no-gpu-baseline', action = 'store_true')
+	ap.add_argument('--cpu-sample-batch', type = int, default = 4)
 	ap.add_argument('--no-cuda-graphs', action = 'store_true')
 	args = ap.parse_args()
 	model_name, C, B, seconds, precision, kind, lengths = WORKLOADS[args.workload]
@@ -417,14 +625,13 @@ def main():
 	if args.impl == 'reference':
 		if rank != 0:
 			return
-		sB = args.cpu_sample_batch if kind == 'infer' else max(2, args.cpu_sample_batch // 2)
 		n_steps = max(1, min(steps, 3))
-		value, sec = run_cpu_baseline(model_name, C, seconds, sB, n_steps, 1, kind, lengths)
-		config = dict(workload = args.workload, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE, precision = 'fp32', kind = kind, step = STEP_DESC[kind])
+		value, sec, cpu = run_cpu_reference(args.workload, args.cpu_sample_batch, n_steps, 1)
+		config = dict(workload = args.workload, lengths = LENGTHS_DESC[lengths], model = model_name, num_classes = C, batch_per_gpu = args.cpu_sample_batch, native_arm_batch_per_gpu = B, seconds_per_utterance = seconds, sample_rate = SAMPLE_RATE,
+						precision = 'fp32', kind = kind, step = STEP_DESC[kind], sample = cpu['sample'])
 		line = dict(
 			impl = 'reference', metric = 'audio_seconds_per_second', value = value, unit = 'audio-s/s', n_gpus = args.gpus, steps = n_steps, warmup = 1, ms_per_step = sec * 1e3,
-			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config,
-			cpu_baseline = dict(value = value, unit = 'audio-s/s', cores = torch.get_num_threads(), kind = 'port', sample = f'{sB} x {seconds:g} s utterances per step, {n_steps} steps (oracle port: torch {torch.__version__} CPU ops, {kind} step)'),
+			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'fp32', data = 'synthetic', config = config, cpu_baseline = cpu,
 			e2e = dict(value = value, unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0), gpu_launches = 0
 		)
 		print(json.dumps(line))
@@ -441,28 +648,45 @@ def main():
 	def reduce_max(vals):
 		if world == 1:
 			return vals
-		t = torch.tensor(vals, device = dev, dtype = torch.float64)
+		t = torch.tensor([v if v is not None else 0.0 for v in vals], device = dev, dtype = torch.float64)
 		torch.distributed.all_reduce(t, op = torch.distributed.ReduceOp.MAX)
 		return t.tolist()
 
-	r = measure(args.workload, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = rank == 0 and world == 1 and not args.no_cpu_baseline, full = True)
+	cpu_baseline = None
+	if rank == 0 and world == 1 and not args.no_cpu_baseline:
+		_, _, cpu_baseline = run_cpu_reference(args.workload, args.cpu_sample_batch, 3, 1)
+	r = measure(args.workload, args, rank, world, local_rank, dev, steps, warmup, 'full')
 	ms, ms_e2e = reduce_max([r['ms'], r['ms_e2e']])
 	also = None
-	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD and world == 1:  # the scaling runs (N > 1) measure the headline workload only
+	if not args.no_secondary and args.workload == DEFAULT_WORKLOAD:
 		also = {}
-		for name2 in SECONDARY_WORKLOADS:
-			r2 = measure(name2, args, rank, world, local_rank, dev, steps, warmup, with_cpu_baseline = False, full = False)
-			ms2, = reduce_max([r2['ms']])
-			also[name2] = dict(value = r2['B'] * r2['seconds'] * world * steps / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / steps, lengths = r2['config']['lengths'], valid_audio_fraction = r2['valid_fraction'], step = r2['config']['step'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'], clocks = r2['clocks'])
+		names = SECONDARY_WORKLOADS + (SINGLE_GPU_WORKLOADS if world == 1 else [])
+		for name2 in names:
+			level = 'roofline' if (world == 1 or WORKLOADS[name2][5] == 'sweep') else 'light'
+			r2 = measure(name2, args, rank, world, local_rank, dev, steps, warmup, level)
+			ms2, ms2_e2e = reduce_max([r2['ms'], r2['ms_e2e']])
+			entry = dict(value = r2['audio_per_step'] * world * r2['steps'] / (ms2 / 1e3), unit = 'audio-s/s', ms_per_step = ms2 / r2['steps'], steps = r2['steps'], lengths = r2['config']['lengths'], valid_audio_fraction = r2['valid_fraction'],
+						step = r2['config']['step'], precision = r2['precision'], cuda_graphs = r2['config']['cuda_graphs'], gpu_launches = r2['launches'], clocks = r2['clocks'], roofline = r2['roofline'], kernels = r2['kernels'])
+			if r2['ms_e2e'] is not None:
+				entry['e2e'] = dict(value = r2['audio_per_step'] * world * r2['steps'] / (ms2_e2e / 1e3), unit = 'audio-s/s', ms_per_step = ms2_e2e / r2['steps'], h2d_bytes_per_step = r2.get('h2d'), d2h_bytes_per_step = r2['d2h'])
+			if name2 == 'wav2letter_char_fwd_ctc_B8x10s_fp32' and rank == 0 and not args.no_cpu_baseline:
+				# config C1 forward + greedy decode is the reference's own CPU-runnable case
+				_, _, entry['cpu_baseline'] = run_cpu_reference(name2, 8, 3, 1)
+			also[name2] = entry
+		if world == 1 and not args.no_gpu_baseline:
+			also['gpu_baseline'] = run_gpu_baseline(args.workload, dev)
 	if rank == 0:
-		audio_s = r['B'] * r['seconds'] * world
+		audio_s = r['audio_per_step'] * world
 		line = dict(
-			metric = 'audio_seconds_per_second', value = audio_s * steps / (ms / 1e3), unit = 'audio-s/s', n_gpus = world, steps = steps, warmup = warmup, ms_per_step = ms / steps,
+			metric = 'audio_seconds_per_second', value = audio_s * r['steps'] / (ms / 1e3), unit = 'audio-s/s', n_gpus = world, steps = r['steps'], warmup = warmup, ms_per_step = ms / r['steps'],
 			higher_is_better = True, scaling = 'weak', vs_baseline = None, dtype = 'bf16' if r['precision'] == 'bf16' else 'bf16x3 (split-bf16, fp32 accumulate)', data = 'synthetic',
 			config = r['config'],
-			e2e = dict(value = audio_s * steps / (ms_e2e / 1e3), unit = 'audio-s/s', ms_per_step = ms_e2e / steps, h2d_bytes_per_step = r['h2d'], d2h_bytes_per_step = r['d2h']),
-			gpu_launches = r['launches'], roofline = r['roofline'], cpu_baseline = r['cpu_baseline'], clocks = r['clocks'], also = also
+			e2e = dict(value = audio_s * r['steps'] / (ms_e2e / 1e3), unit = 'audio-s/s', ms_per_step = ms_e2e / r['steps'], h2d_bytes_per_step = r.get('h2d'), d2h_bytes_per_step = r['d2h']),
+			gpu_launches = r['launches'], roofline = r['roofline'], kernels = r['kernels'], cpu_baseline = cpu_baseline, clocks = r['clocks'], also = also
 		)
+		if r['replicas'] is not None:
+			line['replicas_identical'] = r['replicas']['identical']
+			line['replicas'] = r['replicas']
 		print(json.dumps(line))
 	if world > 1:
 		torch.distributed.destroy_process_group()

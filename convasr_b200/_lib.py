@@ -43,7 +43,7 @@ class BnBranch(ctypes.Structure):
 
 
 ACT_NONE, ACT_RELU, ACT_HARDTANH, ACT_LEAKY_RELU = 0, 1, 2, 3
-EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32 = 0, 1, 2
+EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32, EPI_LOGITS_ROWS = 0, 1, 2, 3
 MAX_CONV_SOURCES = 18
 MAX_BN_BRANCHES = 12
 PACK_MAX_ITEMS = 32
@@ -85,6 +85,7 @@ SIGNATURES = {
 								c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i64, c_void_p],
 	'cab_log_softmax_argmax': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 	'cab_log_softmax_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+	'cab_log_softmax_rows': [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p],
 	'cab_ctc_loss_fwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
 						c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
 	'cab_ctc_loss_bwd': [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -67,6 +67,10 @@ struct alignas(64) ConvParams {
     float* log_probs;
     int* argmax;
     float* stats;  // [2][C_out] per-channel sum / sum of squares of the bf16 outputs, or null
+    // CAB_EPI_LOGITS_ROWS: fp32 logits in class-contiguous memory [B, T_out, logits_ld] through omap_hi (box {32 fp32, 128 rows}),
+    // per-row log-sum-exp and argmax from an online softmax across the N tiles of an M tile (M-tile-major schedule)
+    float* lse;
+    int mtile_major;
     // rows t >= ceil(skip_frac[b] * skip_T) + skip_margin of utterance b are structural zeros (padding of a
     // ragged batch): M tiles that lie entirely there are not computed, the epilogue stores zeros
     const float* skip_frac;
@@ -80,6 +84,19 @@ __device__ __forceinline__ int live_mtiles(const ConvParams& p, int b) {
     if (p.skip_frac == nullptr) return p.mtiles_per_b;
     const int rows = min(p.T_out, frac_len(__ldg(p.skip_frac + b), p.skip_T) + p.skip_margin);
     return rows <= 0 ? 0 : (rows + 127) / 128;
+}
+// tile sequence of one CTA.  Default: tile = blockIdx.x + i * gridDim.x with the N tile fastest (neighbouring CTAs share the
+// A tile in L2).  mtile_major: the CTA owns compacted M tile blockIdx.x + j * gridDim.x and walks ALL of its N tiles in order
+// (the online softmax of the large-vocabulary head needs every class of a row in one CTA).
+__device__ __forceinline__ void tile_at(const ConvParams& p, int i, int& am, int& nt) {
+    if (p.mtile_major) {
+        am = blockIdx.x + (i / p.n_ntiles) * gridDim.x;
+        nt = i % p.n_ntiles;
+    } else {
+        const int tile = blockIdx.x + i * gridDim.x;
+        nt = tile % p.n_ntiles;
+        am = tile / p.n_ntiles;
+    }
 }
 struct TileCursor {
     int b, base, end;
@@ -193,6 +210,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             tma_prefetch_desc(&p.amap[s]);
             tma_prefetch_desc(&p.wmap[s]);
         }
+        if (p.epilogue == CAB_EPI_LOGITS_ROWS) tma_prefetch_desc(&p.omap_hi);
         if (p.epilogue == CAB_EPI_ACT_BF16) {
             tma_prefetch_desc(&p.omap_hi);
             if (p.out_lo != nullptr) tma_prefetch_desc(&p.omap_lo);
@@ -228,9 +246,9 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t phase = 0;
             TileCursor cur;
             cur.init(p);
-            for (int tile = blockIdx.x;; tile += gridDim.x) {
-                const int nt = tile % p.n_ntiles;
-                const int am = tile / p.n_ntiles;
+            for (int it = 0;; ++it) {
+                int am, nt;
+                tile_at(p, it, am, nt);
                 if (!cur.seek(p, am)) break;
                 const int b = cur.b;
                 const int t0 = (am - cur.base) * kBlockM;
@@ -264,8 +282,10 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t acc_phase = 0;
             TileCursor cur;
             cur.init(p);
-            for (int tile = blockIdx.x;; tile += gridDim.x) {
-                if (!cur.seek(p, tile / p.n_ntiles)) break;
+            for (int it = 0;; ++it) {
+                int am_, nt_;
+                tile_at(p, it, am_, nt_);
+                if (!cur.seek(p, am_)) break;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
@@ -302,9 +322,11 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         uint32_t epi_chunks = 0;
         TileCursor cur;
         cur.init(p);
-        for (int tile = blockIdx.x;; tile += gridDim.x) {
-            const int nt = tile % p.n_ntiles;
-            const int am = tile / p.n_ntiles;
+        float run_m = -INFINITY, run_s = 0.f;  // CAB_EPI_LOGITS_ROWS: online softmax of this thread's row across N tiles
+        int run_i = 0;
+        for (int it = 0;; ++it) {
+            int am, nt;
+            tile_at(p, it, am, nt);
             if (!cur.seek(p, am)) break;
             const int b = cur.b;
             const int t0 = (am - cur.base) * kBlockM;
@@ -316,7 +338,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             if (p.epilogue != CAB_EPI_ACT_BF16) {
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
-            }
+            }  // (CAB_EPI_LOGITS_ROWS stages its bias after this wait: one barrier pair per tile, negligible next to 8 TMA stores)
 
             if (p.epilogue == CAB_EPI_ACT_BF16) {
                 int len = p.T_out;
@@ -403,6 +425,69 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                         bulk_commit();
                     }
                     ++epi_chunks;
+                }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+                continue;
+            } else if (p.epilogue == CAB_EPI_LOGITS_ROWS) {
+                // fp32 logits, class-contiguous rows: 32-column chunks staged in smem (128-byte rows, 128B swizzle) and written
+                // with TMA stores; running (max, sum exp, argmax) per row across the N tiles of this M tile
+                const int et = threadIdx.x - 128;
+                const int C = p.C_out;
+                epi_bar(1);
+                for (int i = et; i < block_n; i += 128) {
+                    const int n = n0 + i;
+                    s_bias[i] = (p.bias != nullptr && n < C) ? __ldg(p.bias + n) : 0.f;
+                }
+                epi_bar(1);
+                if (nt == 0) { run_m = -INFINITY; run_s = 0.f; run_i = 0; }
+                uint8_t* stage = smem + kOffStageOut;  // two 16 KB buffers
+                for (int c0 = 0; c0 < block_n; c0 += 32) {
+                    if (n0 + c0 >= C) break;  // uniform
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= block_n || n0 + c0 + 32 >= C) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    float x[32];
+                    float cm = -INFINITY;
+                    int ci = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
+                        const bool in = n0 + c0 + j < C;
+                        if (in && x[j] > cm) { cm = x[j]; ci = n0 + c0 + j; }
+                    }
+                    if (cm > run_m) {  // strict: ties keep the lowest class id (classes are visited in increasing order)
+                        run_s *= __expf(run_m - cm);
+                        run_m = cm;
+                        run_i = ci;
+                    }
+                    float cs = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) cs += (n0 + c0 + j < C) ? __expf(x[j] - run_m) : 0.f;
+                    run_s += cs;
+                    const int buf = epi_chunks & 1;
+                    uint8_t* st = stage + buf * (2 * kEpiTileBytes);
+                    if (et == 0) bulk_wait_read<1>();
+                    epi_bar(2);
+                    // 128-byte rows, 16-byte chunk index XOR (row & 7) == CU_TENSOR_MAP_SWIZZLE_128B
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4)
+                        *reinterpret_cast<float4*>(st + row * 128 + ((q4 ^ (row & 7)) << 4)) = make_float4(x[4 * q4], x[4 * q4 + 1], x[4 * q4 + 2], x[4 * q4 + 3]);
+                    fence_async_smem();
+                    epi_bar(3);
+                    if (et == 0) {
+                        tma_store_3d(&p.omap_hi, st, n0 + c0, t0, b);  // rows >= T_out and columns >= C are clipped
+                        bulk_commit();
+                    }
+                    ++epi_chunks;
+                }
+                if (nt == p.n_ntiles - 1 && row_ok) {
+                    if (p.lse) p.lse[size_t(b) * p.T_out + t] = run_m + logf(run_s);
+                    if (p.argmax) p.argmax[size_t(b) * p.T_out + t] = run_i;
                 }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
                 continue;
@@ -643,6 +728,11 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
         CAB_CHECK_ARG(bn >= ep->C_out, "block_n=%d must cover all %d classes", bn, ep->C_out);
     } else if (ep->epilogue == CAB_EPI_LOGITS_F32) {
         CAB_CHECK_ARG(ep->logits != nullptr, "logits is null");
+    } else if (ep->epilogue == CAB_EPI_LOGITS_ROWS) {
+        CAB_CHECK_ARG(ep->logits != nullptr, "logits is null");
+        CAB_CHECK_ARG(bn % 32 == 0, "block_n=%d must be a multiple of 32 for the row-major logits epilogue", bn);
+        CAB_CHECK_ARG(ep->out_ld_ch >= ep->C_out && ep->out_ld_ch % 4 == 0 && (reinterpret_cast<uintptr_t>(ep->logits) & 15) == 0, "row-major logits need a 16-byte aligned base and a row pitch that is a multiple of 4 floats (got %d)", ep->out_ld_ch);
+        CAB_CHECK_ARG(ep->act == CAB_ACT_NONE, "the row-major logits epilogue applies no activation");
     } else {
         CAB_CHECK_ARG(false, "unknown epilogue %d", ep->epilogue);
     }
@@ -664,6 +754,19 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     p.log_probs = ep->log_probs;
     p.argmax = ep->argmax;
     p.stats = ep->epilogue == CAB_EPI_ACT_BF16 ? ep->stats : nullptr;
+    p.lse = ep->epilogue == CAB_EPI_LOGITS_ROWS ? ep->log_probs : nullptr;  // the log_probs slot carries the [B, T_out] log-sum-exp output
+    p.mtile_major = ep->epilogue == CAB_EPI_LOGITS_ROWS ? 1 : 0;
+    if (ep->epilogue == CAB_EPI_LOGITS_ROWS) {
+        EncodeTiledFn enc = get_encode_fn();
+        CAB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+        cuuint64_t dims[3] = {(cuuint64_t)ep->C_out, (cuuint64_t)ep->T_out, (cuuint64_t)ep->B};
+        cuuint64_t strides[2] = {(cuuint64_t)ep->out_ld_ch * 4, (cuuint64_t)ep->T_out * ep->out_ld_ch * 4};
+        cuuint32_t box[3] = {32, kBlockM, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&p.omap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ep->logits, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CAB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the row-major logits", (int)r);
+    }
     // structural-zero rows: given explicitly (training: zero input rows / don't-care gradient rows), or implied
     // by the temporal mask this launch applies itself
     p.skip_frac = nullptr; p.skip_T = 0; p.skip_margin = 0;
@@ -724,7 +827,8 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     });
     CAB_CHECK_ARG(attr_err == cudaSuccess, "cudaFuncSetAttribute(smem=%d) failed: %s", kSmemBytes, cudaGetErrorString(attr_err));
     CAB_CHECK_ARG(num_sms > 0, "no CUDA device");
-    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    if (p.mtile_major) grid = p.B * p.mtiles_per_b < num_sms ? p.B * p.mtiles_per_b : num_sms;
     conv1d_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);

@@ -244,6 +244,30 @@ __global__ void ctc_grad_init_kernel(const float* __restrict__ lp, int64_t st, i
         }
         return;
     }
+    if (gc == 1 && sc == 1) {  // class-contiguous rows (the large-vocabulary head's layout): one (b, t) row of C classes at a time
+        for (int row = blockIdx.x; row < B * T; row += gridDim.x) {
+            const int b = row / T, t = row - b * T;
+            const bool on = t < (int)in_len[b];
+            const float g0 = go[b];
+            const float* src = lp + (int64_t)b * sb + (int64_t)t * st;
+            float* dst = grad + (int64_t)b * gb + (int64_t)t * gt;
+            if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+                const int n4 = C >> 2;
+                for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on) {
+                        const float4 x = reinterpret_cast<const float4*>(src)[i];
+                        v = make_float4(expf(x.x) * g0, expf(x.y) * g0, expf(x.z) * g0, expf(x.w) * g0);
+                    }
+                    reinterpret_cast<float4*>(dst)[i] = v;
+                }
+                for (int c = (n4 << 2) + threadIdx.x; c < C; c += blockDim.x) dst[c] = on ? expf(src[c]) * g0 : 0.f;
+            } else {
+                for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = on ? expf(src[c]) * g0 : 0.f;
+            }
+        }
+        return;
+    }
     const int64_t n = (int64_t)B * T * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int b, c, t;
@@ -449,6 +473,27 @@ log_softmax_argmax_kernel(const float* __restrict__ x, int B, int C, int T, floa
             }
         }
         if (amax != nullptr && grp == 0) amax[(size_t)b * T + t] = IM == 0x7fffffff ? 0 : IM;
+    }
+}
+
+// log_probs = logits - lse[row] over class-contiguous rows (second half of the fused large-vocabulary head)
+__global__ void __launch_bounds__(256)
+log_softmax_rows_kernel(const float* __restrict__ x, const float* __restrict__ lse, long long R, int C, int ld,
+                        float* __restrict__ out) {
+    const int n4 = C >> 2;  // ld % 4 == 0 and 16-byte aligned bases: float4 all the way, tail scalars
+    for (long long r = blockIdx.x; r < R; r += gridDim.x) {
+        const float l = __ldg(lse + r);
+        const float4* src = reinterpret_cast<const float4*>(x + r * ld);
+        float4* dst = reinterpret_cast<float4*>(out + r * ld);
+        for (int i = threadIdx.x; i < n4; i += 4 * 256) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i + u * 256 < n4) v[u] = src[i + u * 256];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u * 256 < n4) dst[i + u * 256] = make_float4(v[u].x - l, v[u].y - l, v[u].z - l, v[u].w - l);
+        }
+        for (int c = (n4 << 2) + threadIdx.x; c < C; c += 256) out[r * ld + c] = x[r * ld + c] - l;
     }
 }
 
@@ -776,6 +821,18 @@ extern "C" int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, i
     greedy_collapse_kernel<<<(B + 63) / 64, 64, 0, stream>>>(ids, lengths, B, T, C, eps_id, space_id, is_silence,
                                                              is_word_start, blank_amount_to_space, out_tokens,
                                                              out_frames, T_cap, out_counts);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_log_softmax_rows(const float* logits, const float* lse, int64_t R, int C, int ld, float* out_log_probs,
+                                    cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(logits && lse && out_log_probs && R > 0 && C > 0, "bad arguments");
+    CAB_CHECK_ARG(ld >= C && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_log_probs) & 15) == 0, "rows must be 16-byte aligned (ld=%d)", ld);
+    const long long blocks = R < 148LL * 16 ? R : 148LL * 16;
+    log_softmax_rows_kernel<<<(int)blocks, 256, 0, stream>>>(logits, lse, (long long)R, C, ld, out_log_probs);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

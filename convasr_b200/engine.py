@@ -264,12 +264,15 @@ class StackPlan:
 			out_lo = torch.empty_like(out_hi) if self.fp32_tier else None
 			ops.conv1d_fused(srcs, B, T_out, L.C_alloc, bias = L.bias, act = code, act_a = a, act_b = b, xlen = xlen if L.mask else None, out_hi = out_hi, out_lo = out_lo)
 			return _Act(out_hi, out_lo, T_out, L.C_out)
-		logits = torch.empty(B, L.C_out, T_out, dtype = torch.float32, device = dev)
+		if L.epilogue == _lib.EPI_LOGSOFTMAX or code != _lib.ACT_NONE:
+			logits = torch.empty(B, L.C_out, T_out, dtype = torch.float32, device = dev)
 		if L.epilogue == _lib.EPI_LOGSOFTMAX:
 			log_probs = torch.empty_like(logits)
 			argmax = torch.empty(B, T_out, dtype = torch.int32, device = dev)
 			ops.conv1d_fused(srcs, B, T_out, L.C_out, bias = L.bias, logits = logits, log_probs = log_probs, argmax = argmax, epilogue = _lib.EPI_LOGSOFTMAX)
-		else:
+		elif code == _lib.ACT_NONE:
+			return ops.large_vocab_head(srcs, B, T_out, L.C_out, L.bias)  # head 0 with a large vocabulary: fused online softmax
+		else:  # the 'bpe' second head ends in ConvBn1d's activation (models.py:27-33): logits = act(.), then a separate log_softmax
 			ops.conv1d_fused(srcs, B, T_out, L.C_out, bias = L.bias, act = code, act_a = a, act_b = b, logits = logits, epilogue = _lib.EPI_LOGITS_F32)
 			log_probs, argmax = ops.log_softmax_argmax(logits)
 		return logits, log_probs, argmax

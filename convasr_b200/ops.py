@@ -144,6 +144,9 @@ def conv1d_fused(
 	ep.out_lo = None if out_lo is None else out_lo.data_ptr()
 	if out_hi is not None:
 		ep.out_T_rows, ep.out_ld_ch = out_hi.shape[1], out_hi.shape[2]
+	if epilogue == _lib.EPI_LOGITS_ROWS:  # logits: fp32 [B, T_out, ld] class-contiguous; log_probs slot: fp32 [B, T_out] log-sum-exp
+		assert logits is not None and logits.ndim == 3 and logits.is_contiguous() and logits.shape[1] == T_out
+		ep.out_T_rows, ep.out_ld_ch = T_out, logits.shape[2]
 	ep.logits = None if logits is None else logits.data_ptr()
 	ep.log_probs = None if log_probs is None else log_probs.data_ptr()
 	ep.argmax = None if argmax is None else argmax.data_ptr()
@@ -221,6 +224,23 @@ def log_softmax_argmax(logits, want_log_probs = True, want_argmax = True):
 	rc = _lib.load().cab_log_softmax_argmax(_p(logits), 0, B, C, T, _p(lp), _p(am), _stream())
 	_lib.check(rc, 'cab_log_softmax_argmax')
 	return lp, am
+
+
+def large_vocab_head(sources, B, T_out, C, bias):
+	"""Decoder 1x1 conv + log_softmax + argmax for large vocabularies (models.py:26,316; transcript_generators.py:27):
+	one GEMM launch whose epilogue writes the fp32 logits once (class-contiguous rows, TMA stores) and keeps an online
+	softmax per frame across the N tiles, then one streaming pass log_probs = logits - lse.  Returns (logits, log_probs,
+	argmax) with logits / log_probs as [B, C, T] VIEWS of class-contiguous [B, T, C] memory."""
+	dev = sources[0].act.device
+	ld = (C + 3) // 4 * 4
+	logits = torch.empty(B, T_out, ld, dtype = torch.float32, device = dev)
+	lse = torch.empty(B, T_out, dtype = torch.float32, device = dev)
+	argmax = torch.empty(B, T_out, dtype = torch.int32, device = dev)
+	conv1d_fused(sources, B, T_out, C, bias = bias, logits = logits, log_probs = lse, argmax = argmax, epilogue = _lib.EPI_LOGITS_ROWS)
+	log_probs = torch.empty_like(logits)
+	rc = _lib.load().cab_log_softmax_rows(_p(logits), _p(lse), B * T_out, C, ld, _p(log_probs), _stream())
+	_lib.check(rc, 'cab_log_softmax_rows')
+	return logits[:, :, :C].permute(0, 2, 1), log_probs[:, :, :C].permute(0, 2, 1), argmax
 
 
 class _LogSoftmaxDim1(torch.autograd.Function):

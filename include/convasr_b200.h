@@ -103,7 +103,10 @@ enum { CAB_ACT_NONE = 0, CAB_ACT_RELU = 1, CAB_ACT_HARDTANH = 2, CAB_ACT_LEAKY_R
 enum {
     CAB_EPI_ACT_BF16 = 0,   /* bf16 channels-last activation (+ optional lo residual) */
     CAB_EPI_LOGSOFTMAX = 1, /* fp32 [B,C,T] logits + log_probs + int32 argmax, C <= 256 */
-    CAB_EPI_LOGITS_F32 = 2  /* fp32 [B,C,T] logits only (large vocabularies) */
+    CAB_EPI_LOGITS_F32 = 2, /* fp32 [B,C,T] logits only */
+    CAB_EPI_LOGITS_ROWS = 3 /* large vocabularies: fp32 logits in CLASS-CONTIGUOUS memory [B, T_out, out_ld_ch] (TMA stores),
+                               plus per-row log-sum-exp (written to `log_probs`, here fp32 [B, T_out]) and argmax from an
+                               online softmax across the N tiles; cab_log_softmax_rows then writes the log-probs */
 };
 
 typedef struct {
@@ -288,6 +291,9 @@ int cab_grouped_conv1d_wgrad(const void* dy, const void* dy_lo, int dy_T_rows, i
  * ------------------------------------------------------------------------------------- */
 int cab_log_softmax_argmax(const void* logits, int in_dtype, int B, int C, int T,
                            float* out_log_probs, int32_t* out_argmax, cab_stream_t stream);
+/* second half of the fused large-vocabulary head: out[r, c] = logits[r, c] - lse[r] over R rows of C classes (row pitch ld) */
+int cab_log_softmax_rows(const float* logits, const float* lse, int64_t R, int C, int ld, float* out_log_probs,
+                         cab_stream_t stream);
 /* backward of log_softmax over dim 1: gin = gout - exp(lp) * sum_c gout */
 int cab_log_softmax_bwd(const float* log_probs, const float* grad_out, int B, int C, int T,
                         float* grad_in, cab_stream_t stream);

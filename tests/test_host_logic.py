@@ -205,7 +205,9 @@ def test_bench_reference_arm_prints_the_contract_line():
 	d = json.loads(lines[0])
 	assert d['impl'] == 'reference' and d['metric'] == 'audio_seconds_per_second' and d['unit'] == 'audio-s/s'
 	assert d['higher_is_better'] is True and d['value'] > 0 and d['gpu_launches'] == 0
-	assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+	from oracle import reference_shim
+	assert d['cpu_baseline']['kind'] == ('reference' if reference_shim.available() else 'port') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+	assert d['config']['batch_per_gpu'] == 2  # the label says what actually ran
 	assert d['e2e'] == dict(value = d['value'], unit = 'audio-s/s', h2d_bytes_per_step = 0, d2h_bytes_per_step = 0)
 	assert d['config']['workload'] == 'wav2letter_char_fwd_ctc_B8x10s_fp32'
 
