@@ -38,6 +38,10 @@ class PackItem(ctypes.Structure):
 	_fields_ = [('w', c_void_p), ('fwd', c_void_p), ('dgrad', c_void_p), ('fwd_lo', c_void_p), ('dgrad_lo', c_void_p), ('Co', c_i32), ('Ci', c_i32), ('K', c_i32), ('ci_ld', c_i32), ('co_ld', c_i32), ('mode', c_i32), ('pad', c_i32)]
 
 
+class UnpackItem(ctypes.Structure):
+	_fields_ = [('packed', c_void_p), ('grad', c_void_p), ('K', c_i32), ('Co', c_i32), ('Ci', c_i32), ('ld', c_i32), ('transposed', c_i32), ('pair_pad', c_i32), ('pair_ci_alloc', c_i32)]
+
+
 class BnBranch(ctypes.Structure):
 	_fields_ = [('y', c_void_p), ('y_lo', c_void_p), ('ss', c_void_p)]
 
@@ -74,6 +78,7 @@ SIGNATURES = {
 	'cab_pack_weight': [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
 	'cab_pack_weights_batched': [ctypes.POINTER(PackItem), c_int, c_void_p],
 	'cab_unpack_wgrad': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+	'cab_unpack_wgrad_batched': [ctypes.POINTER(UnpackItem), c_int, c_void_p],
 	'cab_bct_to_btc': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
 	'cab_optimizer_step': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
 							c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p, c_void_p],
@@ -95,6 +100,7 @@ SIGNATURES = {
 	'cab_topk_ids': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 	'cab_greedy_collapse': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
 							c_void_p, c_int, c_void_p, c_void_p],
+	'cab_top2_probs': [c_void_p, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_void_p, c_void_p],
 	'cab_entropy': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
 }
 INTROSPECTION = {'cab_abi_version': c_int, 'cab_last_error': ctypes.c_char_p, 'cab_launch_count': c_i64}

@@ -66,7 +66,8 @@ struct alignas(64) ConvParams {
     float* logits;
     float* log_probs;
     int* argmax;
-    float* stats;  // [2][C_out] per-channel sum / sum of squares of the bf16 outputs, or null
+    double* stats;  // [2][C_out] per-channel sum / sum of squares of the stored outputs, or null.  fp64 accumulators: the order of
+                    // the atomics then only touches bits far below the fp32 result -- batch statistics are reproducible run to run
     // CAB_EPI_LOGITS_ROWS: fp32 logits in class-contiguous memory [B, T_out, logits_ld] through omap_hi (box {32 fp32, 128 rows}),
     // per-row log-sum-exp and argmax from an online softmax across the N tiles of an M tile (M-tile-major schedule)
     float* lse;
@@ -413,8 +414,8 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                         // lane l now owns column bit-reversed?  no: the butterfly keeps column index == lane
                         const int col = n0 + c0 + lane;
                         if (col < p.C_out) {
-                            atomicAdd(p.stats + col, cs);
-                            atomicAdd(p.stats + p.C_out + col, cq);
+                            atomicAdd(p.stats + col, (double)cs);
+                            atomicAdd(p.stats + p.C_out + col, (double)cq);
                         }
                     }
                     fence_async_smem();  // generic-proxy smem writes -> visible to the TMA engine
@@ -778,7 +779,7 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
             p.skip_frac = ep->xlen_frac; p.skip_T = ep->T_out;
         }
     }
-    if (p.stats != nullptr) CAB_CHECK_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * 2 * ep->C_out, stream));
+    if (p.stats != nullptr) CAB_CHECK_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * ep->C_out, stream));
     if (ep->epilogue == CAB_EPI_ACT_BF16) {
         CAB_CHECK_ARG(ep->out_lo == nullptr || (reinterpret_cast<uintptr_t>(ep->out_lo) & 15) == 0, "out_lo must be 16-byte aligned");
         int rc = encode_map_3d(&p.omap_hi, ep->out_hi, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,

@@ -549,56 +549,99 @@ __global__ void topk_ids_kernel(const float* __restrict__ x, int B, int C, int T
     for (int k = 0; k < K; ++k) out[((size_t)b * K + k) * T + t] = id[k];
 }
 
+// two largest probabilities per frame, exp(top-2 log_probs) -- models.margin (models.py:676-677); out fp32 [B, 2, T]
+__global__ void top2_probs_kernel(const float* __restrict__ x, int64_t sb, int64_t sc, int64_t st, int B, int C, int T,
+                                  float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* xb = x + (int64_t)b * sb + (int64_t)t * st;
+    float v0 = -INFINITY, v1 = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+        const float v = xb[(int64_t)c * sc];
+        if (v > v0) { v1 = v0; v0 = v; }
+        else if (v > v1) v1 = v;
+    }
+    out[((size_t)b * 2 + 0) * T + t] = expf(v0);
+    out[((size_t)b * 2 + 1) * T + t] = expf(v1);
+}
+
 // ------------------------------------------------------------------------------------------
-// greedy CTC collapse state machine (transcript_generators.py:32-83), one utterance / thread
+// greedy CTC collapse state machine (transcript_generators.py:32-83) as a segmented WARP scan, one utterance per warp.
+//
+// The serial machine carries (last token, allow_repeat, count_eps), but every decision is local: after ANY non-blank
+// frame `last` equals that frame's id (it was either emitted or dropped because it equalled `last`) and allow_repeat is
+// false, and a blank is either ignored (last == space) or counted.  So for a non-blank frame t with previous non-blank
+// frame pt (id xp) and e = t - pt - 1 blanks in between:
+//   emitted  <=>  first token, or  xp == space ? x != space : (e >= 1 || x != xp)
+// and a blank frame t synthesises a space  <=>  t - pt == blank_to_space, xp != space and xp is not a word start.
+// Each frame yields at most one output, in frame order: a ballot + popcount prefix gives the output slot.  32 frames per
+// step, coalesced 128-byte reads; the carry between steps is (pt, xp).
 // ------------------------------------------------------------------------------------------
-__global__ void greedy_collapse_kernel(const int* __restrict__ ids, const int* __restrict__ lengths, int B,
-                                       int T, int C, int eps_id, int space_id,
-                                       const uint8_t* __restrict__ is_silence,
-                                       const uint8_t* __restrict__ is_word_start, int blank_to_space,
-                                       int* __restrict__ out_tok, int* __restrict__ out_frm, int T_cap,
-                                       int* __restrict__ out_cnt) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+greedy_collapse_kernel(const int* __restrict__ ids, const int* __restrict__ lengths, int B,
+                       int T, int C, int eps_id, int space_id,
+                       const uint8_t* __restrict__ is_silence,
+                       const uint8_t* __restrict__ is_word_start, int blank_to_space,
+                       int* __restrict__ out_tok, int* __restrict__ out_frm, int T_cap,
+                       int* __restrict__ out_cnt) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
     const int* row = ids + (size_t)b * T;
     int* tok = out_tok + (size_t)b * T_cap;
     int* frm = out_frm + (size_t)b * T_cap;
-    const int len = lengths ? lengths[b] : T;
-    int t = 0;
+    int len = lengths ? lengths[b] : T;
+    len = len < T ? len : T;
     // leading silence is skipped over the FULL row, not just `len` (transcript_generators.py:38-40)
-    while (t < T) {
-        const int x = row[t];
-        const bool sil = (x >= 0 && x < C) ? is_silence[x] != 0 : false;
-        if (!sil) break;
-        ++t;
-    }
-    if (t >= T) { out_cnt[b] = -1; return; }
-    int last = eps_id;  // tokens = [eps]
-    bool allow_repeat = false;
-    int count_eps = 0, n = 0;
-    for (; t < len && t < T; ++t) {
-        const int x = row[t];
-        if (x == eps_id && last == space_id) continue;
-        if (x == eps_id) {
-            allow_repeat = true;
-            ++count_eps;
-            const bool last_ws = (last >= 0 && last < C) ? is_word_start[last] != 0 : false;
-            if (count_eps >= blank_to_space && !last_ws) {
-                if (n < T_cap) { tok[n] = space_id; frm[n] = -(t + 1); }
-                ++n;
-                last = space_id;
-            }
-            continue;
-        } else if (x == last && !allow_repeat) {
-            continue;
+    int t_start = T;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        bool nonsil = false;
+        if (t < T) {
+            const int x = row[t];
+            nonsil = !((x >= 0 && x < C) ? is_silence[x] != 0 : false);
         }
-        allow_repeat = false;
-        if (n < T_cap) { tok[n] = x; frm[n] = t; }
-        ++n;
-        last = x;
-        count_eps = 0;
+        const unsigned m = __ballot_sync(0xffffffffu, nonsil);
+        if (m) { t_start = t0 + __ffs(m) - 1; break; }
     }
-    out_cnt[b] = n < T_cap ? n : T_cap;
+    if (t_start >= T) { if (lane == 0) out_cnt[b] = -1; return; }
+    int n = 0;
+    int pt = t_start - 1, xp = eps_id;  // previous non-blank frame and its id; the machine starts with tokens = [eps] (transcript_generators.py:42)
+    for (int t0 = t_start & ~31; t0 < len; t0 += 32) {
+        const int t = t0 + lane;
+        const bool in = t >= t_start && t < len;
+        const int x = in ? row[t] : eps_id;
+        const bool is_tok = in && x != eps_id;
+        const unsigned tokmask = __ballot_sync(0xffffffffu, is_tok);
+        // previous non-blank frame of this lane: inside the step, else the carry
+        const unsigned below = tokmask & ((1u << lane) - 1u);
+        const int src = below ? 31 - __clz(below) : 0;
+        const int x_in = __shfl_sync(0xffffffffu, x, src);
+        const int my_pt = below ? t0 + src : pt;
+        const int my_xp = below ? x_in : xp;
+        bool out = false;
+        int o_tok = x, o_frm = t;
+        if (is_tok) {
+            const int e = t - my_pt - 1;
+            out = my_xp == space_id ? x != space_id : (e >= 1 || x != my_xp);
+        } else if (in && t - my_pt == blank_to_space && my_xp != space_id) {
+            const bool ws = (my_xp >= 0 && my_xp < C) ? is_word_start[my_xp] != 0 : false;
+            if (!ws) { out = true; o_tok = space_id; o_frm = -(t + 1); }
+        }
+        const unsigned outmask = __ballot_sync(0xffffffffu, out);
+        if (out) {
+            const int pos = n + __popc(outmask & ((1u << lane) - 1u));
+            if (pos < T_cap) { tok[pos] = o_tok; frm[pos] = o_frm; }
+        }
+        n += __popc(outmask);
+        if (tokmask) {
+            const int last = 31 - __clz(tokmask);
+            pt = t0 + last;
+            xp = __shfl_sync(0xffffffffu, x, last);
+        }
+    }
+    if (lane == 0) out_cnt[b] = n < T_cap ? n : T_cap;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -811,6 +854,17 @@ extern "C" int cab_topk_ids(const float* log_probs, int B, int C, int T, int K, 
     return 0;
 }
 
+extern "C" int cab_top2_probs(const float* log_probs, int64_t stride_b, int64_t stride_c, int64_t stride_t, int B, int C, int T,
+                              float* out, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(log_probs && out && B > 0 && C >= 2 && T > 0, "bad arguments");
+    dim3 grid((T + 127) / 128, B);
+    top2_probs_kernel<<<grid, 128, 0, stream>>>(log_probs, stride_b, stride_c, stride_t, B, C, T, out);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, int B, int T, int C, int eps_id,
                                    int space_id, const uint8_t* is_silence, const uint8_t* is_word_start,
                                    int blank_amount_to_space, int32_t* out_tokens, int32_t* out_frames, int T_cap,
@@ -818,7 +872,7 @@ extern "C" int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, i
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(ids && is_silence && is_word_start && out_tokens && out_frames && out_counts, "null pointer argument");
     CAB_CHECK_ARG(B > 0 && T > 0 && T_cap > 0, "bad shape");
-    greedy_collapse_kernel<<<(B + 63) / 64, 64, 0, stream>>>(ids, lengths, B, T, C, eps_id, space_id, is_silence,
+    greedy_collapse_kernel<<<(B + 7) / 8, 256, 0, stream>>>(ids, lengths, B, T, C, eps_id, space_id, is_silence,
                                                              is_word_start, blank_amount_to_space, out_tokens,
                                                              out_frames, T_cap, out_counts);
     CAB_CHECK_LAUNCH();

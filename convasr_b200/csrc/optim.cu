@@ -16,7 +16,8 @@ extern std::atomic<int64_t> g_launch_count;
 
 constexpr int kOptThreads = 256;
 
-// per-tensor sum of squares of the gradient; one block per chunk
+// sum of squares of one chunk of a gradient -> out[chunk] (no atomics: the per-tensor and total norms are then summed in a
+// fixed order, so data-parallel replicas derive bit-identical clip coefficients from bit-identical gradients)
 __global__ void __launch_bounds__(kOptThreads)
 mt_sumsq_kernel(const long long* __restrict__ grad_ptrs, const long long* __restrict__ numels,
                 const int* __restrict__ chunk_tensor, const long long* __restrict__ chunk_off, int chunk_elems,
@@ -41,17 +42,32 @@ mt_sumsq_kernel(const long long* __restrict__ grad_ptrs, const long long* __rest
         acc = sm[threadIdx.x];
 #pragma unroll
         for (int o = kOptThreads / 64; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffu, acc, o);
-        if (threadIdx.x == 0) atomicAdd(out + ti, acc);
+        if (threadIdx.x == 0) out[blockIdx.x] = acc;
     }
 }
 
 // per-tensor scalars: clip coefficient, NovoGrad second-moment EMA -> scale[i]; step counter / first flag
 // state: [0] = step count (as float bits are avoided: int), kept in an int64 device cell
-__global__ void mt_prepare_kernel(const float* __restrict__ sumsq, int n, int mode, float max_norm, float beta2, float eps,
+__global__ void mt_prepare_kernel(float* __restrict__ sumsq, const float* __restrict__ chunk_sumsq, const int* __restrict__ chunk_tensor,
+                                  int n_chunks, int n, int mode, float max_norm, float beta2, float eps,
                                   float* __restrict__ ema, float* __restrict__ scale, long long* __restrict__ step_cell,
                                   int* __restrict__ first_flag, float* __restrict__ total_norm_out,
                                   const float* __restrict__ ext_total_norm) {
     __shared__ float s_total;
+    // per-tensor sums from the chunk partials, in chunk order (chunks of a tensor are consecutive: binary search for the first)
+    if (chunk_sumsq != nullptr) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int lo = 0, hi = n_chunks;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (chunk_tensor[mid] < i) lo = mid + 1; else hi = mid;
+            }
+            float a = 0.f;
+            for (int c = lo; c < n_chunks && chunk_tensor[c] == i; ++c) a += chunk_sumsq[c];
+            sumsq[i] = a;
+        }
+        __syncthreads();
+    }
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += sumsq[i];
     acc = warp_sum(acc);
@@ -152,13 +168,15 @@ extern "C" int cab_optimizer_step(int mode, int n_tensors, const int64_t* param_
     CAB_CHECK_ARG(mode != 1 || ema != nullptr, "NovoGrad needs the ema state");
     int launches = 1;
     const bool need_norm = mode >= 1 || (max_grad_norm > 0.f && ext_total_norm == nullptr) || total_norm_out != nullptr;
-    CAB_CHECK_CUDA(cudaMemsetAsync(ws_sumsq, 0, sizeof(float) * n_tensors, stream));
+    // ws_sumsq: [n_tensors] per-tensor sums followed by [n_chunks] per-chunk partials
     if (need_norm) {
-        mt_sumsq_kernel<<<n_chunks, kOptThreads, 0, stream>>>(reinterpret_cast<const long long*>(grad_ptrs), reinterpret_cast<const long long*>(numels), chunk_tensor, reinterpret_cast<const long long*>(chunk_off), chunk_elems, ws_sumsq);
+        mt_sumsq_kernel<<<n_chunks, kOptThreads, 0, stream>>>(reinterpret_cast<const long long*>(grad_ptrs), reinterpret_cast<const long long*>(numels), chunk_tensor, reinterpret_cast<const long long*>(chunk_off), chunk_elems, ws_sumsq + n_tensors);
         CAB_CHECK_LAUNCH();
         ++launches;
+    } else {
+        CAB_CHECK_CUDA(cudaMemsetAsync(ws_sumsq, 0, sizeof(float) * n_tensors, stream));
     }
-    mt_prepare_kernel<<<1, 256, 0, stream>>>(ws_sumsq, n_tensors, mode, (need_norm || ext_total_norm) ? max_grad_norm : 0.f, beta2, eps, ema, ws_scale, reinterpret_cast<long long*>(step_cell), ws_first, total_norm_out, ext_total_norm);
+    mt_prepare_kernel<<<1, 256, 0, stream>>>(ws_sumsq, need_norm ? ws_sumsq + n_tensors : nullptr, chunk_tensor, n_chunks, n_tensors, mode, (need_norm || ext_total_norm) ? max_grad_norm : 0.f, beta2, eps, ema, ws_scale, reinterpret_cast<long long*>(step_cell), ws_first, total_norm_out, ext_total_norm);
     CAB_CHECK_LAUNCH();
     if (mode == 2) {
         g_launch_count.fetch_add(launches, std::memory_order_relaxed);

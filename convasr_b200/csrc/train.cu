@@ -76,7 +76,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // reduce 2 x 8 per-thread partials over the row lanes, then one atomic per channel and statistic
 // (mean, invstd given: the second statistic is centred first, q <- invstd * (q - mean * s))
-__device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8], int c0, int C, float* __restrict__ out,
+template <typename OutT>
+__device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8], int c0, int C, OutT* __restrict__ out,
                                                     const float* __restrict__ mean = nullptr, const float* __restrict__ invstd = nullptr) {
     __shared__ float sm[kRowLanes][32][17];
 #pragma unroll
@@ -95,8 +96,8 @@ __device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8]
             }
             if (c0 + e < C) {
                 if (mean != nullptr) b = invstd[c0 + e] * (b - mean[c0 + e] * a);
-                atomicAdd(out + c0 + e, a);
-                atomicAdd(out + C + c0 + e, b);
+                atomicAdd(out + c0 + e, (OutT)a);
+                atomicAdd(out + C + c0 + e, (OutT)b);
             }
         }
     }
@@ -104,7 +105,7 @@ __device__ __forceinline__ void reduce_rows_and_add(float (&s)[8], float (&q)[8]
 
 // per-channel sum / sum of squares of a bf16 [R, ld] matrix (R = B*t rows)
 __global__ void __launch_bounds__(256)
-colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float* __restrict__ out, int kRowsPerBlock) {
+colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, double* __restrict__ out, int kRowsPerBlock) {
     const int cv = blockIdx.x * 32 + threadIdx.x;
     const int c0 = cv * 8;
     float s[8], q[8];
@@ -133,14 +134,16 @@ colstats_kernel(const __nv_bfloat16* __restrict__ x, int R, int C, int ld, float
 }
 
 // mean / invstd / fused scale+shift, running statistics update (momentum, unbiased running_var)
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int C, float n, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, float n, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ out /* [4][C]: scale, shift, mean, invstd */, int sums_ld) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const float mean = stats[c] / n;
-    const float var = fmaxf(stats[sums_ld + c] / n - mean * mean, 0.f);
+    // fp64 sums: E[x^2] - mean^2 without cancellation noise
+    const double mean_d = stats[c] / (double)n;
+    const float mean = (float)mean_d;
+    const float var = (float)fmax(stats[sums_ld + c] / (double)n - mean_d * mean_d, 0.0);
     const float invstd = rsqrtf(var + eps);
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     out[c] = g * invstd;
@@ -347,12 +350,12 @@ struct StreamArgs {
     __nv_bfloat16* out_lo;
     const float* ss;           // [4][C] scale, shift, mean, invstd
     const float* xlen;
-    float* partials;           // [kBnSumReplicas][2][C]
+    double* partials;          // [kBnSumReplicas][2][C]: sum dz, sum dz * y (fp64: reproducible)
     float* sums;               // [2][C] totals (written by the apply pass)
     const long long* seed_ptr;
     unsigned long long salt;
     // forward with the BatchNorm finalize folded in (raw_sums != null): coefficients from the conv epilogue's raw sums
-    const float* raw_sums;     // [2][sums_ld]
+    const double* raw_sums;    // [2][sums_ld]
     const float* gamma;
     const float* beta;
     float* running_mean;
@@ -423,8 +426,9 @@ bn_stream_kernel(const StreamArgs p) {
             sc[e] = 0.f; sh[e] = 0.f;
             if (ok) {
                 const float n = p.n_rows;
-                const float mean = p.raw_sums[c] / n;
-                const float var = fmaxf(p.raw_sums[p.sums_ld + c] / n - mean * mean, 0.f);
+                const double mean_d = p.raw_sums[c] / (double)n;
+                const float mean = (float)mean_d;
+                const float var = (float)fmax(p.raw_sums[p.sums_ld + c] / (double)n - mean_d * mean_d, 0.0);
                 const float invstd = rsqrtf(var + p.eps);
                 const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
                 sc[e] = g * invstd;
@@ -445,15 +449,19 @@ bn_stream_kernel(const StreamArgs p) {
         acc_s[e] = 0.f; acc_q[e] = 0.f; k0[e] = 0.f; k1[e] = 0.f;
         if (MODE == 2) {
             float m1 = 0.f, m2 = 0.f;
+            const float mean = ok ? p.ss[2 * C + c] : 0.f, istd = ok ? p.ss[3 * C + c] : 0.f;
             if (ok) {
+                double d1 = 0.0, d2 = 0.0;
 #pragma unroll
                 for (int r = 0; r < kBnSumReplicas; ++r) {
-                    m1 += p.partials[(size_t)r * 2 * C + c];
-                    m2 += p.partials[(size_t)r * 2 * C + C + c];
+                    d1 += p.partials[(size_t)r * 2 * C + c];
+                    d2 += p.partials[(size_t)r * 2 * C + C + c];
                 }
+                // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)), centred in fp64
+                m1 = (float)d1;
+                m2 = (float)((double)istd * (d2 - (double)mean * d1));
                 if (blockIdx.x == 0 && lane == 0) { p.sums[c] = m1; p.sums[C + c] = m2; }
             }
-            const float mean = ok ? p.ss[2 * C + c] : 0.f, istd = ok ? p.ss[3 * C + c] : 0.f;
             k1[e] = -sc[e] * (m2 * p.inv_n) * istd;          // coefficient of y
             k0[e] = -sc[e] * (m1 * p.inv_n) - k1[e] * mean;  // constant term
         }
@@ -535,7 +543,7 @@ bn_stream_kernel(const StreamArgs p) {
         }
         __syncthreads();
         if (lane == 0) {
-            float* dst = p.partials + (size_t)(blockIdx.x % kBnSumReplicas) * 2 * C;
+            double* dst = p.partials + (size_t)(blockIdx.x % kBnSumReplicas) * 2 * C;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 float a_ = 0.f, b_ = 0.f;
@@ -545,10 +553,8 @@ bn_stream_kernel(const StreamArgs p) {
                 }
                 const int c = c0 + e;
                 if (c < C) {
-                    // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)): linear, so per partial
-                    b_ = p.ss[3 * C + c] * (b_ - p.ss[2 * C + c] * a_);
-                    atomicAdd(dst + c, a_);
-                    atomicAdd(dst + C + c, b_);
+                    atomicAdd(dst + c, (double)a_);
+                    atomicAdd(dst + C + c, (double)b_);
                 }
             }
         }
@@ -729,6 +735,43 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int K, int
     }
 }
 
+// All layers in ONE launch (19 per-layer launches were 0.46 ms of a 24 ms step, launch / latency bound).  thread = (co, ci):
+// reads run along ci (coalesced in every packed layout), each thread writes its K taps -- a warp's writes form one contiguous
+// span of the parameter-layout gradient.
+constexpr int kUnpackMaxItems = 32;
+struct UnpackBatch {
+    const float* packed[kUnpackMaxItems];
+    float* grad[kUnpackMaxItems];
+    int K[kUnpackMaxItems], Co[kUnpackMaxItems], Ci[kUnpackMaxItems], ld[kUnpackMaxItems], mode[kUnpackMaxItems];
+    int pair_pad[kUnpackMaxItems], pair_ci_alloc[kUnpackMaxItems];
+    int block_start[kUnpackMaxItems + 1];
+    int n;
+};
+__global__ void __launch_bounds__(256)
+unpack_wgrad_batched_kernel(const UnpackBatch ub) {
+    int item = 0;
+    while (item + 1 < ub.n && (int)blockIdx.x >= ub.block_start[item + 1]) ++item;
+    const int K = ub.K[item], Co = ub.Co[item], Ci = ub.Ci[item], ld = ub.ld[item], mode = ub.mode[item];
+    const float* __restrict__ packed = ub.packed[item];
+    float* __restrict__ grad = ub.grad[item];
+    const long long idx = (long long)(blockIdx.x - ub.block_start[item]) * 256 + threadIdx.x;
+    if (idx >= (long long)Co * Ci) return;
+    const int co = (int)(idx / Ci), ci = (int)(idx - (long long)co * Ci);
+    float* dst = grad + idx * K;
+    if (mode == 2) {
+        const int pad = ub.pair_pad[item], ca = ub.pair_ci_alloc[item];
+        const int dp_min = floordiv2(-pad);
+        for (int k = 0; k < K; ++k) {
+            const int j = k - pad, dp = floordiv2(j), q = j - 2 * dp;
+            dst[k] = packed[((size_t)(dp - dp_min) * Co + co) * ld + q * ca + ci];
+        }
+    } else if (mode == 1) {
+        for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Ci + ci) * ld + co];
+    } else {
+        for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Co + co) * ld + ci];
+    }
+}
+
 // fp32 [B, C, T] -> bf16 channels-last [B, T, ld] (zero padded channels) + per-class sums over (b, t)
 __global__ void __launch_bounds__(256)
 bct_to_btc_kernel(const float* __restrict__ x, int B, int C, int T, int ld, __nv_bfloat16* __restrict__ out,
@@ -870,12 +913,12 @@ using namespace cab;
 #define GRID_1D(n, per) (int)(((n) / (per) + 255) / 256 > (size_t)num_sms() * 8 ? (size_t)num_sms() * 8 : (((n) / (per) + 255) / 256 < 1 ? 1 : ((n) / (per) + 255) / 256))
 
 extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta, float eps,
-                                  float momentum, float* running_mean, float* running_var, float* ws_sums /*[2][C]*/,
+                                  float momentum, float* running_mean, float* running_var, double* ws_sums /*[2][C]*/,
                                   float* out_ss /*[4][C]*/, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && ws_sums && out_ss, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout C=%d ld=%d", C, ld);
-    CAB_CHECK_CUDA(cudaMemsetAsync(ws_sums, 0, sizeof(float) * 2 * C, stream));
+    CAB_CHECK_CUDA(cudaMemsetAsync(ws_sums, 0, sizeof(double) * 2 * C, stream));
     const int R = B * T, rpb = rows_per_block_for(R, ld);
     dim3 grid((ld / 8 + 31) / 32, (R + rpb - 1) / rpb), block(32, kRowLanes);
     colstats_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), R, C, ld, ws_sums, rpb);
@@ -886,7 +929,7 @@ extern "C" int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, co
     return 0;
 }
 
-extern "C" int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
+extern "C" int cab_bn_finalize(const double* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
                                float momentum, float* running_mean, float* running_var, float* out_ss, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(sums && out_ss && n_rows > 0 && C > 0, "bad arguments");
@@ -927,7 +970,7 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const void* y_lo, const float*
     return 0;
 }
 
-extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const float* raw_sums, int sums_ld, int n_rows,
+extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const double* raw_sums, int sums_ld, int n_rows,
                                          const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                                          float* running_var, float* out_ss, int B, int T, int C, int ld, int act, float act_a,
                                          float act_b, const float* xlen_frac, void* out, void* out_lo, float dropout_p,
@@ -963,7 +1006,7 @@ extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const 
 extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
                                    int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
                                    float* sums /*[2][C]: dbeta, dgamma*/, void* grad_y, void* grad_y_lo, float dropout_p,
-                                   const int64_t* seed, int64_t salt, int frozen, float* ws_partials, cab_stream_t stream_) {
+                                   const int64_t* seed, int64_t salt, int frozen, double* ws_partials, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
@@ -982,7 +1025,7 @@ extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* 
             sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
             sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.inv_n = frozen ? 0.f : 1.f / (float)(B * T);  // frozen: grad_y = scale * dz
             sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
-            CAB_CHECK_CUDA(cudaMemsetAsync(ws_partials, 0, sizeof(float) * kBnSumReplicas * 2 * C, stream));
+            CAB_CHECK_CUDA(cudaMemsetAsync(ws_partials, 0, sizeof(double) * kBnSumReplicas * 2 * C, stream));
             if (split) {
                 CAB_CHECK_CUDA((stream_launch<1, true>(sa, threads, grid_s, smem, stream)));
                 CAB_CHECK_CUDA((stream_launch<2, true>(sa, threads, grid_s, smem, stream)));
@@ -1108,6 +1151,27 @@ extern "C" int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int 
     CAB_CHECK_ARG(transposed >= 0 && transposed <= 2, "transposed=%d", transposed);
     const size_t n = (size_t)Co * Ci * K;
     unpack_wgrad_kernel<<<GRID_1D(n, 1), 256, 0, stream>>>(packed, K, Co, Ci, ld, transposed, grad, accumulate, pair_pad, pair_ci_alloc);
+    CAB_CHECK_LAUNCH();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int cab_unpack_wgrad_batched(const cab_unpack_item_t* items, int n, cab_stream_t stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    CAB_CHECK_ARG(items && n >= 1 && n <= kUnpackMaxItems, "n=%d out of [1,%d]", n, kUnpackMaxItems);
+    static thread_local UnpackBatch ub;
+    int blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        const cab_unpack_item_t& it = items[i];
+        CAB_CHECK_ARG(it.packed && it.grad && it.K > 0 && it.Co > 0 && it.Ci > 0 && it.transposed >= 0 && it.transposed <= 2, "item %d: bad arguments", i);
+        ub.packed[i] = it.packed; ub.grad[i] = it.grad; ub.K[i] = it.K; ub.Co[i] = it.Co; ub.Ci[i] = it.Ci; ub.ld[i] = it.ld; ub.mode[i] = it.transposed;
+        ub.pair_pad[i] = it.pair_pad; ub.pair_ci_alloc[i] = it.pair_ci_alloc;
+        ub.block_start[i] = blocks;
+        blocks += (int)(((long long)it.Co * it.Ci + 255) / 256);
+    }
+    ub.block_start[n] = blocks;
+    ub.n = n;
+    unpack_wgrad_batched_kernel<<<blocks, 256, 0, stream>>>(ub);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

@@ -618,8 +618,13 @@ def weighted_mean_entropy(log_probs, lengths = None, dim = -2, eps = 1e-9, eps_i
 
 
 def margin(log_probs, dim = 1):
-	"""models.py:676-677"""
-	return torch.sub(*log_probs.exp().topk(2, dim = dim).values)
+	"""models.py:676-677: `torch.sub(*probs.topk(2, dim).values)`.  NB the reference unpacks the BATCH dimension, so it is
+	only defined for a batch of two (top-2 of utterance 0 minus top-2 of utterance 1, [2, T]) and raises TypeError for any
+	other batch size; kept as is.  The top-2 probabilities come from a native kernel."""
+	if not log_probs.is_cuda:
+		raise RuntimeError('convasr_b200: margin() runs on CUDA tensors only (there is no CPU fallback)')
+	vals = ops.top2_probs(log_probs) if (dim == 1 and log_probs.ndim == 3) else log_probs.exp().topk(2, dim = dim).values
+	return torch.sub(*vals)
 
 
 def compute_capacity(model, scale = 1):

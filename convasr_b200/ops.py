@@ -294,6 +294,17 @@ def greedy_collapse(ids, lengths, num_classes, eps_id, space_id, is_silence, is_
 	return tok, frm, cnt
 
 
+def top2_probs(log_probs):
+	"""fp32 [B, C, T] (any strides) -> fp32 [B, 2, T]: the two largest probabilities per frame"""
+	_need_cuda(log_probs)
+	lp = log_probs if log_probs.dtype == torch.float32 else log_probs.float()
+	B, C, T = lp.shape
+	out = torch.empty(B, 2, T, dtype = torch.float32, device = lp.device)
+	rc = _lib.load().cab_top2_probs(_p(lp), lp.stride(0), lp.stride(1), lp.stride(2), B, C, T, _p(out), _stream())
+	_lib.check(rc, 'cab_top2_probs')
+	return out
+
+
 def entropy(log_probs, lengths = None, eps_id = -1):
 	_need_cuda(log_probs, lengths)
 	log_probs = log_probs.to(torch.float32).contiguous()

@@ -66,7 +66,7 @@ class _FusedOptimizer(torch.optim.Optimizer):
 				n = n, n_chunks = len(chunk_tensor), ema = ema,
 				chunk_tensor = torch.tensor(chunk_tensor, dtype = torch.int32, device = dev), chunk_off = torch.tensor(chunk_off, dtype = torch.int64, device = dev),
 				numels = torch.tensor([p.numel() for p in params], dtype = torch.int64, device = dev),
-				sumsq = torch.empty(n, dtype = torch.float32, device = dev), scale = torch.empty(n, dtype = torch.float32, device = dev),
+				sumsq = torch.empty(n + len(chunk_tensor), dtype = torch.float32, device = dev), scale = torch.empty(n, dtype = torch.float32, device = dev),
 				step = torch.zeros(1, dtype = torch.int64, device = dev), first = torch.zeros(1, dtype = torch.int32, device = dev),
 				lr = torch.zeros(1, dtype = torch.float32, device = dev), lr_host = None, norm = torch.zeros(1, dtype = torch.float32, device = dev),
 				# two pinned staging tables used alternately, each guarded by an event: the H2D copy of step k may still be

@@ -196,7 +196,7 @@ def _srcs(a, w_hi, w_lo, C_in, taps, dil, pad_left, T_in, pair = False):
 
 
 def _bn_finalize(sums, n_rows, C, bn):
-	"""sums: fp32 [2, ld] accumulated by the conv epilogue -> [scale, shift, mean, invstd] (+ running statistics)"""
+	"""sums: fp64 [2, ld] accumulated by the conv epilogue -> [scale, shift, mean, invstd] (+ running statistics)"""
 	ss = torch.empty(4, C, dtype = torch.float32, device = sums.device)
 	if sums.shape[1] != C:  # the epilogue indexes the statistics with the padded channel count
 		sums = sums[:, :C].contiguous()
@@ -231,7 +231,7 @@ def _conv_bn(cv, x, T_in, B, w, bias, bn, xlen, skip, split):
 	if not bn.training:
 		ops.conv1d_fused(srcs, B, T_out, cv.co_alloc, bias = b_pad, out_hi = y.hi, out_lo = y.lo, skip = skip)
 		return y, _bn_frozen_coeffs(bn), T_out, None
-	sums = torch.empty(2, cv.co_alloc, dtype = torch.float32, device = dev)
+	sums = torch.empty(2, cv.co_alloc, dtype = torch.float64, device = dev)  # fp64 accumulators: reproducible batch statistics
 	ops.conv1d_fused(srcs, B, T_out, cv.co_alloc, bias = b_pad, out_hi = y.hi, out_lo = y.lo, stats = sums, skip = skip)  # batch statistics in the epilogue
 	return y, None, T_out, sums
 
@@ -376,20 +376,33 @@ class NativeStack(torch.autograd.Function):
 			return v
 
 		max_c = max(rep.conv.C_out for rep in reps)
-		partials = torch.empty(_lib.BN_SUM_REPLICAS * 2 * max_c, dtype = torch.float32, device = dev)  # scratch of the BN backward sums
+		partials = torch.empty(_lib.BN_SUM_REPLICAS * 2 * max_c, dtype = torch.float64, device = dev)  # scratch of the BN backward sums
 		d_bias = small[:C] if dec.bias is not None else None
 		rc = lib.cab_bct_to_btc(ops._p(g), B, C, T, c_ld, ops._p(g_cl.hi), ops._p(g_cl.lo), ops._p(d_bias), ops._stream())
 		_lib.check(rc, 'cab_bct_to_btc')
 		grads = {}
 
 		def wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, x_masked):
-			return _wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, xlen if (_SKIP_PADDING and xlen is not None and x_masked) else None)
+			return _wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, xlen if (_SKIP_PADDING and xlen is not None and x_masked) else None, defer = True)
+
+		deferred = []  # packed weight gradients: all-reduced in their packed layout, un-packed into the parameter layout by ONE launch at the end
 
 		def finish_weight(p, grad):
-			if p.requires_grad:
+			if not p.requires_grad:
+				return
+			if isinstance(grad, tuple):
+				packed, K, Co, Ci, transposed, pair_pad, pair_ci_alloc = grad
+				out = torch.empty(Co, Ci, K, dtype = torch.float32, device = dev)
+				deferred.append(_lib.UnpackItem(packed.data_ptr(), out.data_ptr(), K, Co, Ci, packed.shape[2], int(transposed), pair_pad, pair_ci_alloc))
+				deferred_keep.append(packed)
+				grads[p] = out
+				grad = packed
+			else:
 				grads[p] = grad
-				if sync is not None:
-					sync.reduce(grad)  # overlaps the dgrad / wgrad of the layers still to come
+			if sync is not None:
+				sync.reduce(grad)  # overlaps the dgrad / wgrad of the layers still to come
+
+		deferred_keep = []
 
 		# decoder: the wide side (input channels) sits on the 128-row M side -> packed gradient is [1, Ci, Co]
 		x_last, T_last = ctx.last
@@ -397,7 +410,7 @@ class NativeStack(torch.autograd.Function):
 		skip_last = (xlen, T_last, 0) if _SKIP_PADDING and xlen is not None and last_masked else None
 		if dec.weight.requires_grad:
 			packed = _wgrad_packed(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0, skip_last)
-			finish_weight(dec.weight, _unpack(packed, 1, C, dec.in_channels, transposed = True))
+			finish_weight(dec.weight, (packed, 1, C, dec.in_channels, True, 0, 0))
 		if dec.bias is not None and dec.bias.requires_grad:
 			grads[dec.bias] = d_bias
 		# pending[activation id] = contributions to its gradient: ('gemm', dy, w_dgrad (hi, lo), C_in, taps, dil, pad_left, T_in) or ('direct', act)
@@ -491,7 +504,7 @@ class NativeStack(torch.autograd.Function):
 					xv = engine._Act(x.hi.view(B, x.hi.shape[1] // 2, 2 * x.hi.shape[2]), x.lo.view(B, x.lo.shape[1] // 2, 2 * x.lo.shape[2]) if x.lo is not None else None, x.hi.shape[1] // 2, 2 * cv.ci_alloc)
 					taps2 = W[cv][0].shape[0]
 					packed = _wgrad_packed(dy, T_out, cv.C_out, xv, xv.T, 2 * cv.ci_alloc, taps2, 1, -((0 - cv.pad) // 2), None)
-					finish_weight(cv.m.weight, _unpack(packed, cv.k, cv.C_out, cv.C_in, transposed = 2, pair_pad = cv.pad, pair_ci_alloc = cv.ci_alloc))
+					finish_weight(cv.m.weight, (packed, cv.k, cv.C_out, cv.C_in, 2, cv.pad, cv.ci_alloc))
 				else:
 					finish_weight(cv.m.weight, wgrad(dy, T_out, cv.C_out, conv_in, conv_T, cv.C_in, cv.k, cv.dil, cv.pad, in_masked))
 			if rep.in_id == 0 and rep.grouped is None:
@@ -524,6 +537,10 @@ class NativeStack(torch.autograd.Function):
 		if sync is not None:
 			sync.reduce(small)
 			sync.finish()
+		for lo in range(0, len(deferred), 32):
+			chunk = deferred[lo:lo + 32]
+			arr = (_lib.UnpackItem * len(chunk))(*chunk)
+			_lib.check(lib.cab_unpack_wgrad_batched(arr, len(chunk), ops._stream()), 'cab_unpack_wgrad_batched')
 		return (None, None, None, None) + tuple(grads.get(p) for p in holder['params'])
 
 
@@ -542,7 +559,7 @@ def _wgrad_packed(a, a_T, M, bx, b_T, N, taps, dil, pad, skip):
 	return out
 
 
-def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None):
+def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None, defer = False):
 	"""dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * x[b, t + tap*dil - pad, ci].  Either tensor can sit on the
 	128-row M side of the GEMM; pick the orientation with less tile padding (e.g. 640 -> 768 wastes 20 %
 	one way and nothing the other way).  Swapping sides negates the frame shift."""
@@ -551,9 +568,9 @@ def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None):
 	# xlen_zero: x is exactly zero from frame ceil(xlen*x_T) on, so products with t + tap*dil - pad >= that vanish
 	if _padded_work(C_out, C_in) <= _padded_work(C_in, C_out):
 		packed = _wgrad_packed(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, (xlen_zero, x_T, pad) if xlen_zero is not None else None)
-		return _unpack(packed, k, C_out, C_in, transposed = False)
+		return (packed, k, C_out, C_in, False, 0, 0) if defer else _unpack(packed, k, C_out, C_in, transposed = False)
 	packed = _wgrad_packed(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad, (xlen_zero, x_T, 0) if xlen_zero is not None else None)
-	return _unpack(packed, k, C_out, C_in, transposed = True)
+	return (packed, k, C_out, C_in, True, 0, 0) if defer else _unpack(packed, k, C_out, C_in, transposed = True)
 
 
 def _unpack(packed, K, Co, Ci, transposed, pair_pad = 0, pair_ci_alloc = 0):
@@ -626,7 +643,12 @@ class GraphedTrainStep:
 		self.optimizer.zero_grad(set_to_none = True)
 		out = self.model(sx, sxlen, y = sy, ylen = sylen)
 		loss = (out['loss'] * sylen[:, 0]).mean()  # train.py:754-755
-		loss.backward()
+		# torch.autograd.grad instead of loss.backward(): no AccumulateGrad nodes run.  Those are cached per parameter and
+		# remember the stream they were created under; one left over from an eager step on the default stream (any live
+		# reference to that step's outputs keeps it) would make the legacy stream wait on the capturing stream -- illegal.
+		grads = torch.autograd.grad(loss, self.params, allow_unused = True)
+		for p, g in zip(self.params, grads):
+			p.grad = g
 		from . import optimizers
 		if isinstance(self.optimizer, optimizers._FusedOptimizer):
 			self.optimizer.step(max_grad_norm = self.max_grad_norm)  # clipping folded into the native step

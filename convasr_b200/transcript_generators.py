@@ -4,7 +4,7 @@
 The reference does `log_probs.argmax(dim=1).cpu().tolist()` and then walks every frame in
 Python (B*t iterations).  Here the argmax comes fused from the decoder epilogue (or one native
 kernel), the blank/repeat collapse state machine with the 10-blanks->space rule runs on the GPU
-(one utterance per thread, csrc/ctc.cu: greedy_collapse_kernel), and the host only touches the
+(a segmented warp scan, one utterance per warp, csrc/ctc.cu: greedy_collapse_kernel), and the host only touches the
 EMITTED tokens to build segments and text.
 """
 import torch

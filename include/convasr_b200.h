@@ -123,9 +123,11 @@ typedef struct {
     float* logits;           /* LOGSOFTMAX / LOGITS_F32: fp32 [B, C_out, T_out] or NULL */
     float* log_probs;        /* LOGSOFTMAX: fp32 [B, C_out, T_out] or NULL */
     int32_t* argmax;         /* LOGSOFTMAX: int32 [B, T_out] or NULL (ties -> lowest id) */
-    float* stats;            /* ACT_BF16: NULL, or fp32 [2][C_out]: the call zeroes it and the epilogue
-                                accumulates per-channel sum / sum of squares of the (bf16-rounded) outputs
-                                over all B*T_out rows -- BatchNorm batch statistics for training */
+    double* stats;           /* ACT_BF16: NULL, or fp64 [2][C_out]: the call zeroes it and the epilogue
+                                accumulates per-channel sum / sum of squares of the stored outputs (bf16-rounded;
+                                hi + lo in the split tier) over all B*T_out rows -- BatchNorm batch statistics for
+                                training.  fp64 so that the order of the atomics cannot reach the fp32 result:
+                                the forward pass is reproducible run to run and GPU to GPU */
     const float* skip_frac;  /* ACT_BF16: NULL, or [B]: output rows t >= ceil(skip_frac[b]*skip_T) + skip_margin of
                                 utterance b are structural zeros (padding of a ragged batch whose input rows are
                                 zero there, or gradient rows nobody reads): 128-row tiles lying entirely in that
@@ -171,9 +173,9 @@ int cab_conv1d_wgrad(const void* a, int a_T, int a_T_rows, int a_ld, int M_total
 #define CAB_BN_SUM_REPLICAS 8
 int cab_bn_batch_stats(const void* y, int B, int T, int C, int ld, const float* gamma, const float* beta,
                        float eps, float momentum, float* running_mean, float* running_var,
-                       float* ws_sums, float* out_ss, cab_stream_t stream);
+                       double* ws_sums, float* out_ss, cab_stream_t stream);
 /* same as cab_bn_batch_stats but from sums the conv epilogue already accumulated (cab_conv_epilogue_t.stats) */
-int cab_bn_finalize(const float* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
+int cab_bn_finalize(const double* sums, int n_rows, int C, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* out_ss,
                     cab_stream_t stream);
 /* *_lo: NULL, or the bf16 residual halves of the split-bf16 "fp32" tier (value = hi + lo) -- all of a call's
@@ -187,12 +189,12 @@ int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, c
                         const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
                         const float* xlen_frac, float* sums, void* grad_y, void* grad_y_lo, float dropout_p,
                         const int64_t* seed, int64_t salt, int frozen,
-                        float* ws_partials /* fp32 [CAB_BN_SUM_REPLICAS][2][C] scratch, or NULL */,
+                        double* ws_partials /* fp64 [CAB_BN_SUM_REPLICAS][2][C] scratch, or NULL */,
                         cab_stream_t stream);
 /* cab_bn_finalize + cab_bn_act_mask_fwd in one launch: every CTA derives the coefficients of its channels from
  * the raw sums of the conv epilogue (raw_sums: fp32 [2][sums_ld]); CTA 0 also writes out_ss and moves the
  * running statistics. */
-int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const float* raw_sums, int sums_ld, int n_rows,
+int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const double* raw_sums, int sums_ld, int n_rows,
                               const float* gamma, const float* beta, float eps, float momentum,
                               float* running_mean, float* running_var, float* out_ss, int B, int T, int C,
                               int ld, int act, float act_a, float act_b, const float* xlen_frac, void* out,
@@ -241,6 +243,13 @@ int cab_pack_weights_batched(const cab_pack_item_t* items_host, int n_items, cab
  * (pair_pad = the conv's padding, pair_ci_alloc = channels per pair half) */
 int cab_unpack_wgrad(const float* packed, int K, int Co, int Ci, int ld, int transposed, float* grad,
                      int accumulate, int pair_pad, int pair_ci_alloc, cab_stream_t stream);
+/* the same for up to 32 gradients in one launch (every layer of a model at the end of the backward) */
+typedef struct {
+    const float* packed; /* fp32 packed gradient as cab_conv1d_wgrad wrote it */
+    float* grad;         /* fp32 [Co, Ci, K] */
+    int32_t K, Co, Ci, ld, transposed, pair_pad, pair_ci_alloc;
+} cab_unpack_item_t;
+int cab_unpack_wgrad_batched(const cab_unpack_item_t* items_host, int n_items, cab_stream_t stream);
 /* fp32 [B,C,T] (gradient w.r.t. the logits) -> bf16 channels-last [B,T,ld]; class_sums (fp32 [C],
  * optional) receives the sums over (b,t) = the decoder bias gradient. */
 int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, void* out_lo, float* class_sums,
@@ -258,8 +267,8 @@ int cab_bct_to_btc(const float* x, int B, int C, int T, int ld, void* out, void*
  *   (int64 [n]) and a flat chunk list (tensor index int32 [n_chunks], element offset int64
  *   [n_chunks], chunk_elems elements per chunk, multiple of 4).  ema: fp32 [n] NovoGrad state.
  *   step_cell: int64 device cell counting steps (0 = first step initialises ema / momentum);
- *   lr_dev: fp32 device scalar (so CUDA-graph replays can change it); ws_*: workspaces of n floats /
- *   one int32; total_norm_out: fp32 [1] or NULL (pre-clip global gradient norm).
+ *   lr_dev: fp32 device scalar (so CUDA-graph replays can change it); ws_sumsq: n + n_chunks floats (per-tensor sums, then the
+ *   per-chunk partials they are summed from in a fixed order: no atomics, bit-reproducible norms), ws_scale: n floats, ws_first: one int32; total_norm_out: fp32 [1] or NULL (pre-clip global gradient norm).
  * ------------------------------------------------------------------------------------- */
 int cab_optimizer_step(int mode, int n_tensors, const int64_t* param_ptrs, const int64_t* grad_ptrs,
                        const int64_t* mom_ptrs, const int64_t* numels, int n_chunks,
@@ -344,7 +353,7 @@ int cab_topk_ids(const float* log_probs, int B, int C, int T, int K, int32_t* ou
 
 /* ---------------------------------------------------------------------------------------
  * A14: the collapse state machine of GreedyCTCGenerator.generate
- *   (transcript_generators.py:32-83) on device: one utterance per thread.
+ *   (transcript_generators.py:32-83) on device: a segmented warp scan, one utterance per warp.
  *   ids: int32 [B, T] per-frame argmax; lengths: int32 [B] (loop bound, "sample_len").
  *   is_silence / is_word_start: uint8 [C] token class tables.
  *   out_tokens / out_frames: int32 [B, T_cap]; out_frames[i] is the frame the token came
@@ -361,6 +370,10 @@ int cab_greedy_collapse(const int32_t* ids, const int32_t* lengths, int B, int T
  * section 8(f) "next" #1: uncertainty reductions on log_probs (models.py:645-678), fused:
  *   per utterance entropy (masked mean) and weighted_mean_entropy with eps_id weights.
  * ------------------------------------------------------------------------------------- */
+/* models.margin (models.py:676-677): the two largest probabilities per frame, out fp32 [B, 2, T] = exp(top-2 of log_probs over
+ * the class dim); log_probs [B, C, T] through element strides. */
+int cab_top2_probs(const float* log_probs, int64_t stride_b, int64_t stride_c, int64_t stride_t, int B, int C, int T,
+                   float* out, cab_stream_t stream);
 int cab_entropy(const float* log_probs, const int64_t* lengths, int B, int C, int T, int eps_id,
                 float* out_entropy, float* out_weighted_entropy, cab_stream_t stream);
 

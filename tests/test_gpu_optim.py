@@ -82,3 +82,48 @@ def test_schedulers_host_logic():
 		poly.step(s)
 		vals.append(round(opt2.param_groups[0]['lr'], 6))
 	assert vals == [0.0, 0.45, 0.8, 0.5, 0.0, 0.0]
+
+
+def test_novograd_matches_the_reference_optimizer_golden(golden):
+	"""NovoGrad against parameter trajectories minted by the REFERENCE's own optimizers.NovoGrad (optimizers.py:66-90,
+	oracle/make_golden.py: golden_misc): weight decay, dampening, three steps with growing gradients"""
+	from convasr_b200 import optimizers
+	dev = torch.device('cuda:0')
+	for c in golden('misc')['novograd']:
+		mine = [p.clone().to(dev).requires_grad_(True) for p in c['p0']]
+		opt = optimizers.NovoGrad(mine, lr = c['lr'], betas = c['betas'], weight_decay = c['weight_decay'], dampening = c['dampening'])
+		for st in c['steps']:
+			for q, gr in zip(mine, st['grads']):
+				q.grad = gr.clone().to(dev)
+			opt.step()
+			for q, p in zip(mine, st['params']):
+				assert torch.allclose(q.detach().cpu(), p, rtol = 2e-5, atol = 1e-6), (c['weight_decay'], c['dampening'])
+
+
+def test_clip_norm_is_global_over_parameter_groups_and_survives_changes():
+	"""clip_grad_norm_ is one norm over ALL parameters (train.py:776-779), also with several param groups; the
+	cached tables follow a changing set of tensors with gradients and a load_state_dict after the first step"""
+	from convasr_b200 import optimizers
+	dev = torch.device('cuda:0')
+	ps, g = _tensors(3)
+	ref = [p.clone().requires_grad_(True) for p in ps]
+	mine = [p.clone().to(dev).requires_grad_(True) for p in ps]
+	groups = lambda t: [dict(params = t[:3], lr = 0.05), dict(params = t[3:], lr = 0.01, weight_decay = 1e-2)]
+	opt_ref = torch.optim.SGD(groups(ref), lr = 0.05, momentum = 0.9)
+	opt = optimizers.SGD(groups(mine), lr = 0.05, momentum = 0.9)
+	for step in range(5):
+		grads = [torch.randn(p.shape, generator = g) * 2.0 for p in ps]
+		for i, (p, q, gr) in enumerate(zip(ref, mine, grads)):
+			skip = step in (2, 3) and i == 1  # a tensor without a gradient for two steps, then back
+			p.grad = None if skip else gr.clone()
+			q.grad = None if skip else gr.clone().to(dev)
+		total = torch.nn.utils.clip_grad_norm_(ref, 3.0)
+		opt_ref.step()
+		opt.step(max_grad_norm = 3.0)
+		assert torch.allclose(opt.total_grad_norm.cpu(), total.reshape(1), rtol = 1e-5), step
+		for p, q in zip(ref, mine):
+			assert torch.allclose(q.detach().cpu(), p.detach(), rtol = 1e-5, atol = 1e-6), (step, p.shape)
+		if step == 1:  # checkpoint round trip in the middle: momentum must carry over
+			sd = opt.state_dict()
+			opt = optimizers.SGD(groups(mine), lr = 0.05, momentum = 0.9)
+			opt.load_state_dict(sd)

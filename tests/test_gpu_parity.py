@@ -392,3 +392,185 @@ def test_tiny_utterances_in_a_ragged_batch(dev):
 		n = int(olen[k])
 		bias = m.decoder[0].bias.detach()
 		assert torch.allclose(logits[k][:, n:], bias[:, None].expand(-1, logits.shape[2] - n), atol = 1e-6)
+
+
+def test_greedy_collapse_warp_scan_equals_the_serial_state_machine(dev):
+	"""the segmented warp scan of cab_greedy_collapse against a line-by-line transcription of the reference's loop
+	(transcript_generators.py:32-83) on random id rows: blank / space / repeat densities, ragged lengths, frame counts that are
+	not multiples of 32, word-start tables with extra tokens (BPE-style), tiny output capacity"""
+	from convasr_b200 import ops
+	g = torch.Generator().manual_seed(12)
+	for C, T, B, K in ((38, 97, 300, 10), (12, 64, 200, 3), (50, 333, 100, 10), (38, 31, 50, 2)):
+		eps, space = C - 1, C - 2
+		pool = torch.tensor([0, 1, 2, 3, space, space] + [eps] * 14)
+		ids = pool[torch.randint(0, len(pool), (B, T), generator = g)]
+		ids[: B // 4] = torch.randint(0, C, (B // 4, T), generator = g)  # dense tokens, few blanks
+		ids[B // 4] = eps  # nothing but silence
+		lens = torch.randint(0, T + 1, (B, ), generator = g)
+		lens[0] = T
+		sil = torch.zeros(C, dtype = torch.uint8); sil[eps] = sil[space] = 1
+		ws = torch.zeros(C, dtype = torch.uint8); ws[space] = 1; ws[1] = 1  # token 1 also starts words
+		tok, frm, cnt = ops.greedy_collapse(ids.int().to(dev), lens.to(dev), C, eps, space, sil.to(dev), ws.to(dev), K)
+		tok, frm, cnt = tok.cpu(), frm.cpu(), cnt.cpu()
+		for b in range(B):
+			row = ids[b].tolist()
+			t = 0
+			while t < T and sil[row[t]]:
+				t += 1
+			if t >= T:
+				assert int(cnt[b]) == -1, b
+				continue
+			tokens, frames, allow_repeat, count_eps = [eps], [None], False, 0
+			for t in range(t, int(lens[b])):
+				x = row[t]
+				if x == eps and tokens[-1] == space:
+					continue
+				if x == eps:
+					allow_repeat = True
+					count_eps += 1
+					if count_eps >= K and not ws[tokens[-1]]:
+						tokens.append(space); frames.append(-(t + 1))
+					continue
+				elif x == tokens[-1] and not allow_repeat:
+					continue
+				allow_repeat = False
+				tokens.append(x); frames.append(t)
+				count_eps = 0
+			n = len(tokens) - 1
+			assert int(cnt[b]) == n, (b, int(cnt[b]), n)
+			assert tok[b, :n].tolist() == tokens[1:] and frm[b, :n].tolist() == frames[1:], b
+
+
+# ---------------------------------------------------------------- small parity holes closed in round 2
+def test_uncertainty_reductions_against_reference_golden(golden, dev):
+	"""entropy / weighted_mean_entropy / margin (models.py:645-678) against outputs of the reference itself"""
+	from convasr_b200 import models
+	for c in golden('misc')['uncertainty']:
+		lp, lens = c['log_probs'].to(dev), c['lengths'].to(dev)
+		C = lp.shape[1]
+		assert torch.allclose(models.entropy(lp, lens, dim = 1).cpu(), c['entropy'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(models.entropy(lp, None, dim = 1).cpu(), c['entropy_nolen'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(models.weighted_mean_entropy(lp, lens, dim = -2, eps_id = C - 1).cpu(), c['wme'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(models.weighted_mean_entropy(lp, None, dim = -2, eps_id = C - 1).cpu(), c['wme_nolen'], rtol = 1e-5, atol = 1e-6)
+		assert torch.allclose(models.margin(lp[:2], dim = 1).cpu(), c['margin'], rtol = 1e-5, atol = 1e-7)
+		with pytest.raises(TypeError):  # the reference unpacks the batch dimension: only B == 2 is defined
+			models.margin(torch.cat([lp, lp])[:3], dim = 1)
+		# the permuted view the large-vocabulary head returns gives the same numbers
+		lpv = lp.permute(0, 2, 1).contiguous().permute(0, 2, 1)
+		assert torch.allclose(models.margin(lpv[:2]).cpu(), c['margin'], rtol = 1e-5, atol = 1e-7)
+
+
+def test_two_head_bpe_decoder_against_reference_golden(golden, dev):
+	"""Decoder(type = 'bpe') (models.py:27-44): head 0 = 1x1 conv, head 1 = two ConvBn1d(k = 15, relu, no mask); loss = sum of the
+	heads' CTC losses, every head divided by ylen[:, 0] (models.py:323)"""
+	from convasr_b200 import models
+	c = golden('misc')['bpe']
+	m = models.Wav2Letter(64, list(c['num_classes']), frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, **c['kwargs'])
+	assert {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')} == c['shapes']
+	m.load_state_dict(O.synth_state_dict(c['shapes'], seed = c['seed']), strict = False)
+	m = m.to(dev).eval()
+	for precision, tol in (('fp32', 1e-3), ('bf16', 2e-2)):
+		m.set_precision(precision)
+		with torch.no_grad():
+			out = m(c['signal'].to(dev), c['xlen'].to(dev), y = c['y'].to(dev), ylen = c['ylen'].to(dev))
+		assert len(out['logits']) == 2
+		for h in range(2):
+			assert torch.equal(out['olen'][h].cpu(), c['olen'][h])
+			assert rel(out['logits'][h], c['logits'][h]) < tol, (precision, h, rel(out['logits'][h], c['logits'][h]))
+			assert rel(out['log_probs'][h], c['log_probs'][h]) < tol
+		assert torch.allclose(out['loss'].cpu(), c['loss'], rtol = 5 * tol, atol = 5 * tol)
+	m.bpe_only = True
+	with torch.no_grad():
+		only = m(c['signal'].to(dev), c['xlen'].to(dev), y = c['y'].to(dev), ylen = c['ylen'].to(dev))
+	assert float(only['loss'].sum()) < float(out['loss'].sum())
+
+
+def test_bf16_tier_greedy_id_and_text_agreement_is_reported(golden, dev, capsys):
+	"""bf16 tier vs the reference's fp32 outputs on the golden model cases: fraction of valid frames whose greedy id agrees, and
+	the character error rate between the collapsed texts (ids are only guaranteed bit-exact on identical logits; this is the
+	measured cost of the speed tier)"""
+	from convasr_b200 import models, transcript_generators
+	tok = O.CharTokenizer('абвгдеёжзийклмнопрстуфхцчшщъыьэюя')
+	gen = transcript_generators.GreedyCTCGenerator()
+
+	def edit(a, b):
+		d = list(range(len(b) + 1))
+		for i, ca in enumerate(a, 1):
+			p, d[0] = d[0], i
+			for j, cb in enumerate(b, 1):
+				p, d[j] = d[j], min(d[j] + 1, d[j - 1] + 1, p + (ca != cb))
+		return d[-1]
+
+	lines = []
+	for c in golden('models')['cases']:
+		if c['num_classes'] != 38:
+			continue
+		m = getattr(models, c['model'])(64, [38], frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False, **c['kwargs'])
+		m.load_state_dict(O.synth_state_dict(c['shapes'], seed = c['seed']), strict = False)
+		m = m.to(dev).eval()
+		ref_ids = c['log_probs'].argmax(1)
+		B = ref_ids.shape[0]
+		ref_txt = O.greedy_generate(tok, ref_ids.tolist(), c['olen'].tolist(), None, [0.0] * B, [1.0] * B)
+		for precision in ('fp32', 'bf16'):
+			m.set_precision(precision)
+			with torch.no_grad():
+				out = m(c['signal'].to(dev), c['xlen'].to(dev))
+			ids = out['log_probs'][0]._convasr_argmax.long().cpu()
+			valid = torch.arange(ids.shape[1])[None] < c['olen'][:, None]
+			agree = float((ids == ref_ids)[valid].float().mean())
+			tr = gen.generate(tok, out['log_probs'][0], begin = torch.zeros(B, device = dev), end = torch.ones(B, device = dev), output_lengths = out['olen'][0])
+			hyp = [' '.join(s['hyp'] for s in t[0]) for t in tr]
+			ref = [' '.join(s[2] for s in t) for t in ref_txt]
+			cer = sum(edit(h, r) for h, r in zip(hyp, ref)) / max(1, sum(len(r) for r in ref))
+			lines.append(f'{c["model"]:20s} fused={c["fused"]} {precision}: greedy-id agreement {agree:.4f}, CER vs reference text {cer:.4f}')
+			if precision == 'fp32':
+				assert agree > 0.999 and cer < 1e-3, lines[-1]
+			else:
+				assert agree > 0.9, lines[-1]
+	with capsys.disabled():
+		print('\ngreedy decode agreement with the reference (random-init weights: near-uniform posteriors, worst case for argmax ties):\n  ' + '\n  '.join(lines))
+
+
+def test_dropin_modules_run_a_transcribe_shaped_flow(golden, dev):
+	"""`PYTHONPATH=convasr_b200/dropin`: the bare-name modules the reference's callers import (transcribe.py:27-52,140-196;
+	train.py:428-435) resolve to this repo's implementation and run the caller's flow: frontend + model factory with the
+	`dict =` callable and check_time_dim_padded, fuse_conv_bn_eval, forward, GreedyCTCGenerator.generate, ctc.alignment"""
+	import importlib
+	import os
+	import sys
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	dropin = os.path.join(root, 'convasr_b200', 'dropin')
+	saved = {n: sys.modules.pop(n, None) for n in ('models', 'ctc', 'decoders', 'transcript_generators', 'optimizers')}
+	sys.path.insert(0, dropin)
+	try:
+		models, ctc, decoders, transcript_generators, optimizers = [importlib.import_module(n) for n in ('models', 'ctc', 'decoders', 'transcript_generators', 'optimizers')]
+		assert os.path.dirname(models.__file__) == dropin
+		c = golden('models')['cases'][0]
+		frontend = models.LogFilterBankFrontend(out_channels = 64, sample_rate = 8000, window_size = .02, window_stride = .01, window = 'hann_window', dither = 0.0, dither0 = 0.0, stft_mode = None)
+		model = getattr(models, 'Wav2Letter')(num_input_features = 64, num_classes = [38], frontend = frontend, check_time_dim_padded = False,
+												dict = lambda logits, log_probs, olen, **kwargs: (log_probs[0], logits[0], olen[0]), **c['kwargs'])  # transcribe.py:44-52
+		model.load_state_dict(O.synth_state_dict(c['shapes'], seed = c['seed']), strict = False)
+		model.to(dev)
+		model.eval()
+		model.fuse_conv_bn_eval()  # transcribe.py:56
+		model, _ = models.data_parallel_and_autocast(model, opt_level = None, data_parallel = False)
+		x, xlen = c['signal'].unsqueeze(1), c['xlen']
+		with torch.no_grad():
+			log_probs, logits, olen = model(x.squeeze(1).to(dev), xlen.to(dev))  # transcribe.py:140
+		assert rel(logits, c['logits']) < 1e-3 and torch.equal(olen.cpu(), c['olen'])
+		tok = O.CharTokenizer('абвгдеёжзийклмнопрстуфхцчшщъыьэюя')
+		B = len(x)
+		tr = transcript_generators.GreedyCTCGenerator().generate(tokenizer = tok, log_probs = log_probs, begin = torch.zeros(B, device = dev), end = torch.ones(B, device = dev), output_lengths = olen, time_stamps = None, segment_text_key = 'hyp')
+		ref = O.greedy_generate(tok, log_probs.argmax(1).cpu().tolist(), olen.tolist(), None, [0.0] * B, [1.0] * B)
+		assert [[s['hyp'] for s in t[0]] for t in tr] == [[s[2] for s in t] for t in ref]
+		assert decoders.GreedyDecoder().decode(log_probs, olen) == O.greedy_decode(log_probs.cpu(), olen.cpu())
+		y, ylen = c['y'][:, 0].to(dev), c['ylen'][:, 0].to(dev)
+		al = ctc.alignment(log_probs.permute(2, 0, 1), y, olen, ylen, blank = 37, pack_backpointers = False)  # transcribe.py:176-183
+		assert torch.equal(al.cpu(), O.ctc_alignment(log_probs.cpu().permute(2, 0, 1), y.cpu(), olen.cpu(), ylen.cpu(), 37))
+		assert hasattr(optimizers, 'NovoGrad') and hasattr(models, 'entropy') and hasattr(models, 'margin')
+	finally:
+		sys.path.remove(dropin)
+		for n, mod in saved.items():
+			sys.modules.pop(n, None)
+			if mod is not None:
+				sys.modules[n] = mod

@@ -55,13 +55,13 @@ def test_bn_act_mask_forward_backward_kernels():
 		o.backward(go)
 		# native
 		yd = cl(y).to(dev)
-		ws = torch.empty(2, C, device = dev); ss = torch.empty(4, C, device = dev)
+		ws = torch.empty(2, C, dtype = torch.float64, device = dev); ss = torch.empty(4, C, device = dev)
 		rm_d, rv_d, gamma_d, beta_d, go_d = rm.to(dev), rv.to(dev), gamma.to(dev), beta.to(dev), cl(go).to(dev)  # keep alive: raw pointers below
 		_lib.check(lib.cab_bn_batch_stats(ops._p(yd), B, T, C, C, ops._p(gamma_d), ops._p(beta_d), 1e-5, 0.1, ops._p(rm_d), ops._p(rv_d), ops._p(ws), ops._p(ss), ops._stream()), 'stats')
 		out = torch.empty_like(yd)
 		xl = xlen.to(dev)
 		_lib.check(lib.cab_bn_act_mask_fwd(ops._p(yd), None, ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(out), None, 0.0, None, 0, ops._stream()), 'fwd')
-		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+		sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, dtype = torch.float64, device = dev)
 		_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), None, ops._p(go_d), None, ops._p(ss), B, T, C, C, code, a, b, ops._p(xl), ops._p(sums), ops._p(dy), None, 0.0, None, 0, 0, ops._p(part), ops._stream()), 'bwd')
 		# without the replica scratch the row-walker variant runs: same results
 		sums2 = torch.empty(2, C, device = dev); dy2 = torch.empty_like(yd)
@@ -86,7 +86,7 @@ def test_dropout_in_bn_act_kernels():
 	go = torch.randn(B, C, T, generator = g).to(BF16).float()
 	gamma, beta = torch.rand(C, generator = g) + 0.5, torch.randn(C, generator = g) * 0.1
 	yd, go_d, gamma_d, beta_d = cl(y).to(dev), cl(go).to(dev), gamma.to(dev), beta.to(dev)
-	ws = torch.empty(2, C, device = dev); ss = torch.empty(4, C, device = dev)
+	ws = torch.empty(2, C, dtype = torch.float64, device = dev); ss = torch.empty(4, C, device = dev)
 	_lib.check(lib.cab_bn_batch_stats(ops._p(yd), B, T, C, C, ops._p(gamma_d), ops._p(beta_d), 1e-5, 0.1, None, None, ops._p(ws), ops._p(ss), ops._stream()), 'stats')
 	seed = torch.tensor([1234], dtype = torch.int64, device = dev)
 	outs = []
@@ -106,7 +106,7 @@ def test_dropout_in_bn_act_kernels():
 	# backward against autograd with the recovered mask
 	mask = torch.where(pos, (outs[0] != 0).float(), torch.ones_like(z)) / (1 - p)  # where z ~ 0 the mask is irrelevant
 	(z * mask).backward(go)
-	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+	sums = torch.empty(2, C, device = dev); dy = torch.empty_like(yd); part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, dtype = torch.float64, device = dev)
 	_lib.check(lib.cab_bn_act_mask_bwd(ops._p(yd), None, ops._p(go_d), None, ops._p(ss), B, T, C, C, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(sums), ops._p(dy), None, p, ops._p(seed), 3, 0, ops._p(part), ops._stream()), 'bwd')
 	torch.cuda.synchronize()
 	assert rel(dy.float().permute(0, 2, 1), yr.grad) < 2e-2
@@ -282,33 +282,37 @@ def _grad_sync_worker(rank, world, port, tmp):
 	dev = torch.device('cuda', rank)
 	C = 38
 	batches = [[t.to(dev) for t in _batch(C, seed = 3 + k)] for k in range(world)]
-	# per-rank gradients without any exchange, from identical weights and BN state
-	m, sd = _model(dev, dict(base_width = 32, num_blocks = 1))
-	expect = None
-	for k in range(world):
+	# per-rank gradients without any exchange, from identical weights and BN state; then the data-parallel replica: same
+	# module, gradients averaged inside the native backward.  Both precision tiers at 1e-5: the BatchNorm statistics (forward
+	# and backward) are accumulated in fp64, so the forward pass is bit-reproducible run to run and GPU to GPU and the only
+	# difference left is the order of the fp32 split-K reductions of the weight gradients (measured 6e-8 on 2 x B200).  With
+	# the fp32 atomics of round 1 a flipped bf16 rounding / activation gate cost 2e-3 .. 9e-3 here.
+	measured = {}
+	for precision, bound in (('fp32', 1e-5), ('bf16', 1e-5)):
+		m, sd = _model(dev, dict(base_width = 32, num_blocks = 1), precision = precision)
+		expect = None
+		for k in range(world):
+			m.load_state_dict(sd, strict = False)
+			m.zero_grad(set_to_none = True)
+			sig, xlen, y, ylen = batches[k]
+			out = m(sig, xlen, y = y, ylen = ylen)
+			(out['loss'] * ylen[:, 0]).mean().backward()
+			g = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+			expect = g if expect is None else {n: expect[n] + g[n] for n in g}
 		m.load_state_dict(sd, strict = False)
 		m.zero_grad(set_to_none = True)
-		sig, xlen, y, ylen = batches[k]
-		out = m(sig, xlen, y = y, ylen = ylen)
+		net, _ = models.distributed_data_parallel_and_autocast(m, rank, opt_level = 'O2' if precision == 'bf16' else None)
+		assert net is m and isinstance(m._grad_sync, parallel.GradSync) and m._active_precision() == precision
+		sig, xlen, y, ylen = batches[rank]
+		out = net(sig, xlen, y = y, ylen = ylen)
 		(out['loss'] * ylen[:, 0]).mean().backward()
-		g = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
-		expect = g if expect is None else {n: expect[n] + g[n] for n in g}
-	# the data-parallel replica: same module, gradients averaged inside the native backward
-	m.load_state_dict(sd, strict = False)
-	m.zero_grad(set_to_none = True)
-	net, _ = models.distributed_data_parallel_and_autocast(m, rank)
-	assert net is m and isinstance(m._grad_sync, parallel.GradSync)
-	sig, xlen, y, ylen = batches[rank]
-	out = net(sig, xlen, y = y, ylen = ylen)
-	(out['loss'] * ylen[:, 0]).mean().backward()
-	torch.cuda.synchronize()
-	assert m._grad_sync.n_collectives == 6 + 1 + 1  # one per conv layer, the decoder, the flat small-tensor buffer
-	for n, p in m.named_parameters():
-		if n in expect:
-			# not bit-equal: the BN statistics and split-K sums use fp32 atomics, and an ulp there can flip a bf16
-			# rounding that the backward then amplifies (measured 2.4e-3 on the first layer); a wrong exchange
-			# (sum instead of mean, a missing rank) would be off by >= 50 %
-			assert rel(p.grad, expect[n] / world) < 1e-2, (n, rel(p.grad, expect[n] / world))
+		torch.cuda.synchronize()
+		assert m._grad_sync.n_collectives == 6 + 1 + 1  # one per conv layer, the decoder, the flat small-tensor buffer
+		errs = sorted(((rel(p.grad, expect[n] / world), n) for n, p in m.named_parameters() if n in expect), reverse = True)
+		worst = errs[0][0]
+		measured[precision] = worst
+		assert worst < bound, (precision, errs[:4])
+	print(f'rank {rank}: averaged gradients vs mean of per-rank gradients, worst tensor: {measured}', flush = True)
 	# whole step as a CUDA graph with the all-reduces captured inside: replicas stay bit-identical
 	opt = optimizers.SGD([p for p in m.parameters() if p.requires_grad], lr = 1e-3, momentum = 0.9)
 	step = training.GraphedTrainStep(net, opt, sig, xlen, y, ylen, warmup = 2, max_grad_norm = 100.0)
@@ -354,12 +358,12 @@ def test_padding_tiles_are_skipped_exactly():
 	outs = []
 	for skip in (None, (xlen, T, pad)):
 		y = torch.full((B, T, Co), float('nan'), dtype = BF16, device = dev)
-		st = torch.empty(2, Co, device = dev)
+		st = torch.empty(2, Co, dtype = torch.float64, device = dev)
 		ops.conv1d_fused([ops.Source(x, w_fwd, Ci, K, 1, pad, T_in = T)], B, T, Co, out_hi = y, stats = st, skip = skip)
 		outs.append((y, st))
 	torch.cuda.synchronize()
 	assert torch.equal(outs[0][0], outs[1][0])
-	assert torch.allclose(outs[0][1], outs[1][1], rtol = 1e-5, atol = 1e-4)  # fp32 atomics: order of the partial sums differs
+	assert torch.allclose(outs[0][1], outs[1][1], rtol = 1e-12, atol = 1e-9)  # fp64 accumulators: only the order of the partial sums differs
 	assert bool((outs[1][0][3, 200:] == 0).all())  # utterance 3: 35 valid frames, tiles 2.. are pure padding
 	# with the launch's own temporal mask the skip is implied
 	ym = [torch.empty(B, T, Co, dtype = BF16, device = dev) for _ in range(2)]
@@ -509,10 +513,10 @@ def test_multi_branch_bn_kernels_against_autograd():
 			xl = xlen.to(dev)
 			sss = []
 			for i in range(2):
-				ws = torch.empty(2, C, device = dev); ss = torch.empty(4, C, device = dev)
+				ws = torch.empty(2, C, dtype = torch.float64, device = dev); ss = torch.empty(4, C, device = dev)
 				# statistics from the fp32 values (the conv epilogue accumulates hi + lo in the split tier)
 				yf = (y_d[i][0].float() + (y_d[i][1].float() if split else 0)).reshape(-1, C)
-				sums = torch.stack([yf.sum(0), (yf * yf).sum(0)]).contiguous()
+				sums = torch.stack([yf.double().sum(0), (yf.double() * yf.double()).sum(0)]).contiguous()
 				gd, bd = gammas[i].to(dev), betas[i].to(dev)
 				_lib.check(lib.cab_bn_finalize(ops._p(sums), B * T, C, ops._p(gd), ops._p(bd), 1e-5, 0.1, None, None, ops._p(ss), ops._stream()), 'finalize')
 				sss.append(ss)
@@ -526,7 +530,7 @@ def test_multi_branch_bn_kernels_against_autograd():
 			val = lambda hi, lo: (hi.float() + (lo.float() if lo is not None else 0)).permute(0, 2, 1)
 			assert rel(val(out_hi, out_lo), o) < tol, (act_name, split, rel(val(out_hi, out_lo), o))
 			assert rel(val(dz_hi, dz_lo), yr[2].grad) < tol, (act_name, split)  # the identity branch receives dz itself
-			part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, device = dev)
+			part = torch.empty(_lib.BN_SUM_REPLICAS, 2, C, dtype = torch.float64, device = dev)
 			for i in range(2):
 				sums = torch.empty(2, C, device = dev); dy_hi = torch.empty_like(out_hi); dy_lo = torch.empty_like(out_hi) if split else None
 				_lib.check(lib.cab_bn_act_mask_bwd(ops._p(y_d[i][0]), ops._p(y_d[i][1]), ops._p(dz_hi), ops._p(dz_lo), ops._p(sss[i]), B, T, C, C, _lib.ACT_NONE, 0.0, 0.0, None, ops._p(sums), ops._p(dy_hi), ops._p(dy_lo),
