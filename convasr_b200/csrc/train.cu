@@ -749,27 +749,36 @@ struct UnpackBatch {
 };
 __global__ void __launch_bounds__(256)
 unpack_wgrad_batched_kernel(const UnpackBatch ub) {
+    extern __shared__ float ut[];  // [256 (co, ci) pairs][K] in parameter order
     int item = 0;
     while (item + 1 < ub.n && (int)blockIdx.x >= ub.block_start[item + 1]) ++item;
     const int K = ub.K[item], Co = ub.Co[item], Ci = ub.Ci[item], ld = ub.ld[item], mode = ub.mode[item];
     const float* __restrict__ packed = ub.packed[item];
     float* __restrict__ grad = ub.grad[item];
-    const long long idx = (long long)(blockIdx.x - ub.block_start[item]) * 256 + threadIdx.x;
-    if (idx >= (long long)Co * Ci) return;
-    const int co = (int)(idx / Ci), ci = (int)(idx - (long long)co * Ci);
-    float* dst = grad + idx * K;
-    if (mode == 2) {
-        const int pad = ub.pair_pad[item], ca = ub.pair_ci_alloc[item];
-        const int dp_min = floordiv2(-pad);
-        for (int k = 0; k < K; ++k) {
-            const int j = k - pad, dp = floordiv2(j), q = j - 2 * dp;
-            dst[k] = packed[((size_t)(dp - dp_min) * Co + co) * ld + q * ca + ci];
+    const long long base = (long long)(blockIdx.x - ub.block_start[item]) * 256;
+    const long long total = (long long)Co * Ci;
+    const long long idx = base + threadIdx.x;
+    if (idx < total) {
+        const int co = (int)(idx / Ci), ci = (int)(idx - (long long)co * Ci);
+        float* dst = ut + threadIdx.x * K;  // stride K: K odd for every conv of the model zoo -> conflict free
+        if (mode == 2) {
+            const int pad = ub.pair_pad[item], ca = ub.pair_ci_alloc[item];
+            const int dp_min = floordiv2(-pad);
+            for (int k = 0; k < K; ++k) {
+                const int j = k - pad, dp = floordiv2(j), q = j - 2 * dp;
+                dst[k] = packed[((size_t)(dp - dp_min) * Co + co) * ld + q * ca + ci];
+            }
+        } else if (mode == 1) {
+            for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Ci + ci) * ld + co];
+        } else {
+            for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Co + co) * ld + ci];
         }
-    } else if (mode == 1) {
-        for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Ci + ci) * ld + co];
-    } else {
-        for (int k = 0; k < K; ++k) dst[k] = packed[((size_t)k * Co + co) * ld + ci];
     }
+    __syncthreads();
+    // the block's 256 * K outputs are one contiguous span of the parameter-layout gradient
+    const long long n_out = (total - base < 256 ? total - base : 256) * K;
+    float* out = grad + base * K;
+    for (long long i = threadIdx.x; i < n_out; i += 256) out[i] = ut[i];
 }
 
 // fp32 [B, C, T] -> bf16 channels-last [B, T, ld] (zero padded channels) + per-class sums over (b, t)
@@ -1171,7 +1180,16 @@ extern "C" int cab_unpack_wgrad_batched(const cab_unpack_item_t* items, int n, c
     }
     ub.block_start[n] = blocks;
     ub.n = n;
-    unpack_wgrad_batched_kernel<<<blocks, 256, 0, stream>>>(ub);
+    int max_k = 1;
+    for (int i = 0; i < n; ++i) max_k = items[i].K > max_k ? items[i].K : max_k;
+    const size_t smem = sizeof(float) * 256 * max_k;
+    CAB_CHECK_ARG(smem <= 96 * 1024, "kernel size K=%d too large for the unpack tile", max_k);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        CAB_CHECK_CUDA(cudaFuncSetAttribute(unpack_wgrad_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    unpack_wgrad_batched_kernel<<<blocks, 256, smem, stream>>>(ub);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

@@ -123,6 +123,19 @@ class LogFilterBankFrontend(nn.Module):
 			denom_multiplier = self.debug_short_long_records_normalize_signal_multiplier
 		)
 
+	def features(self, signal, xlen, norm, F_pad_even, C_pad, want_lo):
+		"""signal -> instance-normalised bf16 channels-last features in one native call (what JasperNet.forward does at
+		models.py:286-301); norm: the model's MaskedInstanceNorm1d or None"""
+		mel, band, twiddle, window, log_eps = self._device_tables(signal.device)
+		Fr = signal.shape[1] // self.hop_length + 1
+		F_pad = Fr + (Fr % 2) if F_pad_even else Fr
+		hi, lo, _ = ops.frontend_features(
+			signal, xlen, window, mel, band, twiddle, self.hop_length, self.nfft, self.preemphasis, log_eps, self.normalize_signal,
+			self.debug_short_long_records_normalize_signal_multiplier, norm is not None, norm is not None and norm.temporal_mask, norm.eps if norm is not None else 0.0,
+			F_pad, C_pad, want_lo = want_lo
+		)
+		return hi, lo, Fr
+
 	@staticmethod
 	def compute_output_shape(time_dim_length, kernel_size, stride, padding, dilation = 1):
 		return int(math.floor((time_dim_length + 2 * padding - dilation * (kernel_size - 1) - 1) / stride + 1))
@@ -394,13 +407,11 @@ class JasperNet(nn.Module):
 		assert (not self.check_time_dim_padded) or (n_frames % 32 == 0), 'Shape of features after frontend is not divisible by 32'
 
 		if self.training:
-			if self.frontend is not None:
-				x = self.frontend(x, xlen = xlen)
 			from . import training
 			why = training.unsupported_reason(self)
 			if why is not None:
 				raise NotImplementedError(f'convasr_b200: training of this module tree is not built ({why}); there is no ATen / cuDNN fallback')
-			logits, log_probs = training.forward_training(self, x, xlen)  # conv/BN forward + backward on this repo's kernels
+			logits, log_probs = training.forward_training(self, x, xlen)  # frontend, conv/BN forward + backward on this repo's kernels
 		else:
 			logits, log_probs = self._forward_native(x, xlen)
 		olen = [compute_output_lengths(l, xlen) for l in logits]
@@ -451,11 +462,29 @@ class JasperNet(nn.Module):
 		graph.replay()
 		return [(lg.clone(), lp.clone(), am.clone()) for lg, lp, am in outs]
 
+	def _packed_features(self, x, xlen, want_lo):
+		"""raw input (signal when the frontend is in the model, else fp32 features [B, C, F]) -> (bf16 hi, lo or None, frames, channels):
+		log-mel frontend + masked instance norm + channels-last packing (models.py:286-301)"""
+		nf = self.normalize_features
+		if nf is not None and (nf.track_running_stats or nf.affine):
+			raise NotImplementedError('convasr_b200: instance norm with running stats / affine parameters is not built')
+		stride = self.backbone[0].conv[0][0].stride[0]
+		if self.frontend is not None and isinstance(self.frontend, LogFilterBankFrontend) and self.frontend.nfft == 256:
+			C = self.frontend.mel.weight.shape[0]
+			hi, lo, Fr = self.frontend.features(x, xlen, nf, stride == 2, engine._ceil_to(C, 64), want_lo)
+			return hi, lo, Fr, C
+		feats = self.frontend(x, xlen = xlen) if self.frontend is not None else x
+		B, C, Fr = feats.shape
+		F_pad = Fr + (Fr % 2) if stride == 2 else Fr
+		norm_xlen = xlen if (nf is not None and nf.temporal_mask) else None
+		hi, lo, _ = ops.instnorm_pack(feats, norm_xlen, nf.eps if nf is not None else -1.0, F_pad = F_pad, C_pad = engine._ceil_to(C, 64), want_lo = want_lo, normalize = nf is not None)
+		return hi, lo, Fr, C
+
 	def _raw_to_outputs(self, x, xlen):
 		"""raw input (signal or features) -> per head (logits, log_probs, argmax); kernels only"""
-		if self.frontend is not None:
-			x = self.frontend(x, xlen = xlen)
-		return self._features_to_outputs(x, xlen)
+		plan = self._get_plan()
+		hi, lo, Fr, C = self._packed_features(x, xlen, plan.fp32_tier)
+		return plan.run(engine._Act(hi, lo, Fr, C), xlen)
 
 	def _forward_native(self, x, xlen):
 		if getattr(self, '_graphs_enabled', False) and not torch.cuda.is_current_stream_capturing():
@@ -468,19 +497,6 @@ class JasperNet(nn.Module):
 			logits.append(lg)
 			log_probs.append(lp)
 		return tuple(logits), log_probs
-
-	def _features_to_outputs(self, feats, xlen):
-		plan = self._get_plan()
-		B, C, Fr = feats.shape
-		stride = self.backbone[0].conv[0][0].stride[0]
-		F_pad = Fr + (Fr % 2) if stride == 2 else Fr
-		C_pad = engine._ceil_to(C, 64)
-		nf = self.normalize_features
-		if nf is not None and (nf.track_running_stats or nf.affine):
-			raise NotImplementedError('convasr_b200: instance norm with running stats / affine parameters is not built')
-		norm_xlen = xlen if (nf is not None and nf.temporal_mask) else None
-		hi, lo, _ = ops.instnorm_pack(feats, norm_xlen, nf.eps if nf is not None else -1.0, F_pad = F_pad, C_pad = C_pad, want_lo = plan.fp32_tier, normalize = nf is not None)
-		return plan.run(engine._Act(hi, lo, Fr, C), xlen)
 
 	# -- reference utility surface --------------------------------------------------------
 	def freeze(self, backbone = 0, decoder0 = False, frontend = False):

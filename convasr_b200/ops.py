@@ -84,6 +84,35 @@ def frontend_logmel(
 	return out
 
 
+def frontend_features(signal, xlen, window, mel_fb, mel_band, twiddle, hop, nfft, preemphasis, log_eps, normalize_signal, denom_multiplier,
+					normalize_features, norm_masked, norm_eps, F_pad, C_pad, want_lo = False):
+	"""signal [B, T] int16 / fp32 -> (bf16 hi [B, F_pad, C_pad], bf16 lo or None, fp32 log-mel [B, n_mels, F]): frontend + masked
+	instance norm + layout change (cab_frontend_features)"""
+	_need_cuda(signal, xlen, window, mel_fb, mel_band, twiddle)
+	assert signal.ndim == 2
+	is_i16 = int(signal.dtype == torch.int16)
+	if not is_i16:
+		signal = signal.to(torch.float32)
+	signal = signal.contiguous()
+	B, T = signal.shape
+	n_mels = mel_fb.shape[0]
+	F = T // hop + 1
+	dev = signal.device
+	logmel = torch.empty(B, n_mels, F, dtype = torch.float32, device = dev)
+	hi = torch.empty(B, F_pad, C_pad, dtype = BF16, device = dev)
+	lo = torch.empty_like(hi) if want_lo else None
+	absmax = torch.empty(2 * B, dtype = torch.float32, device = dev)
+	partials = torch.empty(B, (F + 63) // 64 + 1, max(n_mels, 1), 2, dtype = torch.float32, device = dev)
+	xl = None if xlen is None else xlen.to(torch.float32).contiguous()
+	rc = _lib.load().cab_frontend_features(
+		_p(signal), is_i16, _p(xl), B, T, window.numel(), hop, nfft, n_mels, _p(window), _p(mel_fb), _p(mel_band), _p(twiddle), float(preemphasis), float(log_eps),
+		int(bool(normalize_signal)), float(denom_multiplier), int(bool(normalize_features)), int(bool(norm_masked)), float(norm_eps), _p(logmel), F_pad, C_pad, _p(hi), _p(lo), None,
+		_p(absmax), _p(partials), _stream()
+	)
+	_lib.check(rc, 'cab_frontend_features')
+	return hi, lo, logmel
+
+
 def instnorm_pack(feat, xlen, eps, F_pad = None, C_pad = None, want_lo = False, want_f32 = False, want_hi = None, normalize = True):
 	"""fp32 [B,C,F] -> (bf16 hi [B,F_pad,C_pad], bf16 lo or None, fp32 [B,C,F] or None)"""
 	_need_cuda(feat, xlen)

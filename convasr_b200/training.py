@@ -580,19 +580,14 @@ def _unpack(packed, K, Co, Ci, transposed, pair_pad = 0, pair_ci_alloc = 0):
 	return grad
 
 
-def forward_training(model, feats_f32, xlen):
-	"""normalised-feature input (fp32 [B, C, F]) -> (logits tuple, log_probs list) with autograd
-	through the native kernels"""
+def forward_training(model, x, xlen):
+	"""raw input (signal when the frontend is in the model, else fp32 features [B, C, F]) -> (logits tuple, log_probs list)
+	with autograd through the native kernels"""
 	split = model._active_precision() == 'fp32'  # fp32 parameters train in the split-bf16 tier unless set_precision('bf16') / an apex opt level says otherwise
 	reps = getattr(model, '_train_graph', None)
 	if reps is None:
 		reps = model._train_graph = _graph(model)
-	B, C, Fr = feats_f32.shape
-	stride = reps[0].conv.stride
-	F_pad = Fr + (Fr % 2) if stride == 2 else Fr
-	nf = model.normalize_features
-	norm_xlen = xlen if (nf is not None and nf.temporal_mask) else None
-	hi, lo, _ = ops.instnorm_pack(feats_f32, norm_xlen, nf.eps if nf is not None else -1.0, F_pad = F_pad, C_pad = engine._ceil_to(C, 64), want_lo = split, normalize = nf is not None)
+	hi, lo, Fr, C = model._packed_features(x, xlen, split)
 	params = []
 	for rep in reps:
 		if rep.grouped is not None:
@@ -608,7 +603,14 @@ def forward_training(model, feats_f32, xlen):
 		# device-resident dropout counter, initialised from torch's seed so torch.manual_seed controls it
 		seed = model._dropout_seed = torch.full((1, ), torch.initial_seed() & 0x7FFFFFFFFFFF, dtype = torch.int64, device = hi.device)
 	holder = dict(model = model, reps = reps, params = params, n_frames = Fr, seed = seed, split = split)
-	logits, log_probs, argmax = NativeStack.apply(holder, hi, lo, xlen, *params)
+	leaves = params
+	if getattr(model, '_alias_params', False):
+		# GraphedTrainStep: differentiate w.r.t. fresh aliases of the parameters (same storage).  A parameter's AccumulateGrad
+		# node is cached while any earlier autograd graph lives and remembers the stream it was created under; an eager step
+		# on the default stream whose outputs are still referenced would make the legacy stream wait on the capturing one.
+		leaves = [p.detach().requires_grad_(p.requires_grad) for p in params]
+		model._aliases = (params, leaves)
+	logits, log_probs, argmax = NativeStack.apply(holder, hi, lo, xlen, *leaves)
 	model._state_epoch = getattr(model, '_state_epoch', 0) + 1  # running statistics moved: cached eval plans are stale
 	log_probs._convasr_argmax = argmax
 	return (logits, ), [log_probs]
@@ -641,14 +643,20 @@ class GraphedTrainStep:
 	def _step(self):
 		sx, sxlen, sy, sylen = self.static
 		self.optimizer.zero_grad(set_to_none = True)
-		out = self.model(sx, sxlen, y = sy, ylen = sylen)
+		m = self.model.module if hasattr(self.model, 'module') else self.model
+		m._alias_params = True
+		try:
+			out = self.model(sx, sxlen, y = sy, ylen = sylen)
+		finally:
+			m._alias_params = False
 		loss = (out['loss'] * sylen[:, 0]).mean()  # train.py:754-755
-		# torch.autograd.grad instead of loss.backward(): no AccumulateGrad nodes run.  Those are cached per parameter and
-		# remember the stream they were created under; one left over from an eager step on the default stream (any live
-		# reference to that step's outputs keeps it) would make the legacy stream wait on the capturing stream -- illegal.
-		grads = torch.autograd.grad(loss, self.params, allow_unused = True)
-		for p, g in zip(self.params, grads):
+		# gradients w.r.t. the per-step aliases (see forward_training), handed to the parameters the optimizer knows
+		params, leaves = m._aliases
+		pairs = [(p, l) for p, l in zip(params, leaves) if l.requires_grad]
+		grads = torch.autograd.grad(loss, [l for _, l in pairs], allow_unused = True)
+		for (p, _), g in zip(pairs, grads):
 			p.grad = g
+		m._aliases = None
 		from . import optimizers
 		if isinstance(self.optimizer, optimizers._FusedOptimizer):
 			self.optimizer.step(max_grad_norm = self.max_grad_norm)  # clipping folded into the native step

@@ -69,6 +69,20 @@ int cab_instnorm_pack(const float* feat, const float* xlen_frac, int B, int C, i
                       int normalize, int F_pad, int C_pad, void* out_hi, void* out_lo, float* out_f32,
                       float* ws_stats, cab_stream_t stream);
 
+/* A1-A4 in one call (what JasperNet.forward does at models.py:286-301 before the backbone): signal -> per-utterance
+ * normalisation -> log-mel (ws_logmel: fp32 [B, n_mels, F], also a valid output) -> masked instance norm -> bf16
+ * channels-last features.  Three launches: abs-max, the STFT / mel / log kernel (which also emits per-tile instance-norm
+ * partial statistics), normalise + pack.  normalize_features: 0 = layout change only; norm_masked: statistics over the valid
+ * frames (normalize_features_temporal_mask).  ws_partials: fp32 [B, ceil(F / 64) + 1, n_mels, 2]; ws_absmax: 2 * B floats.  Other arguments as in
+ * cab_frontend_logmel / cab_instnorm_pack. */
+int cab_frontend_features(const void* signal, int signal_is_int16, const float* xlen_frac, int B, int T,
+                          int win_length, int hop, int nfft, int n_mels, const float* window,
+                          const float* mel_fb, const int32_t* mel_band, const float* twiddle, float preemphasis,
+                          float log_eps, int normalize_signal, float denom_multiplier, int normalize_features,
+                          int norm_masked, float norm_eps, float* ws_logmel, int F_pad, int C_pad, void* out_hi,
+                          void* out_lo, float* out_f32, float* ws_absmax, float* ws_partials,
+                          cab_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * A5-A9: Conv1d (+folded BatchNorm) + residual 1x1 convs + activation + temporal mask as ONE
  *   tcgen05/TMEM implicit GEMM.  Replaces ConvBn1d.forward (models.py:127-139) in its

@@ -323,9 +323,14 @@ def _grad_sync_worker(rank, world, port, tmp):
 	both = [torch.empty_like(flat) for _ in range(world)]
 	dist.all_gather(both, flat)
 	assert all(torch.equal(both[0], b) for b in both[1:])
-	dist.barrier()
-	dist.destroy_process_group()
 	open(os.path.join(tmp, f'ok{rank}'), 'w').write('ok')
+	# tear down in this order: a live CUDA graph that holds captured NCCL kernels makes destroy_process_group() wait forever
+	del step
+	import gc
+	gc.collect()
+	torch.cuda.synchronize()
+	dist.barrier()
+	os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason = 'needs two GPUs')

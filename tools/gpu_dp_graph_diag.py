@@ -14,13 +14,26 @@ sig, xlen, y, ylen = [t.to(dev) for t in T._batch(C, seed = 3 + rank)]
 kw = dict(base_width = 32, num_blocks = 1) if variant != 'D' else dict(base_width = 128)
 m, sd = T._model(dev, kw, precision = 'bf16')
 net, _ = models.distributed_data_parallel_and_autocast(m, rank, opt_level = 'O2')
-if variant in ('B', 'C'):
+opt = optimizers.SGD([p for p in m.parameters() if p.requires_grad], lr = 1e-3, momentum = 0.9)
+if variant in ('B', 'C', 'B2', 'B4'):
 	out = net(sig, xlen, y = y, ylen = ylen)
 	(out['loss'] * ylen[:, 0]).mean().backward()
 	torch.cuda.synchronize()
+if variant == 'B3':
+	side = torch.cuda.Stream()
+	side.wait_stream(torch.cuda.current_stream())
+	with torch.cuda.stream(side):
+		out = net(sig, xlen, y = y, ylen = ylen)
+		(out['loss'] * ylen[:, 0]).mean().backward()
+	torch.cuda.synchronize()
 if variant == 'C':
 	m.zero_grad(set_to_none = True)
-opt = optimizers.SGD([p for p in m.parameters() if p.requires_grad], lr = 1e-3, momentum = 0.9)
+if variant == 'B2':
+	del out
+	import gc; gc.collect()
+if variant == 'B4':
+	opt.step(max_grad_norm = 100.0); opt.zero_grad(set_to_none = True); del out
+	torch.cuda.synchronize()
 try:
 	step = training.GraphedTrainStep(net, opt, sig, xlen, y, ylen, warmup = 3 if variant == 'E' else 2, max_grad_norm = 100.0)
 	for _ in range(3):

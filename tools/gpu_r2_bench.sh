@@ -1,8 +1,10 @@
 #!/bin/bash
-# round 2: full GPU test-suite, then the default bench line (every "also" entry, gpu_baseline, cpu_baseline)
+# round 2: GPU test-suite (tight per-test timeout), frontend A/B, then the default bench line
 mkdir -p gpurun_out
-echo skip-tests
-SECONDS=0; timeout 1500 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "bench rc=$? wall ${SECONDS}s"; grep -E "Error|error" gpurun_out/r02_bench.err | head
+timeout 600 python -m pytest tests -m gpu -q -s --timeout 150 > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|^FAILED|^E  " gpurun_out/r02_pytest_gpu.log | head -20
+timeout 120 python tools/time_frontend.py 2>&1 | grep "^\[" | tee gpurun_out/r02_frontend_ab.log
+CONVASR_B200_FRONTEND=radix2 timeout 120 python tools/time_frontend.py 2>&1 | grep "^\[" | tee -a gpurun_out/r02_frontend_ab.log
+SECONDS=0; timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err; echo "bench rc=$? wall ${SECONDS}s"; grep -E "Error|error" gpurun_out/r02_bench.err | head
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/r02_bench.json').read().strip().splitlines()[-1])
