@@ -21,6 +21,7 @@
 #include "../../include/convasr_b200.h"
 #include <mutex>
 #include <atomic>
+#include <cstdlib>
 
 namespace cab {
 
@@ -72,6 +73,11 @@ struct alignas(64) ConvParams {
     // per-row log-sum-exp and argmax from an online softmax across the N tiles of an M tile (M-tile-major schedule)
     float* lse;
     int mtile_major;
+    // dynamic tile scheduling: units (tiles, or M tiles when mtile_major) are claimed with atomicAdd on this zeroed counter
+    // instead of the static blockIdx.x + i * gridDim.x walk -- a CTA that starts late (its SM was busy with another kernel,
+    // e.g. an NCCL all-reduce of the data-parallel step) simply claims fewer units instead of delaying the whole launch.
+    // null = static schedule.
+    int* tile_counter;
     // rows t >= ceil(skip_frac[b] * skip_T) + skip_margin of utterance b are structural zeros (padding of a
     // ragged batch): M tiles that lie entirely there are not computed, the epilogue stores zeros
     const float* skip_frac;
@@ -86,19 +92,53 @@ __device__ __forceinline__ int live_mtiles(const ConvParams& p, int b) {
     const int rows = min(p.T_out, frac_len(__ldg(p.skip_frac + b), p.skip_T) + p.skip_margin);
     return rows <= 0 ? 0 : (rows + 127) / 128;
 }
-// tile sequence of one CTA.  Default: tile = blockIdx.x + i * gridDim.x with the N tile fastest (neighbouring CTAs share the
-// A tile in L2).  mtile_major: the CTA owns compacted M tile blockIdx.x + j * gridDim.x and walks ALL of its N tiles in order
-// (the online softmax of the large-vocabulary head needs every class of a row in one CTA).
-__device__ __forceinline__ void tile_at(const ConvParams& p, int i, int& am, int& nt) {
-    if (p.mtile_major) {
-        am = blockIdx.x + (i / p.n_ntiles) * gridDim.x;
-        nt = i % p.n_ntiles;
-    } else {
-        const int tile = blockIdx.x + i * gridDim.x;
-        nt = tile % p.n_ntiles;
-        am = tile / p.n_ntiles;
-    }
+// Unit sequence of one CTA.  A unit is a tile (N tile fastest: neighbouring units share the A tile in L2), or -- mtile_major --
+// one compacted M tile whose N tiles the CTA then walks in order (the online softmax of the large-vocabulary head needs every
+// class of a row in one CTA).  Static schedule: unit j of this CTA = blockIdx.x + j * gridDim.x.  Dynamic schedule: the
+// producer thread claims units with atomicAdd and publishes them to the MMA / epilogue warps through a 4-deep shared-memory
+// ring (full / empty mbarriers); every role then derives (am, nt) and its TileCursor position from the same unit index.
+constexpr int kSched = 4;
+struct SchedRing {
+    int* unit;          // [kSched]
+    uint64_t* full;     // [kSched], 1 arrival (producer)
+    uint64_t* empty;    // [kSched], 1 (MMA thread) + 4 (epilogue warps) arrivals
+};
+__device__ __forceinline__ int sched_produce(const ConvParams& p, const SchedRing& r, int j) {
+    if (p.tile_counter == nullptr) return blockIdx.x + j * gridDim.x;
+    const int slot = j % kSched;
+    mbar_wait(&r.empty[slot], ((j / kSched) & 1) ^ 1);
+    const int u = atomicAdd(p.tile_counter, 1);
+    r.unit[slot] = u;
+    mbar_arrive(&r.full[slot]);  // release: the slot's value is visible to whoever acquires the barrier
+    return u;
 }
+template <bool WARP>  // WARP: called by all 32 lanes of a warp (one arrival per warp), else by a single thread
+__device__ __forceinline__ int sched_consume(const ConvParams& p, const SchedRing& r, int j, int lane) {
+    if (p.tile_counter == nullptr) return blockIdx.x + j * gridDim.x;
+    const int slot = j % kSched;
+    mbar_wait(&r.full[slot], (j / kSched) & 1);
+    const int u = r.unit[slot];
+    if (WARP) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.empty[slot]);
+    } else {
+        mbar_arrive(&r.empty[slot]);
+    }
+    return u;
+}
+// next (am, nt) of a role's walk; `u`, `nt_next`, `j` are the role's private state
+#define CAB_NEXT_UNIT(FETCH)                                                   \
+    int am, nt;                                                                \
+    if (p.mtile_major) {                                                       \
+        if (nt_next == 0) u = (FETCH);                                         \
+        am = u;                                                                \
+        nt = nt_next;                                                          \
+        nt_next = nt_next + 1 == p.n_ntiles ? 0 : nt_next + 1;                 \
+    } else {                                                                   \
+        u = (FETCH);                                                           \
+        nt = u % p.n_ntiles;                                                   \
+        am = u / p.n_ntiles;                                                   \
+    }
 struct TileCursor {
     int b, base, end;
     __device__ __forceinline__ void init(const ConvParams& p) { b = 0; base = 0; end = live_mtiles(p, 0); }
@@ -201,7 +241,11 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + kAccStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    SchedRing ring;
+    ring.full = tmem_empty + kAccStages;
+    ring.empty = ring.full + kSched;
+    ring.unit = reinterpret_cast<int*>(ring.empty + kSched);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ring.unit + kSched);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -226,6 +270,10 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
         }
+        for (int i = 0; i < kSched; ++i) {
+            mbar_init(&ring.full[i], 1);
+            mbar_init(&ring.empty[i], 5);  // MMA thread + one per epilogue warp
+        }
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -247,9 +295,9 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t phase = 0;
             TileCursor cur;
             cur.init(p);
-            for (int it = 0;; ++it) {
-                int am, nt;
-                tile_at(p, it, am, nt);
+            int u = 0, nt_next = 0, j = 0;
+            for (;;) {
+                CAB_NEXT_UNIT(sched_produce(p, ring, j++))
                 if (!cur.seek(p, am)) break;
                 const int b = cur.b;
                 const int t0 = (am - cur.base) * kBlockM;
@@ -283,10 +331,11 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t acc_phase = 0;
             TileCursor cur;
             cur.init(p);
-            for (int it = 0;; ++it) {
-                int am_, nt_;
-                tile_at(p, it, am_, nt_);
-                if (!cur.seek(p, am_)) break;
+            int u = 0, nt_next = 0, j = 0;
+            for (;;) {
+                CAB_NEXT_UNIT(sched_consume<false>(p, ring, j++, 0))
+                (void)nt;
+                if (!cur.seek(p, am)) break;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMaxBlockN;
@@ -325,9 +374,9 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         cur.init(p);
         float run_m = -INFINITY, run_s = 0.f;  // CAB_EPI_LOGITS_ROWS: online softmax of this thread's row across N tiles
         int run_i = 0;
-        for (int it = 0;; ++it) {
-            int am, nt;
-            tile_at(p, it, am, nt);
+        int u = 0, nt_next = 0, j = 0;
+        for (;;) {
+            CAB_NEXT_UNIT(sched_consume<true>(p, ring, j++, lane))
             if (!cur.seek(p, am)) break;
             const int b = cur.b;
             const int t0 = (am - cur.base) * kBlockM;
@@ -690,6 +739,27 @@ static int pick_block_n(int C_out, int epilogue, long long m_tiles, int num_sms)
 
 extern std::atomic<int64_t> g_launch_count;
 
+// Counters of the dynamic tile schedule: one int per launch out of a ring that is allocated once per process (the only
+// allocation this library makes; 64 K launches must be in flight before a slot could be reused).  Zeroed on the launch's
+// stream right before the kernel, so CUDA-graph replays re-zero their own slots.  CONVASR_B200_STATIC_TILES=1 keeps the
+// round-1 static schedule (A/B).
+int* next_tile_counter(cudaStream_t stream) {
+    constexpr int kSlots = 1 << 16;
+    static int* ring = nullptr;
+    static std::atomic<unsigned> next{0};
+    static std::once_flag once;
+    static bool disabled = false;
+    std::call_once(once, [] {
+        const char* e = getenv("CONVASR_B200_STATIC_TILES");
+        disabled = e && e[0] == '1';
+        if (!disabled && cudaMalloc(&ring, sizeof(int) * kSlots) != cudaSuccess) ring = nullptr;
+    });
+    if (disabled || ring == nullptr) return nullptr;
+    int* slot = ring + (next.fetch_add(1, std::memory_order_relaxed) % kSlots);
+    if (cudaMemsetAsync(slot, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
+    return slot;
+}
+
 }  // namespace cab
 
 using namespace cab;
@@ -830,6 +900,7 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
     CAB_CHECK_ARG(num_sms > 0, "no CUDA device");
     int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     if (p.mtile_major) grid = p.B * p.mtiles_per_b < num_sms ? p.B * p.mtiles_per_b : num_sms;
+    p.tile_counter = next_tile_counter(stream);
     conv1d_umma_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(p);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
