@@ -103,13 +103,16 @@ struct SchedRing {
     uint64_t* full;     // [kSched], 1 arrival (producer)
     uint64_t* empty;    // [kSched], 1 (MMA thread) + 4 (epilogue warps) arrivals
 };
-__device__ __forceinline__ int sched_produce(const ConvParams& p, const SchedRing& r, int j) {
+// The producer claims one unit AHEAD: the atomicAdd for unit j + 1 is issued when unit j is published and its result is first
+// needed a whole tile later, so the ~1 us round trip of the global atomic never sits on the producer's critical path.
+__device__ __forceinline__ int sched_produce(const ConvParams& p, const SchedRing& r, int j, int& ahead) {
     if (p.tile_counter == nullptr) return blockIdx.x + j * gridDim.x;
     const int slot = j % kSched;
+    const int u = j == 0 ? atomicAdd(p.tile_counter, 1) : ahead;
     mbar_wait(&r.empty[slot], ((j / kSched) & 1) ^ 1);
-    const int u = atomicAdd(p.tile_counter, 1);
     r.unit[slot] = u;
     mbar_arrive(&r.full[slot]);  // release: the slot's value is visible to whoever acquires the barrier
+    ahead = atomicAdd(p.tile_counter, 1);
     return u;
 }
 template <bool WARP>  // WARP: called by all 32 lanes of a warp (one arrival per warp), else by a single thread
@@ -295,9 +298,10 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             uint32_t phase = 0;
             TileCursor cur;
             cur.init(p);
-            int u = 0, nt_next = 0, j = 0;
+            int u = 0, nt_next = 0, j = 0, ahead = 0;
             for (;;) {
-                CAB_NEXT_UNIT(sched_produce(p, ring, j++))
+                CAB_NEXT_UNIT(sched_produce(p, ring, j, ahead))
+                if (!p.mtile_major || nt == 0) ++j;
                 if (!cur.seek(p, am)) break;
                 const int b = cur.b;
                 const int t0 = (am - cur.base) * kBlockM;
@@ -741,8 +745,9 @@ extern std::atomic<int64_t> g_launch_count;
 
 // Counters of the dynamic tile schedule: one int per launch out of a ring that is allocated once per process (the only
 // allocation this library makes; 64 K launches must be in flight before a slot could be reused).  Zeroed on the launch's
-// stream right before the kernel, so CUDA-graph replays re-zero their own slots.  CONVASR_B200_STATIC_TILES=1 keeps the
-// round-1 static schedule (A/B).
+// stream right before the kernel, so CUDA-graph replays re-zero their own slots.  OPT-IN (CONVASR_B200_DYNAMIC_TILES=1): the
+// same-box A/B on 8 x B200 (profiles/r02_tile_schedule_ab.md) measured the dynamic schedule 1 % slower at N = 1 and 3 % slower
+// at N = 8 than the static round-robin walk, so static stays the default.
 int* next_tile_counter(cudaStream_t stream) {
     constexpr int kSlots = 1 << 16;
     static int* ring = nullptr;
@@ -750,8 +755,8 @@ int* next_tile_counter(cudaStream_t stream) {
     static std::once_flag once;
     static bool disabled = false;
     std::call_once(once, [] {
-        const char* e = getenv("CONVASR_B200_STATIC_TILES");
-        disabled = e && e[0] == '1';
+        const char* e = getenv("CONVASR_B200_DYNAMIC_TILES");
+        disabled = !(e && e[0] == '1');
         if (!disabled && cudaMalloc(&ring, sizeof(int) * kSlots) != cudaSuccess) ring = nullptr;
     });
     if (disabled || ring == nullptr) return nullptr;

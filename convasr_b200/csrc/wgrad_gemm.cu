@@ -60,13 +60,16 @@ struct SchedRing {
     uint64_t* full;
     uint64_t* empty;
 };
-__device__ __forceinline__ int sched_produce(const Params& p, const SchedRing& r, int j) {
+// The producer claims one unit AHEAD: the atomicAdd for unit j + 1 is issued when unit j is published and its result is first
+// needed a whole tile later, so the ~1 us round trip of the global atomic never sits on the producer's critical path.
+__device__ __forceinline__ int sched_produce(const Params& p, const SchedRing& r, int j, int& ahead) {
     if (p.item_counter == nullptr) return blockIdx.x + j * gridDim.x;
     const int slot = j % kSched;
+    const int u = j == 0 ? atomicAdd(p.item_counter, 1) : ahead;
     mbar_wait(&r.empty[slot], ((j / kSched) & 1) ^ 1);
-    const int u = atomicAdd(p.item_counter, 1);
     r.unit[slot] = u;
-    mbar_arrive(&r.full[slot]);
+    mbar_arrive(&r.full[slot]);  // release: the slot's value is visible to whoever acquires the barrier
+    ahead = atomicAdd(p.item_counter, 1);
     return u;
 }
 template <bool WARP>
@@ -162,8 +165,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) wgrad_umma_kernel(const __grid
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int ahead = 0;
             for (int j = 0;; ++j) {
-                const int item = sched_produce(p, ring, j);
+                const int item = sched_produce(p, ring, j, ahead);
                 if (item >= p.n_items) break;
                 int tap, mt, nt, b0, b1;
                 decode(item, tap, mt, nt, b0, b1);

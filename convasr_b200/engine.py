@@ -241,8 +241,22 @@ class StackPlan:
 				srcs.append(ops.Source(hi, g.weights.lo, g.c_in_alloc, g.taps, g.dilation, g.pad_left, T_in = T_in))
 				if lo is not None:
 					srcs.append(ops.Source(lo, g.weights.hi, g.c_in_alloc, g.taps, g.dilation, g.pad_left, T_in = T_in))
-		if len(srcs) > _lib.MAX_CONV_SOURCES:
-			raise NotImplementedError(f'convasr_b200: {len(srcs)} GEMM operand pairs in one launch (max {_lib.MAX_CONV_SOURCES})')
+		return srcs
+
+	def _fold_excess_sources(self, srcs, B, T_out, C_alloc, dev):
+		"""more operand pairs than one launch has K segments (dense 'Big' models in the split tier: 10 branches x 3 products):
+		the first groups run as plain linear launches (no bias / activation / mask) and re-enter the last launch as identity
+		K segments of their (hi, lo) partial sum"""
+		eye = None
+		while len(srcs) > _lib.MAX_CONV_SOURCES:
+			room = _lib.MAX_CONV_SOURCES - 4  # leave room for the identity segments of the running partial sum
+			now, srcs = srcs[:room], srcs[room:]
+			part_hi = torch.empty(B, T_out, C_alloc, dtype = BF16, device = dev)
+			part_lo = torch.empty_like(part_hi) if self.fp32_tier else None
+			ops.conv1d_fused(now, B, T_out, C_alloc, out_hi = part_hi, out_lo = part_lo)
+			if eye is None:
+				eye = torch.eye(C_alloc, dtype = BF16, device = dev).unsqueeze(0).contiguous()
+			srcs = [ops.Source(part_hi, eye, C_alloc, 1, 1, 0, T_in = T_out)] + ([ops.Source(part_lo, eye, C_alloc, 1, 1, 0, T_in = T_out)] if part_lo is not None else []) + srcs
 		return srcs
 
 	def _run_launch(self, L, x, residuals, xlen, B):
@@ -260,6 +274,7 @@ class StackPlan:
 		srcs = self._sources(L, x, tmp, residuals)
 		code, a, b = L.act
 		if L.epilogue == _lib.EPI_ACT_BF16:
+			srcs = self._fold_excess_sources(srcs, B, T_out, L.C_alloc, dev)
 			out_hi = torch.empty(B, T_out, L.C_alloc, dtype = BF16, device = dev)
 			out_lo = torch.empty_like(out_hi) if self.fp32_tier else None
 			ops.conv1d_fused(srcs, B, T_out, L.C_alloc, bias = L.bias, act = code, act_a = a, act_b = b, xlen = xlen if L.mask else None, out_hi = out_hi, out_lo = out_lo)

@@ -187,7 +187,7 @@ def conv1d_fused(
 	_lib.check(rc, 'cab_conv1d_fused')
 
 
-def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0, skip = None, out = None):
+def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_splits = 0, skip = None, out = None, alloc = None):
 	"""out[tap, m, n] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dilation - pad_left, n]  (fp32 [taps, M, N_ld]);
 	skip = (frac [B], T, margin): frames t >= ceil(frac[b]*T) + margin only contribute zeros and are left out;
 	out given: the products are ADDED to it (partial products of the split-bf16 tier)"""
@@ -197,7 +197,8 @@ def conv1d_wgrad(a, a_T, M_total, bx, b_T, N_total, taps, dilation, pad_left, n_
 	out_ld = (N_total + 3) // 4 * 4
 	accumulate = out is not None
 	if out is None:
-		out = torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
+		# alloc: caller-provided allocator (numel -> flat fp32 tensor), e.g. slices of a gradient bucket
+		out = alloc(taps * M_total * out_ld).view(taps, M_total, out_ld) if alloc is not None else torch.empty(taps, M_total, out_ld, dtype = torch.float32, device = a.device)
 	rc = _lib.load().cab_conv1d_wgrad(
 		_p(a), a_T, a.shape[1], a.shape[2], M_total, _p(bx), b_T, bx.shape[1], bx.shape[2], N_total, B, taps, dilation, pad_left,
 		_p(out), out_ld, n_splits, _p(skip[0]) if skip is not None else None, int(skip[1]) if skip is not None else 0,

@@ -41,6 +41,7 @@ from . import _lib, engine, ops
 BF16 = torch.bfloat16
 _SEPARATE_BN_STATS = os.environ.get('CONVASR_B200_SEPARATE_BN_STATS', '0') == '1'
 _SKIP_PADDING = os.environ.get('CONVASR_B200_SKIP_PADDING', '1') == '1'  # A/B switch: leave tiles of pure padding out
+_GRAD_BUCKET_MB = int(os.environ.get('CONVASR_B200_GRAD_BUCKET_MB', '64'))  # data-parallel gradient bucket size; 0 = one collective per layer
 
 
 def unsupported_reason(model):
@@ -382,8 +383,31 @@ class NativeStack(torch.autograd.Function):
 		_lib.check(rc, 'cab_bct_to_btc')
 		grads = {}
 
+		# Gradient buckets (data-parallel replicas): the packed weight gradients are carved, in backward order, out of flat
+		# buffers of ~CONVASR_B200_GRAD_BUCKET_MB; a bucket is all-reduced in ONE collective as soon as it is full -- 266 MB of
+		# Wav2Letter gradients travel in 5 collectives instead of 20 (each costs a launch, ~40 us of latency at 8 ranks and a
+		# window in which NCCL and the persistent GEMMs compete for SMs), still overlapped with the rest of the backward.
+		bucket = dict(buf = None, used = 0, start = 0)
+		bucket_floats = max(1, _GRAD_BUCKET_MB) * (1 << 18)
+
+		def flush_bucket():
+			if sync is not None and bucket['buf'] is not None and bucket['used'] > bucket['start']:
+				sync.reduce(bucket['buf'][bucket['start']:bucket['used']])
+			bucket['start'] = bucket['used']
+
+		def alloc(numel):
+			if sync is None:
+				return torch.empty(numel, dtype = torch.float32, device = dev)
+			if bucket['buf'] is None or bucket['used'] + numel > bucket['buf'].numel():
+				flush_bucket()
+				bucket['buf'] = torch.empty(max(bucket_floats, numel), dtype = torch.float32, device = dev)
+				bucket['used'] = bucket['start'] = 0
+			out = bucket['buf'][bucket['used']:bucket['used'] + numel]
+			bucket['used'] += numel
+			return out
+
 		def wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, x_masked):
-			return _wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, xlen if (_SKIP_PADDING and xlen is not None and x_masked) else None, defer = True)
+			return _wgrad(dy, dy_T, C_out, x, x_T, C_in, k, dil, pad, xlen if (_SKIP_PADDING and xlen is not None and x_masked) else None, defer = True, alloc = alloc)
 
 		deferred = []  # packed weight gradients: all-reduced in their packed layout, un-packed into the parameter layout by ONE launch at the end
 
@@ -396,11 +420,12 @@ class NativeStack(torch.autograd.Function):
 				deferred.append(_lib.UnpackItem(packed.data_ptr(), out.data_ptr(), K, Co, Ci, packed.shape[2], int(transposed), pair_pad, pair_ci_alloc))
 				deferred_keep.append(packed)
 				grads[p] = out
-				grad = packed
-			else:
-				grads[p] = grad
+				if bucket['buf'] is not None and bucket['used'] - bucket['start'] >= bucket_floats:
+					flush_bucket()  # overlaps the dgrad / wgrad of the layers still to come
+				return
+			grads[p] = grad
 			if sync is not None:
-				sync.reduce(grad)  # overlaps the dgrad / wgrad of the layers still to come
+				sync.reduce(grad)
 
 		deferred_keep = []
 
@@ -409,7 +434,7 @@ class NativeStack(torch.autograd.Function):
 		last_masked = masked[reps[-1].out_id]
 		skip_last = (xlen, T_last, 0) if _SKIP_PADDING and xlen is not None and last_masked else None
 		if dec.weight.requires_grad:
-			packed = _wgrad_packed(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0, skip_last)
+			packed = _wgrad_packed(x_last, T_last, dec.in_channels, g_cl, T, C, 1, 1, 0, skip_last, alloc)
 			finish_weight(dec.weight, (packed, 1, C, dec.in_channels, True, 0, 0))
 		if dec.bias is not None and dec.bias.requires_grad:
 			grads[dec.bias] = d_bias
@@ -503,7 +528,7 @@ class NativeStack(torch.autograd.Function):
 				if cv.pair:
 					xv = engine._Act(x.hi.view(B, x.hi.shape[1] // 2, 2 * x.hi.shape[2]), x.lo.view(B, x.lo.shape[1] // 2, 2 * x.lo.shape[2]) if x.lo is not None else None, x.hi.shape[1] // 2, 2 * cv.ci_alloc)
 					taps2 = W[cv][0].shape[0]
-					packed = _wgrad_packed(dy, T_out, cv.C_out, xv, xv.T, 2 * cv.ci_alloc, taps2, 1, -((0 - cv.pad) // 2), None)
+					packed = _wgrad_packed(dy, T_out, cv.C_out, xv, xv.T, 2 * cv.ci_alloc, taps2, 1, -((0 - cv.pad) // 2), None, alloc)
 					finish_weight(cv.m.weight, (packed, cv.k, cv.C_out, cv.C_in, 2, cv.pad, cv.ci_alloc))
 				else:
 					finish_weight(cv.m.weight, wgrad(dy, T_out, cv.C_out, conv_in, conv_T, cv.C_in, cv.k, cv.dil, cv.pad, in_masked))
@@ -535,6 +560,7 @@ class NativeStack(torch.autograd.Function):
 				dx_hi, dx_lo = ops.grouped_conv1d(dzh.hi, h.T, gconv.out_channels, wt, None, gconv.groups, K - 1 - gconv.padding[0], ld_out = x.hi.shape[2], act_lo = dzh.lo, want_lo = split, relu = False, T_out = x_T)
 				pending.setdefault(rep.in_id, []).append(('direct', engine._Act(dx_hi, dx_lo, x_T, x.hi.shape[2])))
 		if sync is not None:
+			flush_bucket()
 			sync.reduce(small)
 			sync.finish()
 		for lo in range(0, len(deferred), 32):
@@ -550,16 +576,16 @@ def _padded_work(M, N):
 	return ((M + 127) // 128 * 128) * n_nt * bn
 
 
-def _wgrad_packed(a, a_T, M, bx, b_T, N, taps, dil, pad, skip):
+def _wgrad_packed(a, a_T, M, bx, b_T, N, taps, dil, pad, skip, alloc = None):
 	"""fp32 [taps, M, ld] = sum_{b,t} a[b,t,m] * bx[b, t + tap*dil - pad, n]; three accumulated launches in the split tier"""
-	out = ops.conv1d_wgrad(a.hi, a_T, M, bx.hi, b_T, N, taps, dil, pad, skip = skip)
+	out = ops.conv1d_wgrad(a.hi, a_T, M, bx.hi, b_T, N, taps, dil, pad, skip = skip, alloc = alloc)
 	if a.lo is not None:
 		ops.conv1d_wgrad(a.hi, a_T, M, bx.lo, b_T, N, taps, dil, pad, skip = skip, out = out)
 		ops.conv1d_wgrad(a.lo, a_T, M, bx.hi, b_T, N, taps, dil, pad, skip = skip, out = out)
 	return out
 
 
-def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None, defer = False):
+def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None, defer = False, alloc = None):
 	"""dW[co, ci, tap] = sum_{b,t} dy[b,t,co] * x[b, t + tap*dil - pad, ci].  Either tensor can sit on the
 	128-row M side of the GEMM; pick the orientation with less tile padding (e.g. 640 -> 768 wastes 20 %
 	one way and nothing the other way).  Swapping sides negates the frame shift."""
@@ -567,9 +593,9 @@ def _wgrad(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, xlen_zero = None, defer 
 		dy, x = engine._Act(dy, None, T_out, C_out), engine._Act(x, None, x_T, C_in)
 	# xlen_zero: x is exactly zero from frame ceil(xlen*x_T) on, so products with t + tap*dil - pad >= that vanish
 	if _padded_work(C_out, C_in) <= _padded_work(C_in, C_out):
-		packed = _wgrad_packed(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, (xlen_zero, x_T, pad) if xlen_zero is not None else None)
+		packed = _wgrad_packed(dy, T_out, C_out, x, x_T, C_in, k, dil, pad, (xlen_zero, x_T, pad) if xlen_zero is not None else None, alloc)
 		return (packed, k, C_out, C_in, False, 0, 0) if defer else _unpack(packed, k, C_out, C_in, transposed = False)
-	packed = _wgrad_packed(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad, (xlen_zero, x_T, 0) if xlen_zero is not None else None)
+	packed = _wgrad_packed(x, x_T, C_in, dy, T_out, C_out, k, -dil, -pad, (xlen_zero, x_T, 0) if xlen_zero is not None else None, alloc)
 	return (packed, k, C_out, C_in, True, 0, 0) if defer else _unpack(packed, k, C_out, C_in, transposed = True)
 
 

@@ -307,7 +307,7 @@ def _grad_sync_worker(rank, world, port, tmp):
 		out = net(sig, xlen, y = y, ylen = ylen)
 		(out['loss'] * ylen[:, 0]).mean().backward()
 		torch.cuda.synchronize()
-		assert m._grad_sync.n_collectives == 6 + 1 + 1  # one per conv layer, the decoder, the flat small-tensor buffer
+		assert m._grad_sync.n_collectives == 1 + 1  # one bucket holds every packed weight gradient of this small model, plus the flat small-tensor buffer
 		errs = sorted(((rel(p.grad, expect[n] / world), n) for n, p in m.named_parameters() if n in expect), reverse = True)
 		worst = errs[0][0]
 		measured[precision] = worst

@@ -1,15 +1,12 @@
 #!/bin/bash
-# round 2: full GPU test-suite on a 2-GPU box (includes the data-parallel GradSync test; kept log), the cross-GPU
-# reproducibility diagnostic, then the 2-GPU bench line (replicas_identical)
+# round 2: the data-parallel GradSync test on two GPUs (kept log), then the 2-GPU bench line (replicas_identical)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -s --timeout 900 > gpurun_out/r02_pytest_2gpu.log 2>&1; echo "pytest rc=$?"; grep -E "rank [01]:|passed|failed|skipped|Error" gpurun_out/r02_pytest_2gpu.log | head
-for v in B C; do VARIANT=$v timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/gpu_dp_graph_diag.py 2>&1 | grep '^variant'; done
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/gpu_dp_diag.py 2>&1 | grep -E "^rank|^   " > gpurun_out/r02_dp_diag.log; cat gpurun_out/r02_dp_diag.log | head -30
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02_bench_2gpu.json 2> gpurun_out/r02_bench_2gpu.err; echo "bench2 rc=$?"; grep -E "Error" gpurun_out/r02_bench_2gpu.err | head -5
+timeout 300 python -m pytest tests/test_gpu_training.py -m gpu -q -s --timeout 200 -k "two_gpus" > gpurun_out/r02_pytest_2gpu.log 2>&1; echo "pytest rc=$?"; grep -E "rank [01]:|passed|failed|skipped|Error" gpurun_out/r02_pytest_2gpu.log | head
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r02_bench_2gpu.json 2> gpurun_out/r02_bench_2gpu.err; echo "bench2 rc=$?"; grep -E "Error" gpurun_out/r02_bench_2gpu.err | head -5
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/r02_bench_2gpu.json').read().strip().splitlines()[-1])
-print('N=2', d['value'], d['ms_per_step'], 'replicas', d.get('replicas'), 'kernel ms', d['roofline']['kernel_ms_per_step'])
+print('N=2', d['value'], d['ms_per_step'], 'replicas', d.get('replicas'), 'kernel ms', d['roofline']['kernel_ms_per_step'], d['clocks'])
 for n, e in d['also'].items():
     print(n, round(e['value']), round(e['ms_per_step'], 3), e.get('e2e', {}).get('value'))
 PY
