@@ -147,6 +147,8 @@ def algorithmic_bytes(model, B, T, t_out, C, kind, L):
 		'cab_ctc_loss_bwd': 2 * B * t_out * C * 4 + 2 * B * t_out * (2 * L + 1) * 4,  # log_probs read, grad written; alpha, beta read
 		'cab_greedy_collapse': B * t_out * 4 * 2,
 		'cab_log_softmax_argmax': B * t_out * C * 4 * 2,
+		'cab_log_softmax_rows': B * t_out * C * 4 * 2,  # logits read, log-probs written
+		'cab_frontend_features': B * T * 2 + B * (F + F % 2) * 64 * 2,  # int16 PCM in, normalised bf16 channels-last features out (28.8 KB per audio-second)
 	}
 	if kind == 'train':
 		acts, t, params = 0, F, 0
@@ -163,6 +165,7 @@ def algorithmic_bytes(model, B, T, t_out, C, kind, L):
 			'cab_bn_act_mask_bwd': 5 * acts,  # reduce: y, g read; apply: y, g read, dy written
 			'cab_pack_weights_batched': params * (4 + 2 + 2),  # fp32 master read, forward + dgrad bf16 operands written
 			'cab_unpack_wgrad': params * 8,
+			'cab_unpack_wgrad_batched': params * 8,
 			'cab_optimizer_step': n_all * 20 + n_all * 4,  # p, g, m read + p, m written; g read once more for the norm
 			'cab_log_softmax_bwd': 3 * B * t_out * C * 4,
 			'cab_bct_to_btc': B * t_out * C * 4 + B * t_out * 64 * 2,
@@ -460,13 +463,21 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, level):
 				nll = infer_once(shard[a:a + B], shard_xlen[a:a + B], shard_y[a:a + B], shard_ylen[a:a + B], False)[0]
 			return nll
 
+		loss_host = torch.empty(n_local, dtype = torch.float32).pin_memory()
+		cnt_host = torch.empty(n_local, dtype = torch.int32).pin_memory()
+
 		def step_e2e(batches):
-			res = []
+			# results come back through pinned buffers with asynchronous copies; one synchronisation at the end of the pass (a
+			# transcription loop consumes them a micro-batch behind), so the H2D of the next micro-batch, the kernels and the D2H overlap
+			a = 0
 			for _, _, s, xl, yy, yl in batches:
 				out = model(s, xl, y = yy, ylen = yl)
 				tok, frm, cnt = ops.greedy_collapse(out['log_probs'][0]._convasr_argmax, out['olen'][0], C, C - 1, C - 2, sil, ws, 10)
-				res.append((out['loss'].cpu(), cnt.cpu()))
-			return res
+				loss_host[a:a + len(s)].copy_(out['loss'], non_blocking = True)
+				cnt_host[a:a + len(s)].copy_(cnt, non_blocking = True)
+				a += len(s)
+			torch.cuda.synchronize()
+			return loss_host, cnt_host
 
 		d2h = n_local * 8
 		tensor_entries = ['cab_conv1d_fused']

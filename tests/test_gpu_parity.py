@@ -574,3 +574,35 @@ def test_dropin_modules_run_a_transcribe_shaped_flow(golden, dev):
 			sys.modules.pop(n, None)
 			if mod is not None:
 				sys.modules[n] = mod
+
+
+def test_dense_big_model_beyond_18_k_segments_per_launch(dev):
+	"""JasperNetBig (dense residual, 2 sub-blocks per block): the last blocks join 10 branches, i.e. 30 operand pairs in the split
+	tier -- more than one launch has K segments.  Eval engine and training path both chain launches (the partial sum re-enters
+	as an identity segment); logits against the oracle in both tiers, and a native training step in the fp32 tier."""
+	from convasr_b200 import models, training
+	g = torch.Generator().manual_seed(21)
+	m = models.JasperNetBig(64, [38], base_width = 16, frontend = models.LogFilterBankFrontend(64, 8000, .02, .01, 'hann_window'), dropout = 0., check_time_dim_padded = False)
+	shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith('frontend.')}
+	sd = O.synth_state_dict(shapes, seed = 31)
+	m.load_state_dict(sd, strict = False)
+	m = m.to(dev).eval()
+	sig = (torch.randn(3, 6400, generator = g) * 3000).round().clamp(-32767, 32767).to(torch.int16)
+	xlen = torch.tensor([1.0, 0.7, 0.45])
+	ref_logits, _, ref_olen = O.model_forward(sd, sig, xlen, model = 'JasperNetBig')
+	for precision, tol in (('fp32', 1e-3), ('bf16', 3e-2)):
+		m.set_precision(precision)
+		with torch.no_grad():
+			out = m(sig.to(dev), xlen.to(dev))
+		assert torch.equal(out['olen'][0].cpu(), ref_olen[0])
+		assert rel(out['logits'][0], ref_logits[0]) < tol, (precision, rel(out['logits'][0], ref_logits[0]))
+	# training, split tier: forward quantities against the oracle's train-mode forward, finite gradients for every parameter
+	m.train().set_precision('fp32')
+	assert training.unsupported_reason(m) is None
+	y = torch.randint(0, 37, (3, 1, 6), generator = g)
+	ylen = torch.tensor([[6], [4], [2]])
+	out = m(sig.to(dev), xlen.to(dev), y = y.to(dev), ylen = ylen.to(dev))
+	(out['loss'] * ylen[:, 0].to(dev)).mean().backward()
+	ref_train, _, _ = O.model_forward(sd, sig, xlen, model = 'JasperNetBig', training = True)
+	assert rel(out['logits'][0], ref_train[0]) < 1e-3, rel(out['logits'][0], ref_train[0])
+	assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in m.named_parameters() if not n.startswith('frontend.'))
