@@ -163,6 +163,7 @@ def algorithmic_bytes(model, B, T, t_out, C, kind, L):
 		out.update({
 			'cab_bn_act_mask_fwd_stats': 2 * acts,  # y read, activation written
 			'cab_bn_act_mask_bwd': 5 * acts,  # reduce: y, g read; apply: y, g read, dy written
+			'cab_bn_act_mask_bwd_apply': 3 * acts,  # the channel sums came out of the dgrad epilogue: y, g read, dy written
 			'cab_pack_weights_batched': params * (4 + 2 + 2),  # fp32 master read, forward + dgrad bf16 operands written
 			'cab_unpack_wgrad': params * 8,
 			'cab_unpack_wgrad_batched': params * 8,

@@ -30,7 +30,10 @@ class ConvEpilogue(ctypes.Structure):
 		('act_a', c_float), ('act_b', c_float), ('bias', c_void_p), ('xlen_frac', c_void_p), ('out_hi', c_void_p),
 		('out_lo', c_void_p), ('out_T_rows', c_i32), ('out_ld_ch', c_i32), ('logits', c_void_p),
 		('log_probs', c_void_p), ('argmax', c_void_p), ('stats', c_void_p), ('skip_frac', c_void_p), ('skip_T', c_i32),
-		('skip_margin', c_i32)
+		('skip_margin', c_i32),
+		# BatchNorm-backward reduction folded into a dgrad launch
+		('bnr_y', c_void_p), ('bnr_ss', c_void_p), ('bnr_xlen_frac', c_void_p), ('bnr_partials', c_void_p), ('bnr_C', c_i32), ('bnr_act', c_i32),
+		('bnr_act_a', c_float), ('bnr_act_b', c_float)
 	]
 
 
@@ -51,7 +54,7 @@ EPI_ACT_BF16, EPI_LOGSOFTMAX, EPI_LOGITS_F32, EPI_LOGITS_ROWS = 0, 1, 2, 3
 MAX_CONV_SOURCES = 18
 MAX_BN_BRANCHES = 12
 PACK_MAX_ITEMS = 32
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> argtypes; every function returns int except the three introspection calls
 BN_SUM_REPLICAS = 8  # CAB_BN_SUM_REPLICAS
@@ -73,6 +76,8 @@ SIGNATURES = {
 							c_void_p, c_i64, c_void_p],
 	'cab_bn_act_mask_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
 							c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i64, c_int, c_void_p, c_void_p],
+	'cab_bn_act_mask_bwd_apply': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+								c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_i64, c_int, c_void_p, c_void_p],
 	'cab_bn_multi_act_mask_fwd': [ctypes.POINTER(BnBranch), c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
 								c_float, c_void_p, c_i64, c_void_p],
 	'cab_act_mask_bwd_dz': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,

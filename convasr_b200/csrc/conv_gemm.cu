@@ -82,6 +82,19 @@ struct alignas(64) ConvParams {
     // ragged batch): M tiles that lie entirely there are not computed, the epilogue stores zeros
     const float* skip_frac;
     int skip_T, skip_margin;
+    // BatchNorm-backward reduction folded into a dgrad launch (bf16 tier): this launch produces g = dL/d(out) of a layer whose
+    // pre-BatchNorm conv output is `y` (same [B, T_out, out_ld] geometry as the output, read through ymap: box {32 ch, 128 rows},
+    // 64B swizzle -- the mirror image of the output store).  After a 32-column chunk of g is staged (bf16-rounded, exactly what
+    // the BatchNorm backward will read), the epilogue accumulates sum(dz) and sum(dz * y) per channel, dz = g * act'(y*scale +
+    // shift) * (t < len_b), into fp64 partials [CAB_BN_SUM_REPLICAS][2][bnr_C]: the separate reduce pass over (y, g) -- two of the
+    // five activation-sized passes of the BatchNorm backward -- disappears.
+    int stats_columns;       // forward statistics: column-parallel pass over the staged tile (default) or the per-row shuffle butterfly
+    CUtensorMap ymap;
+    const float* bnr_ss;     // [4][bnr_C]: scale, shift, (mean, invstd)
+    const float* bnr_xlen;   // temporal mask of the layer (or null)
+    double* bnr_partials;    // null = no fold
+    int bnr_C, bnr_act;
+    float bnr_a, bnr_b;
 };
 
 // Tile schedule.  Only M tiles that hold at least one live row are enumerated ("compacted" index am), so
@@ -233,6 +246,56 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
     }
 }
 
+// Folded BatchNorm-backward reduction over one staged chunk: g and y are bf16 [128 rows][32 cols] tiles in the 64B-swizzled
+// staging layout.  Thread = (column et % 32, row group et / 32): the per-channel coefficients are two scalars, the 32 lanes of
+// a warp read the 64 contiguous (swizzled) bytes of one row -- conflict free -- and no cross-lane reduction is needed; the
+// four row groups meet in the fp64 atomics.  Same arithmetic per element as bn_stream_kernel<1> (train.cu).
+template <int ACT>
+__device__ __forceinline__ void bnr_column_pass(const uint8_t* __restrict__ st_g, const uint8_t* __restrict__ st_y, int et, int nrows,
+                                                float sc, float sh, float a, float b, float& s_out, float& q_out) {
+    const int c = et & 31, rg = et >> 5;
+    const int r_end = min(rg * 32 + 32, nrows);
+    const int cq = c >> 3, cb = (c & 7) << 1;
+    float s = 0.f, q = 0.f;
+#pragma unroll 8
+    for (int r = rg * 32; r < r_end; ++r) {
+        const int off = r * 64 + ((cq ^ ((r >> 1) & 3)) << 4) + cb;
+        const float g = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(st_g + off)) << 16);
+        const float y = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(st_y + off)) << 16);
+        const float z = fmaf(y, sc, sh);
+        float dz;
+        if (ACT == CAB_ACT_RELU) dz = z > 0.f ? g : 0.f;
+        else if (ACT == CAB_ACT_HARDTANH) dz = (z > a && z < b) ? g : 0.f;
+        else if (ACT == CAB_ACT_LEAKY_RELU) dz = z > 0.f ? g : g * a;
+        else dz = g;
+        s += dz;
+        q = fmaf(dz, y, q);
+    }
+    s_out = s;
+    q_out = q;
+}
+
+// Forward batch statistics over one staged chunk, same thread mapping as bnr_column_pass: per-channel sum / sum of squares of
+// the stored values (hi [+ lo]) over the tile's rows < nrows.  Replaces two 31-step shuffle butterflies per thread and chunk.
+template <bool LO>
+__device__ __forceinline__ void stats_column_pass(const uint8_t* __restrict__ st_h, const uint8_t* __restrict__ st_l, int et, int nrows,
+                                                  float& s_out, float& q_out) {
+    const int c = et & 31, rg = et >> 5;
+    const int r_end = min(rg * 32 + 32, nrows);
+    const int cq = c >> 3, cb = (c & 7) << 1;
+    float s = 0.f, q = 0.f;
+#pragma unroll 8
+    for (int r = rg * 32; r < r_end; ++r) {
+        const int off = r * 64 + ((cq ^ ((r >> 1) & 3)) << 4) + cb;
+        float x = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(st_h + off)) << 16);
+        if (LO) x += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(st_l + off)) << 16);
+        s += x;
+        q = fmaf(x, x, q);
+    }
+    s_out = s;
+    q_out = q;
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -249,6 +312,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
     ring.empty = ring.full + kSched;
     ring.unit = reinterpret_cast<int*>(ring.empty + kSched);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(ring.unit + kSched);
+    uint64_t* ybar = reinterpret_cast<uint64_t*>(ring.unit + kSched + 2);  // [2]: y tiles of the folded BatchNorm-backward reduction
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -262,6 +326,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         if (p.epilogue == CAB_EPI_ACT_BF16) {
             tma_prefetch_desc(&p.omap_hi);
             if (p.out_lo != nullptr) tma_prefetch_desc(&p.omap_lo);
+            if (p.bnr_partials != nullptr) tma_prefetch_desc(&p.ymap);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -277,6 +342,8 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
             mbar_init(&ring.full[i], 1);
             mbar_init(&ring.empty[i], 5);  // MMA thread + one per epilogue warp
         }
+        mbar_init(&ybar[0], 1);
+        mbar_init(&ybar[1], 1);
         mbar_fence_init();
     }
     if (warp == 2) {
@@ -378,6 +445,8 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
         cur.init(p);
         float run_m = -INFINITY, run_s = 0.f;  // CAB_EPI_LOGITS_ROWS: online softmax of this thread's row across N tiles
         int run_i = 0;
+        uint32_t yphase = 0;  // bit i = parity ybar[i] completes next
+        const bool fold = p.bnr_partials != nullptr;  // (host: ACT_BF16 epilogue, no lo output, no stats)
         int u = 0, nt_next = 0, j = 0;
         for (;;) {
             CAB_NEXT_UNIT(sched_consume<true>(p, ring, j++, lane))
@@ -400,6 +469,20 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                 const bool keep = t < len;
                 const int et = threadIdx.x - 128;  // 0..127 within the epilogue warps
                 const bool has_lo = p.out_lo != nullptr;
+                uint8_t* const ystage = smem + kOffStageOut + 2 * kEpiTileBytes;  // the lo staging pair is free in the bf16 tier
+                int bnr_rows = 0;
+                if (fold) {
+                    // y tile of this tile's first chunk: buffer (epi_chunks & 1) was last read two chunks ago, and every thread
+                    // finished that read before the epi_bar(2) of the chunk after it, which this thread has passed
+                    if (et == 0) {
+                        const int ybuf = epi_chunks & 1;
+                        mbar_expect_tx(&ybar[ybuf], kEpiTileBytes);
+                        tma_load_3d(ystage + ybuf * kEpiTileBytes, &p.ymap, &ybar[ybuf], n0, t0, b);
+                    }
+                    int blen = p.T_out;
+                    if (p.bnr_xlen != nullptr) blen = min(blen, frac_len(__ldg(p.bnr_xlen + b), p.T_out));
+                    bnr_rows = min(max(blen - t0, 0), kBlockM);
+                }
                 // stage this tile's bias (zeros past C_out / without bias)
                 epi_bar(1);  // previous tile's readers are done with s_bias
                 for (int i = et; i < block_n; i += 128) {
@@ -426,7 +509,20 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                     uint8_t* st_lo = stage + (2 + buf) * kEpiTileBytes;
                     // the TMA store that last read this buffer was committed two chunks ago
                     if (et == 0) bulk_wait_read<1>();
+                    float bnr_sc = 0.f, bnr_sh = 0.f;
+                    const int bnr_col = n0 + c0 + (et & 31);
+                    if (fold && bnr_col < p.bnr_C) {
+                        bnr_sc = __ldg(p.bnr_ss + bnr_col);
+                        bnr_sh = __ldg(p.bnr_ss + p.bnr_C + bnr_col);
+                    }
                     epi_bar(2);
+                    if (fold && et == 0 && c0 + kEpiCols < block_n && n0 + c0 + kEpiCols < p.C_out) {
+                        // y tile of the NEXT chunk of this tile into the other buffer: its last readers (the column pass of the
+                        // previous chunk) all arrived at the barrier above
+                        const int ynext = (epi_chunks + 1) & 1;
+                        mbar_expect_tx(&ybar[ynext], kEpiTileBytes);
+                        tma_load_3d(ystage + ynext * kEpiTileBytes, &p.ymap, &ybar[ynext], n0 + c0 + kEpiCols, t0, b);
+                    }
                     const float* sb = s_bias + c0;
 #define CAB_EPI_CALL(ACT)                                                                          \
     if (has_lo) epi_chunk<ACT, true>(v, sb, p.act_a, p.act_b, keep, row, st_hi, st_lo);            \
@@ -438,7 +534,7 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                         default: CAB_EPI_CALL(CAB_ACT_NONE) break;
                     }
 #undef CAB_EPI_CALL
-                    if (p.stats != nullptr) {
+                    if (p.stats != nullptr && !p.stats_columns) {
                         // BatchNorm batch statistics of what was just stored (bf16-rounded; hi + lo in the split
                         // tier), valid rows only
                         float xs[32], xq[32];
@@ -477,6 +573,37 @@ conv1d_umma_kernel(const __grid_constant__ ConvParams p) {
                         tma_store_3d(&p.omap_hi, st_hi, n0 + c0, t0, b);  // rows >= T_out are clipped
                         if (has_lo) tma_store_3d(&p.omap_lo, st_lo, n0 + c0, t0, b);
                         bulk_commit();
+                    }
+                    if (p.stats != nullptr && p.stats_columns) {
+                        // batch statistics, column-parallel over the staged tile (every thread's row is there: barrier 3 above; the
+                        // buffer is rewritten two chunks from now, behind that chunk's barrier 2)
+                        float cs, cq;
+                        const int srows = min(max(p.T_out - t0, 0), kBlockM);
+                        if (has_lo) stats_column_pass<true>(st_hi, st_lo, et, srows, cs, cq);
+                        else stats_column_pass<false>(st_hi, st_lo, et, srows, cs, cq);
+                        const int col = n0 + c0 + (et & 31);
+                        if (col < p.C_out && srows > (et >> 5) * 32) {
+                            atomicAdd(p.stats + col, (double)cs);
+                            atomicAdd(p.stats + p.C_out + col, (double)cq);
+                        }
+                    }
+                    if (fold) {
+                        // every thread's row of g is staged (barrier 3 above); the y tile was requested a chunk ago
+                        mbar_wait(&ybar[buf], (yphase >> buf) & 1u);
+                        yphase ^= 1u << buf;
+                        const uint8_t* st_y = ystage + buf * kEpiTileBytes;
+                        float cs, cq;
+                        switch (p.bnr_act) {
+                            case CAB_ACT_RELU: bnr_column_pass<CAB_ACT_RELU>(st_hi, st_y, et, bnr_rows, bnr_sc, bnr_sh, p.bnr_a, p.bnr_b, cs, cq); break;
+                            case CAB_ACT_HARDTANH: bnr_column_pass<CAB_ACT_HARDTANH>(st_hi, st_y, et, bnr_rows, bnr_sc, bnr_sh, p.bnr_a, p.bnr_b, cs, cq); break;
+                            case CAB_ACT_LEAKY_RELU: bnr_column_pass<CAB_ACT_LEAKY_RELU>(st_hi, st_y, et, bnr_rows, bnr_sc, bnr_sh, p.bnr_a, p.bnr_b, cs, cq); break;
+                            default: bnr_column_pass<CAB_ACT_NONE>(st_hi, st_y, et, bnr_rows, bnr_sc, bnr_sh, p.bnr_a, p.bnr_b, cs, cq); break;
+                        }
+                        if (bnr_col < p.bnr_C && bnr_rows > (et >> 5) * 32) {
+                            double* dst = p.bnr_partials + (size_t)(blockIdx.x % CAB_BN_SUM_REPLICAS) * 2 * p.bnr_C;
+                            atomicAdd(dst + bnr_col, (double)cs);
+                            atomicAdd(dst + p.bnr_C + bnr_col, (double)cq);
+                        }
                     }
                     ++epi_chunks;
                 }
@@ -855,6 +982,28 @@ extern "C" int cab_conv1d_fused(const cab_conv_source_t* srcs, int n_src,
         }
     }
     if (p.stats != nullptr) CAB_CHECK_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(double) * 2 * ep->C_out, stream));
+    {
+        static int stats_columns = -1;  // CONVASR_B200_STATS_COLUMNS=0: the round-1 shuffle-butterfly statistics (A/B switch)
+        if (stats_columns < 0) {
+            const char* e = getenv("CONVASR_B200_STATS_COLUMNS");
+            stats_columns = (e && e[0] == '0') ? 0 : 1;
+        }
+        p.stats_columns = stats_columns;
+    }
+    // folded BatchNorm-backward reduction (see ConvParams)
+    p.bnr_partials = nullptr; p.bnr_ss = nullptr; p.bnr_xlen = nullptr; p.bnr_C = 0; p.bnr_act = CAB_ACT_NONE; p.bnr_a = 0.f; p.bnr_b = 0.f;
+    if (ep->bnr_partials != nullptr) {
+        CAB_CHECK_ARG(ep->epilogue == CAB_EPI_ACT_BF16 && ep->out_lo == nullptr && ep->stats == nullptr, "the folded BatchNorm-backward reduction needs the bf16 activation epilogue without a lo output and without forward statistics");
+        CAB_CHECK_ARG(ep->bnr_y != nullptr && ep->bnr_ss != nullptr && ep->bnr_C > 0 && ep->bnr_C <= ep->C_out, "folded BatchNorm-backward reduction: bad y / ss / C=%d", ep->bnr_C);
+        CAB_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->bnr_y) & 15) == 0, "bnr_y must be 16-byte aligned");
+        p.bnr_partials = ep->bnr_partials; p.bnr_ss = ep->bnr_ss; p.bnr_xlen = ep->bnr_xlen_frac; p.bnr_C = ep->bnr_C;
+        p.bnr_act = ep->bnr_act; p.bnr_a = ep->bnr_act_a; p.bnr_b = ep->bnr_act_b;
+        int rc = encode_map_3d(&p.ymap, ep->bnr_y, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,
+                               (uint64_t)ep->out_ld_ch, (uint64_t)ep->out_T_rows * ep->out_ld_ch, kEpiCols, kBlockM,
+                               CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        CAB_CHECK_CUDA(cudaMemsetAsync(p.bnr_partials, 0, sizeof(double) * CAB_BN_SUM_REPLICAS * 2 * ep->bnr_C, stream));
+    }
     if (ep->epilogue == CAB_EPI_ACT_BF16) {
         CAB_CHECK_ARG(ep->out_lo == nullptr || (reinterpret_cast<uintptr_t>(ep->out_lo) & 15) == 0, "out_lo must be 16-byte aligned");
         int rc = encode_map_3d(&p.omap_hi, ep->out_hi, (uint64_t)ep->out_ld_ch, (uint64_t)ep->T_out, (uint64_t)ep->B,

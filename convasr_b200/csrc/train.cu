@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "../../include/convasr_b200.h"
 #include <atomic>
+#include <cstdlib>
 
 namespace cab {
 extern std::atomic<int64_t> g_launch_count;
@@ -29,6 +30,24 @@ __device__ __forceinline__ float act_grad(float z, int act, float a, float b) {
         case CAB_ACT_LEAKY_RELU: return z > 0.f ? 1.f : a;
         default: return 1.f;
     }
+}
+
+// compile-time activation (the streamed kernels are instantiated per activation: a run-time switch per element cost ~28
+// instructions of uniform branches per value and made the kernels issue bound at 50 % of the slots, ncu round 1)
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float z, float a, float b) {
+    if (ACT == CAB_ACT_RELU) return fmaxf(z, 0.f);
+    if (ACT == CAB_ACT_HARDTANH) return fminf(fmaxf(z, a), b);
+    if (ACT == CAB_ACT_LEAKY_RELU) return z > 0.f ? z : z * a;
+    return z;
+}
+// g * act'(z): a select for the 0 / 1 gates
+template <int ACT>
+__device__ __forceinline__ float act_gate_t(float g, float z, float a, float b) {
+    if (ACT == CAB_ACT_RELU) return z > 0.f ? g : 0.f;
+    if (ACT == CAB_ACT_HARDTANH) return (z > a && z < b) ? g : 0.f;
+    if (ACT == CAB_ACT_LEAKY_RELU) return z > 0.f ? g : g * a;
+    return g;
 }
 
 // Dropout keep-decision: counter-based, recomputed identically in the backward pass (no mask is
@@ -366,6 +385,7 @@ struct StreamArgs {
     float a, bb, drop_p, inv_n;
     int B, T, C, ld, act;
     int vectors, rows_per_chunk, n_chunks, stages, stage_bytes;
+    int reverse;
 };
 
 __device__ __forceinline__ void add8(float (&f)[8], const uint4& lo) {
@@ -383,7 +403,7 @@ __device__ __forceinline__ uint4 pack8_lo(const float (&f)[8], const uint4& hi) 
     return pack8(r);
 }
 
-template <int MODE, bool SPLIT>  // 0: forward, 1: backward reduce, 2: backward apply
+template <int MODE, bool SPLIT, int ACT>  // MODE 0: forward, 1: backward reduce, 2: backward apply; ACT: the activation, compile time
 __global__ void __launch_bounds__(kStreamMaxThreads)
 bn_stream_kernel(const StreamArgs p) {
     constexpr int NT = MODE == 0 ? 1 : 2;          // tensors read (y [, g])
@@ -399,7 +419,11 @@ bn_stream_kernel(const StreamArgs p) {
     }
     __syncthreads();
     const int stride = gridDim.x;
-    auto issue = [&](int chunk, int s) {
+    // p.reverse: walk the chunks from the last row to the first.  The producer of the tensor (a conv / dgrad GEMM, or the pass
+    // before this one) finished with the high rows, so those are what is still resident in L2; an ascending walk over a tensor
+    // larger than what L2 keeps would evict exactly the lines it is about to need.
+    auto issue = [&](int ci, int s) {
+        const int chunk = p.reverse ? p.n_chunks - 1 - ci : ci;
         const int row0 = chunk * p.rows_per_chunk;
         const uint32_t bytes = (uint32_t)(min(p.rows_per_chunk, R - row0) * ld) * 2u;
         unsigned char* dst = smem_raw + (size_t)s * NIN * p.stage_bytes;
@@ -466,12 +490,14 @@ bn_stream_kernel(const StreamArgs p) {
             k0[e] = -sc[e] * (m1 * p.inv_n) - k1[e] * mean;  // constant term
         }
     }
+    const float act_a = p.a, act_b = p.bb;
     const bool dropping = p.drop_p > 0.f;
     const unsigned long long seed = dropping ? (unsigned long long)p.seed_ptr[0] + p.salt * 0xD1B54A32D192ED03ULL : 0ull;
     const float inv_keep = dropping ? 1.f / (1.f - p.drop_p) : 1.f;
 
     int it = 0;
-    for (int chunk = blockIdx.x; chunk < p.n_chunks; chunk += stride, ++it) {
+    for (int ci = blockIdx.x; ci < p.n_chunks; ci += stride, ++it) {
+        const int chunk = p.reverse ? p.n_chunks - 1 - ci : ci;
         const int s = it % p.stages;
         mbar_wait(&full[s], (uint32_t)(it / p.stages) & 1u);
         const unsigned char* src = smem_raw + (size_t)s * NIN * p.stage_bytes;
@@ -499,7 +525,7 @@ bn_stream_kernel(const StreamArgs p) {
             if (SPLIT) add8(yf, *reinterpret_cast<const uint4*>(src + (size_t)NT * p.stage_bytes + unit * 16));
             if (MODE == 0) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = (keep && c0 + e < C) ? act_fwd(fmaf(yf[e], sc[e], sh[e]), p.act, p.a, p.bb) : 0.f;
+                for (int e = 0; e < 8; ++e) o[e] = (keep && c0 + e < C) ? act_fwd_t<ACT>(fmaf(yf[e], sc[e], sh[e]), act_a, act_b) : 0.f;
                 if (dropping) {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = dropout_keep(seed, (unsigned long long)rr * ld + c0 + e, p.drop_p) ? o[e] * inv_keep : 0.f;
@@ -515,7 +541,7 @@ bn_stream_kernel(const StreamArgs p) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     // padded rows may hold anything in g (nobody is required to write them): select, never multiply
-                    const float dz = keep ? gf[e] * act_grad(fmaf(yf[e], sc[e], sh[e]), p.act, p.a, p.bb) : 0.f;
+                    const float dz = keep ? act_gate_t<ACT>(gf[e], fmaf(yf[e], sc[e], sh[e]), act_a, act_b) : 0.f;
                     if (MODE == 1) {
                         acc_s[e] += dz;
                         acc_q[e] = fmaf(dz, yf[e], acc_q[e]);
@@ -531,7 +557,7 @@ bn_stream_kernel(const StreamArgs p) {
             }
         }
         __syncthreads();  // everybody is done reading stage s
-        if (tid == 0 && chunk + p.stages * stride < p.n_chunks) issue(chunk + p.stages * stride, s);
+        if (tid == 0 && ci + p.stages * stride < p.n_chunks) issue(ci + p.stages * stride, s);
     }
     if (MODE == 1) {
         // every issued chunk was consumed, so the stages are free: reduce the 16 partials over the row lanes
@@ -585,6 +611,16 @@ static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& thr
     return true;
 }
 
+// CONVASR_B200_BN_ORDER=0 restores the ascending walk everywhere (A/B switch); default: L2-aware order
+static int bn_l2_order() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("CONVASR_B200_BN_ORDER");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 static int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -596,11 +632,11 @@ static int num_sms() {
     return n;
 }
 
-template <int MODE, bool SPLIT>
-static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, size_t smem, cudaStream_t stream) {
+template <int MODE, bool SPLIT, int ACT>
+static cudaError_t stream_launch_act(const StreamArgs& a, int threads, int grid, size_t smem, cudaStream_t stream) {
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bn_stream_kernel<MODE, SPLIT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
@@ -610,15 +646,24 @@ static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, siz
     for (int i = 0; i < n_cache; ++i)
         if (cache_threads[i] == threads && cache_smem[i] == (int)smem) per_sm = cache_per_sm[i];
     if (per_sm == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_stream_kernel<MODE, SPLIT>, threads, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_stream_kernel<MODE, SPLIT, ACT>, threads, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
         if (n_cache < 8) { cache_threads[n_cache] = threads; cache_smem[n_cache] = (int)smem; cache_per_sm[n_cache] = per_sm; ++n_cache; }
     }
     (void)grid;
     const int g = a.n_chunks < num_sms() * per_sm ? a.n_chunks : num_sms() * per_sm;
-    bn_stream_kernel<MODE, SPLIT><<<g, threads, smem, stream>>>(a);
+    bn_stream_kernel<MODE, SPLIT, ACT><<<g, threads, smem, stream>>>(a);
     return cudaGetLastError();
+}
+template <int MODE, bool SPLIT>
+static cudaError_t stream_launch(const StreamArgs& a, int threads, int grid, size_t smem, cudaStream_t stream) {
+    switch (a.act) {
+        case CAB_ACT_RELU: return stream_launch_act<MODE, SPLIT, CAB_ACT_RELU>(a, threads, grid, smem, stream);
+        case CAB_ACT_HARDTANH: return stream_launch_act<MODE, SPLIT, CAB_ACT_HARDTANH>(a, threads, grid, smem, stream);
+        case CAB_ACT_LEAKY_RELU: return stream_launch_act<MODE, SPLIT, CAB_ACT_LEAKY_RELU>(a, threads, grid, smem, stream);
+        default: return stream_launch_act<MODE, SPLIT, CAB_ACT_NONE>(a, threads, grid, smem, stream);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -978,6 +1023,7 @@ extern "C" int cab_bn_act_mask_fwd(const void* y, const void* y_lo, const float*
         sa.y_lo = static_cast<const __nv_bfloat16*>(y_lo); sa.out_lo = static_cast<__nv_bfloat16*>(out_lo);
         sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
         sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+        sa.reverse = bn_l2_order();  // the conv that produced y finished with the high rows
         if (split) CAB_CHECK_CUDA((stream_launch<0, true>(sa, threads, grid_s, smem, stream)));
         else CAB_CHECK_CUDA((stream_launch<0, false>(sa, threads, grid_s, smem, stream)));
         g_launch_count.fetch_add(1, std::memory_order_relaxed);
@@ -1019,16 +1065,17 @@ extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const 
     sa.raw_sums = raw_sums; sa.sums_ld = sums_ld; sa.gamma = gamma; sa.beta = beta; sa.running_mean = running_mean; sa.running_var = running_var;
     sa.ss_out = out_ss; sa.n_rows = (float)n_rows; sa.eps = eps; sa.momentum = momentum;
     sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+    sa.reverse = bn_l2_order();
     if (split) CAB_CHECK_CUDA((stream_launch<0, true>(sa, threads, grid_s, smem, stream)));
     else CAB_CHECK_CUDA((stream_launch<0, false>(sa, threads, grid_s, smem, stream)));
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
-extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
-                                   int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
-                                   float* sums /*[2][C]: dbeta, dgamma*/, void* grad_y, void* grad_y_lo, float dropout_p,
-                                   const int64_t* seed, int64_t salt, int frozen, double* ws_partials, cab_stream_t stream_) {
+static int bn_bwd_impl(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
+                       int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
+                       float* sums /*[2][C]: dbeta, dgamma*/, void* grad_y, void* grad_y_lo, float dropout_p,
+                       const int64_t* seed, int64_t salt, int frozen, double* ws_partials, bool partials_ready, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CAB_CHECK_ARG(y && grad_out && ss && sums && grad_y, "null pointer argument");
     CAB_CHECK_ARG(ld % 8 == 0 && ld >= C, "bad channel layout");
@@ -1047,18 +1094,32 @@ extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* 
             sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
             sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.inv_n = frozen ? 0.f : 1.f / (float)(B * T);  // frozen: grad_y = scale * dz
             sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
+            if (partials_ready) {
+                // the dgrad GEMM that produced grad_out also accumulated the sums and finished with the high rows: descend
+                sa.reverse = bn_l2_order();
+                if (split) CAB_CHECK_CUDA((stream_launch<2, true>(sa, threads, grid_s, smem, stream)));
+                else CAB_CHECK_CUDA((stream_launch<2, false>(sa, threads, grid_s, smem, stream)));
+                g_launch_count.fetch_add(1, std::memory_order_relaxed);
+                return 0;
+            }
             CAB_CHECK_CUDA(cudaMemsetAsync(ws_partials, 0, sizeof(double) * kBnSumReplicas * 2 * C, stream));
+            // reduce pass: descending (the dgrad GEMM that produced grad_out finished with the high rows); apply pass: ascending
+            // (the reduce pass finished with the low rows)
+            StreamArgs sr = sa;
+            sr.reverse = bn_l2_order();
+            sa.reverse = 0;
             if (split) {
-                CAB_CHECK_CUDA((stream_launch<1, true>(sa, threads, grid_s, smem, stream)));
+                CAB_CHECK_CUDA((stream_launch<1, true>(sr, threads, grid_s, smem, stream)));
                 CAB_CHECK_CUDA((stream_launch<2, true>(sa, threads, grid_s, smem, stream)));
             } else {
-                CAB_CHECK_CUDA((stream_launch<1, false>(sa, threads, grid_s, smem, stream)));
+                CAB_CHECK_CUDA((stream_launch<1, false>(sr, threads, grid_s, smem, stream)));
                 CAB_CHECK_CUDA((stream_launch<2, false>(sa, threads, grid_s, smem, stream)));
             }
             g_launch_count.fetch_add(2, std::memory_order_relaxed);
             return 0;
         }
     }
+    CAB_CHECK_ARG(!partials_ready, "cab_bn_act_mask_bwd_apply: row pitch ld=%d is not covered by the streamed kernel", ld);
     CAB_CHECK_ARG(!split, "split-bf16 BatchNorm backward needs ws_partials and a row pitch the streamed kernel covers (ld=%d)", ld);
     CAB_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, stream));
     const int R = B * T, rpb = rows_per_block_for(R, ld);
@@ -1069,6 +1130,23 @@ extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* 
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(2, std::memory_order_relaxed);
     return 0;
+}
+
+extern "C" int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
+                                   int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
+                                   float* sums, void* grad_y, void* grad_y_lo, float dropout_p, const int64_t* seed, int64_t salt,
+                                   int frozen, double* ws_partials, cab_stream_t stream_) {
+    return bn_bwd_impl(y, y_lo, grad_out, grad_out_lo, ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, grad_y, grad_y_lo, dropout_p, seed, salt,
+                       frozen, ws_partials, false, stream_);
+}
+
+extern "C" int cab_bn_act_mask_bwd_apply(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo, const float* ss,
+                                         int B, int T, int C, int ld, int act, float act_a, float act_b, const float* xlen_frac,
+                                         float* sums, void* grad_y, void* grad_y_lo, float dropout_p, const int64_t* seed, int64_t salt,
+                                         int frozen, const double* partials, cab_stream_t stream_) {
+    CAB_CHECK_ARG(partials != nullptr, "partials is null");
+    return bn_bwd_impl(y, y_lo, grad_out, grad_out_lo, ss, B, T, C, ld, act, act_a, act_b, xlen_frac, sums, grad_y, grad_y_lo, dropout_p, seed, salt,
+                       frozen, const_cast<double*>(partials), true, stream_);
 }
 
 extern "C" int cab_bn_multi_act_mask_fwd(const cab_bn_branch_t* branches, int n_branches, int B, int T, int C, int ld, int act,

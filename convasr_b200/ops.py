@@ -157,10 +157,13 @@ class Source:
 def conv1d_fused(
 	sources, B, T_out, C_out, bias = None, act = _lib.ACT_NONE, act_a = 0.0, act_b = 0.0, xlen = None, out_hi = None,
 	out_lo = None, logits = None, log_probs = None, argmax = None, epilogue = _lib.EPI_ACT_BF16, block_n = 0, stats = None,
-	skip = None
+	skip = None, bn_reduce = None
 ):
 	"""skip = (frac [B] fp32, T, margin): output rows t >= ceil(frac[b]*T) + margin are structural zeros (ragged-batch
-	padding) -- whole 128-row tiles there are stored as zeros without being computed"""
+	padding) -- whole 128-row tiles there are stored as zeros without being computed.
+	bn_reduce = (y bf16 [B, T_out, ld] like out_hi, ss fp32 [4, C], C, act, act_a, act_b, xlen or None, partials fp64
+	[BN_SUM_REPLICAS, 2, C]): the launch is the dgrad GEMM producing dL/d(out) of a ConvBn1d repeat; its epilogue also
+	accumulates that repeat's BatchNorm-backward channel sums (cab_conv_epilogue_t.bnr_*)"""
 	_need_cuda(*(s.act for s in sources), bias, xlen, out_hi, out_lo, logits, log_probs, argmax)
 	n = len(sources)
 	arr = (_lib.ConvSource * n)(*[s.to_c() for s in sources])
@@ -183,6 +186,14 @@ def conv1d_fused(
 	if skip is not None:
 		_need_cuda(skip[0])
 		ep.skip_frac, ep.skip_T, ep.skip_margin = skip[0].data_ptr(), int(skip[1]), int(skip[2])
+	if bn_reduce is not None:
+		y, ss, C, b_act, b_a, b_b, b_xlen, partials = bn_reduce
+		_need_cuda(y, ss, b_xlen, partials)
+		assert out_hi is not None and out_lo is None and stats is None and y.shape == out_hi.shape and y.dtype == BF16 and y.is_contiguous()
+		assert ss.dtype == torch.float32 and ss.shape == (4, C) and ss.is_contiguous() and partials.dtype == torch.float64 and partials.numel() >= _lib.BN_SUM_REPLICAS * 2 * C
+		ep.bnr_y, ep.bnr_ss, ep.bnr_partials = y.data_ptr(), ss.data_ptr(), partials.data_ptr()
+		ep.bnr_xlen_frac = None if b_xlen is None else b_xlen.data_ptr()
+		ep.bnr_C, ep.bnr_act, ep.bnr_act_a, ep.bnr_act_b = int(C), int(b_act), float(b_a), float(b_b)
 	rc = _lib.load().cab_conv1d_fused(arr, n, ctypes.byref(ep), _stream())
 	_lib.check(rc, 'cab_conv1d_fused')
 

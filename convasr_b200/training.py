@@ -41,6 +41,8 @@ from . import _lib, engine, ops
 BF16 = torch.bfloat16
 _SEPARATE_BN_STATS = os.environ.get('CONVASR_B200_SEPARATE_BN_STATS', '0') == '1'
 _SKIP_PADDING = os.environ.get('CONVASR_B200_SKIP_PADDING', '1') == '1'  # A/B switch: leave tiles of pure padding out
+# BatchNorm-backward channel sums accumulated by the dgrad GEMM's epilogue instead of a separate pass over (y, g)
+_FOLD_BN_REDUCE = os.environ.get('CONVASR_B200_FOLD_BN_REDUCE', '1') == '1'
 _GRAD_BUCKET_MB = int(os.environ.get('CONVASR_B200_GRAD_BUCKET_MB', '64'))  # data-parallel gradient bucket size; 0 = one collective per layer
 
 
@@ -442,11 +444,13 @@ class NativeStack(torch.autograd.Function):
 		pending = {reps[-1].out_id: [('gemm', g_cl, (ctx.w_dec[1], ctx.w_dec[3]), c_ld, 1, 1, 0, T)]}
 		eyes = {}
 
-		def materialize(act_id, T_act, ld):
-			"""sum of all contributions to d(loss)/d(activation): ONE fused GEMM launch over every consumer"""
+		def materialize(act_id, T_act, ld, bn_reduce = None):
+			"""sum of all contributions to d(loss)/d(activation): ONE fused GEMM launch over every consumer.  bn_reduce (see
+			ops.conv1d_fused): fold the BatchNorm-backward reduction of the repeat that produced this activation into that launch;
+			returns (gradient, folded?)"""
 			contribs = pending.pop(act_id)
 			if len(contribs) == 1 and contribs[0][0] == 'direct':
-				return contribs[0][1]
+				return contribs[0][1], False
 			srcs = []
 			for c in contribs:
 				if c[0] == 'gemm':
@@ -463,6 +467,7 @@ class NativeStack(torch.autograd.Function):
 			# gradient rows of masked frames are never read (the mask's backward selects, it does not multiply)
 			skip = (xlen, T_act, 0) if (_SKIP_PADDING and xlen is not None and masked[act_id]) else None
 			gx = None
+			folded = False
 			while srcs:
 				# more consumers than one launch has K segments (dense 'Big' models in the split tier): chain launches, the
 				# partial sum re-enters as an identity segment
@@ -473,23 +478,29 @@ class NativeStack(torch.autograd.Function):
 						eyes[ld] = torch.eye(ld, dtype = BF16, device = dev).unsqueeze(0).contiguous()
 					now = now + [ops.Source(gx.hi, eyes[ld], ld, 1, 1, 0, T_in = T_act)] + ([ops.Source(gx.lo, eyes[ld], ld, 1, 1, 0, T_in = T_act)] if split else [])
 				nxt = _empty_act(B, T_act, ld, dev, split)
-				ops.conv1d_fused(now, B, T_act, ld, out_hi = nxt.hi, out_lo = nxt.lo, skip = skip)
+				fold_now = bn_reduce if (not srcs and not split) else None  # the launch that writes the final sum
+				ops.conv1d_fused(now, B, T_act, ld, out_hi = nxt.hi, out_lo = nxt.lo, skip = skip, bn_reduce = fold_now)
+				folded = fold_now is not None
 				gx = nxt
-			return gx
+			return gx, folded
 
 		for rep, rec in zip(reversed(reps), reversed(saved)):
 			cv = rep.conv
 			T_out = rec['T_out']
-			gx = materialize(rep.out_id, T_out, cv.co_alloc)
 			code, a, b = rep.act
 			y, ss = rec['y'], rec['ss']
+			bn_reduce = None
+			if _FOLD_BN_REDUCE and not split and rec['branches'] is None and rep.dropout == 0 and cv.co_alloc % 8 == 0 and (cv.co_alloc // 8) <= 512:
+				bn_reduce = (y.hi, ss, cv.C_out, code, a, b, xlen if rep.mask else None, partials)
+			gx, folded = materialize(rep.out_id, T_out, cv.co_alloc, bn_reduce)
 			mask_ptr = ops._p(xlen if rep.mask else None)
 			sums = take(2 * cv.C_out).view(2, cv.C_out)
 			dy = _empty_act(B, T_out, cv.co_alloc, dev, split)
 			if rec['branches'] is None:
-				rc = lib.cab_bn_act_mask_bwd(ops._p(y.hi), ops._p(y.lo), ops._p(gx.hi), ops._p(gx.lo), ops._p(ss), B, T_out, cv.C_out, cv.co_alloc, code, a, b, mask_ptr, ops._p(sums), ops._p(dy.hi), ops._p(dy.lo),
-												rep.dropout, ops._p(ctx.seed), rep.salt, int(not rep.bn.training), ops._p(partials), ops._stream())
-				_lib.check(rc, 'cab_bn_act_mask_bwd')
+				fn, name = (lib.cab_bn_act_mask_bwd_apply, 'cab_bn_act_mask_bwd_apply') if folded else (lib.cab_bn_act_mask_bwd, 'cab_bn_act_mask_bwd')
+				rc = fn(ops._p(y.hi), ops._p(y.lo), ops._p(gx.hi), ops._p(gx.lo), ops._p(ss), B, T_out, cv.C_out, cv.co_alloc, code, a, b, mask_ptr, ops._p(sums), ops._p(dy.hi), ops._p(dy.lo),
+						rep.dropout, ops._p(ctx.seed), rep.salt, int(not rep.bn.training), ops._p(partials), ops._stream())
+				_lib.check(rc, name)
 			else:
 				out = rec['out']
 				dz = _empty_act(B, T_out, cv.co_alloc, dev, split)
@@ -543,7 +554,7 @@ class NativeStack(torch.autograd.Function):
 			gconv, h = rep.grouped, rec['h']
 			pending[('h', rep.salt)] = [contrib]
 			masked[('h', rep.salt)] = False
-			dh = materialize(('h', rep.salt), h.T, cv.ci_alloc)
+			dh, _ = materialize(('h', rep.salt), h.T, cv.ci_alloc)
 			dzh = _empty_act(B, h.T, cv.ci_alloc, dev, split)
 			rc = lib.cab_act_mask_bwd_dz(ops._p(h.hi), ops._p(h.lo), ops._p(dh.hi), ops._p(dh.lo), B, h.T, gconv.out_channels, cv.ci_alloc, _lib.ACT_RELU, 0.0, 0.0, None, ops._p(dzh.hi), ops._p(dzh.lo), 0.0, None, 0, ops._stream())
 			_lib.check(rc, 'cab_act_mask_bwd_dz')

@@ -26,7 +26,7 @@ extern "C" {
 
 typedef void* cab_stream_t; /* cudaStream_t */
 
-#define CAB_ABI_VERSION 2
+#define CAB_ABI_VERSION 3
 
 int cab_abi_version(void);
 const char* cab_last_error(void);
@@ -148,6 +148,20 @@ typedef struct {
                                 range are not computed and are stored as zeros.  With xlen_frac set and skip_frac
                                 NULL the launch's own temporal mask implies (xlen_frac, T_out, 0). */
     int32_t skip_T, skip_margin;
+    /* Training, bf16 tier: BatchNorm-backward reduction folded into the dgrad launch that produces g = dL/d(out) of a
+     * ConvBn1d repeat (models.py:127-139 under autograd).  bnr_partials (NULL = off): fp64
+     * [CAB_BN_SUM_REPLICAS][2][bnr_C]; the call zeroes it and the epilogue accumulates, per channel, sum(dz) and
+     * sum(dz * y) with dz = g * act'(y*scale + shift) * (t < ceil(bnr_xlen_frac[b]*T_out)), g as stored (bf16).
+     * bnr_y: that repeat's pre-BatchNorm conv output, bf16 with the geometry of out_hi ([B, out_T_rows, out_ld_ch]);
+     * bnr_ss: fp32 [4][bnr_C] as written by cab_bn_finalize / cab_bn_act_mask_fwd_stats (scale, shift, ...).
+     * cab_bn_act_mask_bwd_apply then finishes the BatchNorm backward without re-reading (y, g) for the sums.
+     * Needs out_lo == NULL and stats == NULL. */
+    const void* bnr_y;
+    const float* bnr_ss;
+    const float* bnr_xlen_frac;
+    double* bnr_partials;
+    int32_t bnr_C, bnr_act;       /* real channel count; CAB_ACT_* of the repeat */
+    float bnr_act_a, bnr_act_b;
 } cab_conv_epilogue_t;
 
 int cab_conv1d_fused(const cab_conv_source_t* sources_host, int n_sources,
@@ -205,6 +219,15 @@ int cab_bn_act_mask_bwd(const void* y, const void* y_lo, const void* grad_out, c
                         const int64_t* seed, int64_t salt, int frozen,
                         double* ws_partials /* fp64 [CAB_BN_SUM_REPLICAS][2][C] scratch, or NULL */,
                         cab_stream_t stream);
+/* Second half of cab_bn_act_mask_bwd alone: `partials` (fp64 [CAB_BN_SUM_REPLICAS][2][C]) already hold the channel sums --
+ * accumulated by the dgrad launch that produced grad_out (cab_conv_epilogue_t.bnr_partials) -- so only the apply pass runs:
+ * sums = [dbeta, dgamma], grad_y.  bf16 tier or split tier alike; dropout_p must be what the sums were taken with (0 for the
+ * folded reduction). */
+int cab_bn_act_mask_bwd_apply(const void* y, const void* y_lo, const void* grad_out, const void* grad_out_lo,
+                              const float* ss, int B, int T, int C, int ld, int act, float act_a, float act_b,
+                              const float* xlen_frac, float* sums, void* grad_y, void* grad_y_lo, float dropout_p,
+                              const int64_t* seed, int64_t salt, int frozen, const double* partials,
+                              cab_stream_t stream);
 /* cab_bn_finalize + cab_bn_act_mask_fwd in one launch: every CTA derives the coefficients of its channels from
  * the raw sums of the conv epilogue (raw_sums: fp32 [2][sums_ld]); CTA 0 also writes out_ss and moves the
  * running statistics. */

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 	for name in declared_symbols():
 		assert hasattr(lib, name), f'{name} declared in the header but not exported'
 	loaded = _lib.load()
-	assert loaded.cab_abi_version() == _lib.ABI_VERSION == 2
+	assert loaded.cab_abi_version() == _lib.ABI_VERSION == 3
 	# the ctypes table binds exactly the declared compute entry points
 	assert sorted(_lib.SIGNATURES) == sorted(s for s in declared_symbols() if s not in _lib.INTROSPECTION)
 
@@ -70,4 +70,6 @@ def test_ctypes_table_matches_header_prototypes():
 	assert ctypes.sizeof(_lib.BnBranch) == 24
 	assert _lib.ConvEpilogue.skip_frac.offset == _lib.ConvEpilogue.stats.offset + 8
 	assert _lib.ConvEpilogue.skip_margin.offset == _lib.ConvEpilogue.skip_frac.offset + 12
-	assert ctypes.sizeof(_lib.ConvEpilogue) == _lib.ConvEpilogue.skip_frac.offset + 16
+	assert _lib.ConvEpilogue.bnr_y.offset == _lib.ConvEpilogue.skip_frac.offset + 16
+	assert _lib.ConvEpilogue.bnr_C.offset == _lib.ConvEpilogue.bnr_y.offset + 32
+	assert ctypes.sizeof(_lib.ConvEpilogue) == _lib.ConvEpilogue.bnr_y.offset + 48

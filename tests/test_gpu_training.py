@@ -383,6 +383,79 @@ def test_padding_tiles_are_skipped_exactly():
 		assert rel(part, full) < 1e-6, rel(part, full)
 
 
+def test_bn_backward_reduction_folded_into_the_dgrad_epilogue():
+	"""cab_conv_epilogue_t.bnr_*: the dgrad GEMM accumulates the BatchNorm-backward channel sums of the repeat whose output
+	gradient it produces, cab_bn_act_mask_bwd_apply finishes.  Against the unfused pair (same GEMM + cab_bn_act_mask_bwd): the
+	gradient activation is bit-identical, dbeta / dgamma / grad_y agree up to the order of the fp32 partial sums."""
+	from convasr_b200 import _lib, ops, training
+	dev = torch.device('cuda:0')
+	lib = _lib.load()
+	g = torch.Generator().manual_seed(5)
+	cases = [
+		# B, T, C_up (channels of the layer above), C (this layer), k, dil, pad, act, ragged mask, skip padding tiles
+		(3, 300, 128, 96, 7, 1, 3, (_lib.ACT_HARDTANH, 0.0, 20.0), True, True),
+		(2, 129, 64, 320, 1, 1, 0, (_lib.ACT_RELU, 0.0, 0.0), False, False),
+		(4, 257, 192, 256, 11, 2, 10, (_lib.ACT_LEAKY_RELU, 0.01, 0.0), True, False),
+		(2, 140, 64, 40, 3, 1, 1, (_lib.ACT_HARDTANH, -1.0, 1.0), True, True),  # C not a multiple of the allocation (40 -> 64)
+	]
+	for B, T, C_up, C, k, dil, pad, (code, a, b), ragged, skip_tiles in cases:
+		ld = (C + 63) // 64 * 64
+		xlen = (torch.tensor([1.0, 0.52, 0.3, 0.07])[:B] if ragged else torch.ones(B)).to(dev)
+		# the layer above: dy_up [B, T, C_up] and its dgrad weights [k, C (ld), C_up]
+		dy_up = torch.randn(B, T, C_up, generator = g).to(BF16).to(dev)
+		w = (torch.randn(C_up, C, k, generator = g) / (C * k) ** 0.5).to(dev)
+		_, w_dgr = training._pack(w, ld, C_up, want_dgrad = True)
+		y = torch.zeros(B, T, ld, dtype = BF16, device = dev)
+		y[:, :, :C] = (torch.randn(B, T, C, generator = g) * 2 + torch.randn(1, 1, C, generator = g)).to(BF16).to(dev)
+		gamma, beta = (torch.rand(C, generator = g) + 0.5).to(dev), (torch.randn(C, generator = g) + (8.0 if code == _lib.ACT_HARDTANH and b == 20.0 else 0.0)).to(dev)
+		gamma[::7] *= -1  # negative scales flip the side of the gate
+		rm, rv = torch.zeros(C, device = dev), torch.ones(C, device = dev)
+		ws, ss = torch.empty(2, C, dtype = torch.float64, device = dev), torch.empty(4, C, device = dev)
+		_lib.check(lib.cab_bn_batch_stats(ops._p(y), B, T, C, ld, ops._p(gamma), ops._p(beta), 1e-5, 0.1, ops._p(rm), ops._p(rv), ops._p(ws), ops._p(ss), ops._stream()), 'stats')
+		src = [ops.Source(dy_up, w_dgr, C_up, k, dil, dil * (k - 1) - pad, T_in = T)]
+		skip = (xlen, T, 0) if (skip_tiles and ragged) else None
+		mask = xlen if ragged else None
+		out = {}
+		for fold in (False, True):
+			gx = torch.full((B, T, ld), float('nan'), dtype = BF16, device = dev)
+			partials = torch.full((_lib.BN_SUM_REPLICAS * 2 * C, ), float('nan'), dtype = torch.float64, device = dev)
+			sums = torch.empty(2, C, device = dev)
+			dyl = torch.empty(B, T, ld, dtype = BF16, device = dev)
+			ops.conv1d_fused(src, B, T, ld, out_hi = gx, skip = skip, bn_reduce = (y, ss, C, code, a, b, mask, partials) if fold else None)
+			fn = lib.cab_bn_act_mask_bwd_apply if fold else lib.cab_bn_act_mask_bwd
+			_lib.check(fn(ops._p(y), None, ops._p(gx), None, ops._p(ss), B, T, C, ld, code, a, b, ops._p(mask), ops._p(sums), ops._p(dyl), None, 0.0, None, 0, 0, ops._p(partials), ops._stream()), 'bn bwd')
+			torch.cuda.synchronize()
+			out[fold] = (gx, sums, dyl)
+		lens = ops.frac_lengths(xlen, T)
+		valid = (torch.arange(T, device = dev)[None, :, None] < lens[:, None, None])
+		if skip is None:
+			assert torch.equal(out[False][0], out[True][0]), 'the folded launch must store the same gradient activation'
+		else:
+			assert torch.equal(out[False][0] * valid, out[True][0] * valid)
+		assert float(out[False][1].abs().max()) > 0
+		assert rel(out[True][1], out[False][1]) < 1e-4, (C, rel(out[True][1], out[False][1]))
+		assert rel(out[True][2][:, :, :C].float(), out[False][2][:, :, :C].float()) < 2e-3, (C, rel(out[True][2].float(), out[False][2].float()))  # bf16 outputs: a last-bit difference of a coefficient moves roundings
+
+
+def test_training_step_same_with_and_without_folded_bn_reduction():
+	from convasr_b200 import training
+	dev = torch.device('cuda:0')
+	sig, xlen, y, ylen = _batch(38)
+	grads = []
+	for fold in (False, True):
+		old, training._FOLD_BN_REDUCE = training._FOLD_BN_REDUCE, fold
+		try:
+			m, _ = _model(dev, dict(base_width = 32, num_blocks = 2))
+			out = m(sig.to(dev), xlen.to(dev), y = y.to(dev), ylen = ylen.to(dev))
+			out['loss'].mean().backward()
+			grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+		finally:
+			training._FOLD_BN_REDUCE = old
+	assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 10
+	worst = max(rel(grads[1][k], grads[0][k]) for k in grads[0])
+	assert worst < 2e-2, worst  # bf16 tier: an ulp in a BatchNorm-backward coefficient moves bf16 roundings of the gradient activations downstream
+
+
 def test_training_step_same_with_and_without_padding_skip():
 	from convasr_b200 import training
 	dev = torch.device('cuda:0')
