@@ -160,9 +160,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, floa
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     // fp64 sums: E[x^2] - mean^2 without cancellation noise
-    const double mean_d = stats[c] / (double)n;
+    const double inv_nd = 1.0 / (double)n;
+    const double mean_d = stats[c] * inv_nd;
     const float mean = (float)mean_d;
-    const float var = (float)fmax(stats[sums_ld + c] / (double)n - mean_d * mean_d, 0.0);
+    const float var = (float)fmax(stats[sums_ld + c] * inv_nd - mean_d * mean_d, 0.0);
     const float invstd = rsqrtf(var + eps);
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     out[c] = g * invstd;
@@ -386,6 +387,8 @@ struct StreamArgs {
     int B, T, C, ld, act;
     int vectors, rows_per_chunk, n_chunks, stages, stage_bytes;
     int reverse;
+    double inv_n_rows;         // forward with folded finalize: 1 / n_rows
+    int coef_off;              // byte offset of the [4][ld] coefficient table in dynamic shared memory
 };
 
 __device__ __forceinline__ void add8(float (&f)[8], const uint4& lo) {
@@ -439,56 +442,69 @@ bn_stream_kernel(const StreamArgs p) {
         for (int s = 0; s < p.stages; ++s)
             if (blockIdx.x + s * stride < p.n_chunks) issue(blockIdx.x + s * stride, s);
 
-    // per-channel coefficients
+    // Per-channel coefficients, computed ONCE per CTA (channel c by thread c % nthreads) into a shared-memory table and then
+    // picked up by the `lanes` threads that own the channel.  Every thread used to derive its 8 channels itself: lanes x
+    // redundant, and with the BatchNorm finalize folded in that meant 16 fp64 divisions per thread -- ~10 us of a 28 us launch
+    // at 256 channels (tools/time_train_kernels.py: the kernels stream at 6.2-6.4 TB/s on top of a 17-25 us fixed cost).
+    float* coef = reinterpret_cast<float*>(smem_raw + p.coef_off);  // [4][ld]: scale, shift, k0, k1
+    {
+        const double inv_nd = p.inv_n_rows;  // 1 / n_rows, from the host: no fp64 division on the device
+        for (int c = tid; c < ld; c += nthreads) {
+            float sc_ = 0.f, sh_ = 0.f, k0_ = 0.f, k1_ = 0.f;
+            if (c < C) {
+                if (MODE == 0 && p.raw_sums != nullptr) {
+                    // same arithmetic as bn_finalize_kernel
+                    const float n = p.n_rows;
+                    const double mean_d = p.raw_sums[c] * inv_nd;
+                    const float mean = (float)mean_d;
+                    const float var = (float)fmax(p.raw_sums[p.sums_ld + c] * inv_nd - mean_d * mean_d, 0.0);
+                    const float invstd = rsqrtf(var + p.eps);
+                    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+                    sc_ = g * invstd;
+                    sh_ = b - mean * g * invstd;
+                    if (blockIdx.x == 0) {
+                        p.ss_out[c] = sc_;
+                        p.ss_out[C + c] = sh_;
+                        p.ss_out[2 * C + c] = mean;
+                        p.ss_out[3 * C + c] = invstd;
+                        if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
+                        if (p.running_var) p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (n / fmaxf(n - 1.f, 1.f));
+                    }
+                } else {
+                    sc_ = p.ss[c];
+                    sh_ = p.ss[C + c];
+                }
+                if (MODE == 2) {
+                    const float mean = p.ss[2 * C + c], istd = p.ss[3 * C + c];
+                    double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < kBnSumReplicas; ++r) {
+                        d1 += p.partials[(size_t)r * 2 * C + c];
+                        d2 += p.partials[(size_t)r * 2 * C + C + c];
+                    }
+                    // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)), centred in fp64
+                    const float m1 = (float)d1;
+                    const float m2 = (float)((double)istd * (d2 - (double)mean * d1));
+                    if (blockIdx.x == 0) { p.sums[c] = m1; p.sums[C + c] = m2; }
+                    k1_ = -sc_ * (m2 * p.inv_n) * istd;        // coefficient of y
+                    k0_ = -sc_ * (m1 * p.inv_n) - k1_ * mean;  // constant term
+                }
+            }
+            coef[c] = sc_;
+            coef[ld + c] = sh_;
+            coef[2 * ld + c] = k0_;
+            coef[3 * ld + c] = k1_;
+        }
+    }
+    __syncthreads();
     float sc[8], sh[8], k0[8], k1[8], acc_s[8], acc_q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int c = c0 + e;
-        const bool ok = c < C;
-        if (MODE == 0 && p.raw_sums != nullptr) {
-            // same arithmetic as bn_finalize_kernel
-            sc[e] = 0.f; sh[e] = 0.f;
-            if (ok) {
-                const float n = p.n_rows;
-                const double mean_d = p.raw_sums[c] / (double)n;
-                const float mean = (float)mean_d;
-                const float var = (float)fmax(p.raw_sums[p.sums_ld + c] / (double)n - mean_d * mean_d, 0.0);
-                const float invstd = rsqrtf(var + p.eps);
-                const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-                sc[e] = g * invstd;
-                sh[e] = b - mean * g * invstd;
-                if (blockIdx.x == 0 && lane == 0) {
-                    p.ss_out[c] = sc[e];
-                    p.ss_out[C + c] = sh[e];
-                    p.ss_out[2 * C + c] = mean;
-                    p.ss_out[3 * C + c] = invstd;
-                    if (p.running_mean) p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * mean;
-                    if (p.running_var) p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * var * (n / fmaxf(n - 1.f, 1.f));
-                }
-            }
-        } else {
-            sc[e] = ok ? p.ss[c] : 0.f;
-            sh[e] = ok ? p.ss[C + c] : 0.f;
-        }
-        acc_s[e] = 0.f; acc_q[e] = 0.f; k0[e] = 0.f; k1[e] = 0.f;
-        if (MODE == 2) {
-            float m1 = 0.f, m2 = 0.f;
-            const float mean = ok ? p.ss[2 * C + c] : 0.f, istd = ok ? p.ss[3 * C + c] : 0.f;
-            if (ok) {
-                double d1 = 0.0, d2 = 0.0;
-#pragma unroll
-                for (int r = 0; r < kBnSumReplicas; ++r) {
-                    d1 += p.partials[(size_t)r * 2 * C + c];
-                    d2 += p.partials[(size_t)r * 2 * C + C + c];
-                }
-                // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)), centred in fp64
-                m1 = (float)d1;
-                m2 = (float)((double)istd * (d2 - (double)mean * d1));
-                if (blockIdx.x == 0 && lane == 0) { p.sums[c] = m1; p.sums[C + c] = m2; }
-            }
-            k1[e] = -sc[e] * (m2 * p.inv_n) * istd;          // coefficient of y
-            k0[e] = -sc[e] * (m1 * p.inv_n) - k1[e] * mean;  // constant term
-        }
+        sc[e] = coef[c0 + e];
+        sh[e] = coef[ld + c0 + e];
+        k0[e] = coef[2 * ld + c0 + e];
+        k1[e] = coef[3 * ld + c0 + e];
+        acc_s[e] = 0.f; acc_q[e] = 0.f;
     }
     const float act_a = p.a, act_b = p.bb;
     const bool dropping = p.drop_p > 0.f;
@@ -591,7 +607,16 @@ bn_stream_kernel(const StreamArgs p) {
 static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& threads, int& grid, size_t& smem) {
     if (ld % 8 != 0 || R <= 0) return false;
     const int vectors = ld / 8;
-    int lanes = 256 / vectors;  // ~256 threads: the kernels are register-heavy, more CTAs per SM beat bigger CTAs
+    static int target_threads = 0, stage_budget = 0;
+    if (target_threads == 0) {  // tuning knobs (A/B runs): CTA size and bytes of stages per CTA
+        const char* e = getenv("CONVASR_B200_BN_THREADS");
+        target_threads = e ? atoi(e) : 256;
+        if (target_threads < 32 || target_threads > kStreamMaxThreads) target_threads = 256;
+        e = getenv("CONVASR_B200_BN_STAGE_KB");
+        stage_budget = (e ? atoi(e) : 48) * 1024;
+        if (stage_budget < 16 * 1024 || stage_budget > 200 * 1024) stage_budget = 48 * 1024;
+    }
+    int lanes = target_threads / vectors;  // ~256 threads: the kernels are register-heavy, more CTAs per SM beat bigger CTAs
     if (lanes < 1) lanes = 1;
     while ((vectors * lanes) % 32 != 0) ++lanes;
     threads = vectors * lanes;
@@ -602,9 +627,12 @@ static bool stream_geometry(int R, int ld, int n_inputs, StreamArgs& a, int& thr
     a.stage_bytes = kStreamUnits * threads * 16;
     // ~48 KB of stages per CTA: 3-4 CTAs per SM (ncu: with 2 fat CTAs the SM idled on LDS / fixed-latency waits at
     // 52 % issue utilisation); bytes in flight per SM stay ~150-190 KB
-    int stages = (int)((48 * 1024) / ((size_t)n_inputs * a.stage_bytes));
+    int stages = (int)((size_t)stage_budget / ((size_t)n_inputs * a.stage_bytes));
     a.stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
     smem = (size_t)a.stages * n_inputs * a.stage_bytes + 8 * a.stages;
+    smem = (smem + 15) & ~(size_t)15;
+    a.coef_off = (int)smem;
+    smem += (size_t)4 * ld * sizeof(float);
     if (smem < (size_t)threads * 64) smem = (size_t)threads * 64;  // the reduction scratch of the reduce pass
     if (smem > 220 * 1024) return false;
     grid = 0;  // sized by stream_launch from the occupancy of the instantiation
@@ -1063,7 +1091,7 @@ extern "C" int cab_bn_act_mask_fwd_stats(const void* y, const void* y_lo, const 
     sa.y_lo = static_cast<const __nv_bfloat16*>(y_lo); sa.out_lo = static_cast<__nv_bfloat16*>(out_lo);
     sa.seed_ptr = reinterpret_cast<const long long*>(seed); sa.salt = (unsigned long long)salt;
     sa.raw_sums = raw_sums; sa.sums_ld = sums_ld; sa.gamma = gamma; sa.beta = beta; sa.running_mean = running_mean; sa.running_var = running_var;
-    sa.ss_out = out_ss; sa.n_rows = (float)n_rows; sa.eps = eps; sa.momentum = momentum;
+    sa.ss_out = out_ss; sa.n_rows = (float)n_rows; sa.inv_n_rows = 1.0 / (double)(float)n_rows; sa.eps = eps; sa.momentum = momentum;
     sa.a = act_a; sa.bb = act_b; sa.drop_p = dropout_p; sa.B = B; sa.T = T; sa.C = C; sa.ld = ld; sa.act = act;
     sa.reverse = bn_l2_order();
     if (split) CAB_CHECK_CUDA((stream_launch<0, true>(sa, threads, grid_s, smem, stream)));
