@@ -12,6 +12,7 @@
 #include "../../include/convasr_b200.h"
 #include <atomic>
 #include <float.h>
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 namespace cab {
@@ -334,12 +335,26 @@ __global__ void ctc_grad_scatter_kernel(const float* __restrict__ lp, int64_t st
 // ------------------------------------------------------------------------------------------
 // ctc.alignment (ctc.py:6-75)
 // ------------------------------------------------------------------------------------------
+// HALF: the log-probs came from an fp16 tensor (exactly representable fp32 values here) and the reference ran its whole
+// recursion in fp16 (ctc.py:29: "zero" = finfo(float16).min): torch.logsumexp on fp16 is the composite amax / sub / exp / sum /
+// log / add with an fp16 result after EVERY operation (the 3-term sum accumulates in fp32 and rounds once), then the fp16
+// add of the emission.  rh() reproduces those roundings; values stay fp16-representable in the fp32 buffers.
+__device__ __forceinline__ float rh(float x) { return __half2float(__float2half_rn(x)); }
+// exp / log of an fp16 value are functions on 65536 inputs: with tables (fp16 bit pattern -> fp16 bit pattern, e.g. taken from the
+// host's torch) the recursion reproduces that implementation's fp16 results bit for bit; without, expf / logf rounded to fp16
+// (two math libraries disagree on the fp16 rounding of ~1e-4 of the inputs, enough to flip an argmax tie in a long utterance).
+__device__ __forceinline__ float half_fn(const uint16_t* __restrict__ table, float x_half_valued, float computed) {
+    if (table == nullptr) return rh(computed);
+    return __half2float(__ushort_as_half(__ldg(table + __half_as_ushort(__float2half_rn(x_half_valued)))));
+}
+template <bool HALF>
 __global__ void ctc_align_kernel(const float* __restrict__ lp, int64_t st, int64_t sb, int64_t sc,
                                  const int64_t* __restrict__ targets, const int64_t* __restrict__ in_len,
                                  const int64_t* __restrict__ tgt_len, int T, int L_max, int blank,
-                                 uint8_t* __restrict__ bp_ws, int64_t* __restrict__ out) {
+                                 uint8_t* __restrict__ bp_ws, int64_t* __restrict__ out,
+                                 const uint16_t* __restrict__ tab_exp, const uint16_t* __restrict__ tab_log) {
     extern __shared__ float sh[];
-    const float ZERO = -FLT_MAX;  // torch.finfo(float32).min, ctc.py:29
+    const float ZERO = HALF ? -65504.f : -FLT_MAX;  // torch.finfo(dtype).min, ctc.py:29
     const int b = blockIdx.x;
     const int S_max = 2 * L_max + 1;
     int tl = (int)tgt_len[b];
@@ -391,8 +406,17 @@ __global__ void ctc_align_kernel(const float* __restrict__ lp, int64_t st, int64
                 if (p1 > p0) arg = 1;
                 if (p2 > fmaxf(p0, p1)) arg = 2;
                 const float ms = (fabsf(m) == INFINITY) ? 0.f : m;
-                const float lse = logf(expf(p0 - ms) + expf(p1 - ms) + expf(p2 - ms)) + ms;
-                cur[s + 2] = lpb[(int64_t)t * st + (int64_t)ext[i] * sc] + lse;
+                const float e_t = lpb[(int64_t)t * st + (int64_t)ext[i] * sc];
+                if (HALF) {
+                    const float d0 = rh(p0 - ms), d1 = rh(p1 - ms), d2 = rh(p2 - ms);
+                    const float e0 = half_fn(tab_exp, d0, expf(d0)), e1 = half_fn(tab_exp, d1, expf(d1)), e2 = half_fn(tab_exp, d2, expf(d2));
+                    const float ssum = rh((e0 + e1) + e2);
+                    const float lse = rh(half_fn(tab_log, ssum, logf(ssum)) + ms);
+                    cur[s + 2] = rh(e_t + lse);
+                } else {
+                    const float lse = logf(expf(p0 - ms) + expf(p1 - ms) + expf(p2 - ms)) + ms;
+                    cur[s + 2] = e_t + lse;
+                }
                 bp[(size_t)t * S_max + s] = (uint8_t)arg;
             }
         }
@@ -811,13 +835,18 @@ extern "C" int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_
 extern "C" int cab_ctc_alignment(const float* log_probs, int64_t stride_t, int64_t stride_b, int64_t stride_c,
                                  const int64_t* targets, const int64_t* input_lengths,
                                  const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                                 uint8_t* ws_backptr, int64_t* out_alignment, cab_stream_t stream_) {
+                                 uint8_t* ws_backptr, int64_t* out_alignment, int fp16_arithmetic, const uint16_t* fp16_exp_table,
+                                 const uint16_t* fp16_log_table, cab_stream_t stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     CTC_COMMON_CHECKS();
     CAB_CHECK_ARG(ws_backptr && out_alignment, "null workspace/output");
-    ctc_align_kernel<<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets,
-                                                   input_lengths, target_lengths, T, L_max, blank, ws_backptr,
-                                                   out_alignment);
+    CAB_CHECK_ARG((fp16_exp_table == nullptr) == (fp16_log_table == nullptr), "give both fp16 tables or neither");
+    if (fp16_arithmetic)
+        ctc_align_kernel<true><<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets, input_lengths, target_lengths, T, L_max, blank,
+                                                             ws_backptr, out_alignment, fp16_exp_table, fp16_log_table);
+    else
+        ctc_align_kernel<false><<<B, threads, smem, stream>>>(log_probs, stride_t, stride_b, stride_c, targets, input_lengths, target_lengths, T, L_max, blank,
+                                                              ws_backptr, out_alignment, nullptr, nullptr);
     CAB_CHECK_LAUNCH();
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return 0;

@@ -3,7 +3,8 @@ GPU with one CTA per utterance (convasr_b200/csrc/ctc.cu: ctc_align_kernel).
 
 All of the reference's behaviours are reproduced, including the batch-coupled ones (recursion
 over all T frames of the padded batch, terminal state read after the last global frame,
-back-trace from input_length-1, finite "zero", stay-preferred argmax ties) -- SURVEY.md A12.
+back-trace from input_length-1, finite "zero", stay-preferred argmax ties) -- SURVEY.md A12 -- and
+its fp16 mode: on fp16 log_probs every operation of the recursion rounds to fp16 ("zero" = finfo(float16).min).
 `pack_backpointers` only changes the reference's memory format, never its result; the native
 kernel keeps one byte per back-pointer in a caller-owned workspace and ignores the flag.
 """
@@ -18,8 +19,8 @@ def alignment(
 ):
 	"""log_probs [T, B, C] (any strides), targets [B, L] -> int64 [B, L]: for every target label the
 	last frame index at which the best path sits in it (zeros past target_length)."""
-	if log_probs.dtype == torch.float16:
-		raise NotImplementedError('convasr_b200.ctc.alignment: fp16 log_probs are not supported (the model emits fp32 log_probs, models.py:316)')
+	if log_probs.dtype not in (torch.float32, torch.float16):
+		raise NotImplementedError(f'convasr_b200.ctc.alignment: {log_probs.dtype} log_probs (the reference handles float32 and float16, ctc.py:29)')
 	return ops.ctc_alignment(log_probs, targets, input_lengths, target_lengths, blank = blank)
 
 

@@ -426,7 +426,24 @@ def ctc_loss(log_probs, targets, input_lengths, target_lengths, blank = 0):
 	return _CtcLoss.apply(log_probs, targets, input_lengths, target_lengths, int(blank))
 
 
+_FP16_TABLES = {}
+
+
+def _fp16_tables(device):
+	"""exp and log of every fp16 value as computed by this host's torch, as uint16 bit patterns on the device: with them the
+	fp16 alignment recursion equals the reference's fp16 arithmetic on this machine bit for bit (ctc.cu: half_fn)"""
+	key = str(device)
+	if key not in _FP16_TABLES:
+		x = torch.arange(65536, dtype = torch.int32).to(torch.int16).view(torch.float16)
+		bits = lambda t: t.view(torch.int16).to(torch.int32).bitwise_and(0xFFFF).to(torch.uint16)
+		_FP16_TABLES[key] = (bits(x.exp()).to(device), bits(x.log()).to(device))
+	return _FP16_TABLES[key]
+
+
 def ctc_alignment(log_probs, targets, input_lengths, target_lengths, blank = 0):
+	"""fp16 log_probs: the recursion rounds to fp16 after every operation, as the reference does on an fp16 tensor (the
+	values are handed to the kernel as their exact fp32 images)"""
+	half = log_probs.dtype == torch.float16
 	lp = log_probs if log_probs.dtype == torch.float32 else log_probs.float()
 	T, B, C, L, targets, input_lengths, target_lengths = _ctc_args(lp, targets, input_lengths, target_lengths)
 	S = 2 * L + 1
@@ -435,9 +452,10 @@ def ctc_alignment(log_probs, targets, input_lengths, target_lengths, blank = 0):
 	if B == 0 or L == 0:
 		return out.zero_()
 	st, sb, sc = _tbc_strides(lp)
+	tabs = _fp16_tables(lp.device) if half else None
 	rc = _lib.load().cab_ctc_alignment(
 		_p(lp), st, sb, sc, _p(targets), _p(input_lengths), _p(target_lengths), B, T, C, L, blank, _p(bp), _p(out),
-		_stream()
+		int(half), _p(tabs[0]) if half else None, _p(tabs[1]) if half else None, _stream()
 	)
 	_lib.check(rc, 'cab_ctc_alignment')
 	return out

@@ -375,11 +375,17 @@ int cab_ctc_loss_bwd(const float* log_probs, int64_t stride_t, int64_t stride_b,
  *   recursion runs over all T frames of the padded batch, terminal state read at global T-1,
  *   back-trace from input_length-1, output = last frame index per target label.
  *   ws_backptr: uint8 [B, T, 2*L_max+1] workspace.  out: int64 [B, L_max].
+ *   fp16_arithmetic != 0: log_probs are the fp32 images of an fp16 tensor and the recursion rounds to
+ *   fp16 after every operation, "zero" = finfo(float16).min -- what the reference computes when it is
+ *   handed fp16 log_probs (ctc.py:29).  fp16_exp_table / fp16_log_table (both or neither; device, uint16
+ *   [65536]): exp and log as maps from fp16 bit pattern to fp16 bit pattern, e.g. tabulated with the host's torch --
+ *   the recursion then equals that implementation's fp16 arithmetic bit for bit; NULL: expf / logf rounded to fp16.
  * ------------------------------------------------------------------------------------- */
 int cab_ctc_alignment(const float* log_probs, int64_t stride_t, int64_t stride_b,
                       int64_t stride_c, const int64_t* targets, const int64_t* input_lengths,
                       const int64_t* target_lengths, int B, int T, int C, int L_max, int blank,
-                      uint8_t* ws_backptr, int64_t* out_alignment, cab_stream_t stream);
+                      uint8_t* ws_backptr, int64_t* out_alignment, int fp16_arithmetic,
+                      const uint16_t* fp16_exp_table, const uint16_t* fp16_log_table, cab_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * A13: GreedyDecoder.decode (decoders.py:5-16): per-frame top-K class ids of [B, C, T],

@@ -355,6 +355,9 @@ def ctc_alignment(log_probs, targets, input_lengths, target_lengths, blank = 0):
 	(ctc.py:48-50), the terminal state is read after the last global frame (ctc.py:56-61) and the
 	back-trace starts at input_length-1 (ctc.py:61).  Output: last frame index per label
 	(ctc.py:72-75).  log_probs [T, B, C] torch fp32; returns int64 [B, L]."""
+	half = log_probs.dtype == torch.float16
+	if half:
+		return _ctc_alignment_fp16(log_probs, targets, input_lengths, target_lengths, blank)
 	lp = log_probs.detach().to(torch.float32).numpy()
 	T, B, C = lp.shape
 	L = targets.shape[1]
@@ -387,6 +390,53 @@ def ctc_alignment(log_probs, targets, input_lengths, target_lengths, blank = 0):
 			path[t - 1] += idx - int(bp[t, idx])
 		full = np.zeros(S, dtype = np.int64)
 		for t in range(T):  # scatter_: the last write wins
+			full[max(path[t] - 2, 0)] = t
+		out[b] = full[1::2]
+	return torch.from_numpy(out)
+
+
+def _ctc_alignment_fp16(log_probs, targets, input_lengths, target_lengths, blank):
+	"""ctc.alignment on fp16 log_probs (ctc.py:29 picks finfo(float16).min as "zero"): every tensor of the reference's
+	recursion is fp16, so every operation rounds to fp16 -- torch.logsumexp is the composite amax / sub / exp / sum / log /
+	add, each with an fp16 result (the 3-term sum accumulates in fp32 and rounds once); checked against the reference on
+	CPU (tests/test_oracle_golden.py).  Same structure as the fp32 restatement above."""
+	f16, f32 = np.float16, np.float32
+	lp = log_probs.detach().numpy().astype(f16)
+	T, B, C = lp.shape
+	L = targets.shape[1]
+	zero = f16(np.finfo(f16).min)
+	out = np.zeros((B, L), dtype = np.int64)
+	for b in range(B):
+		tl, il = int(target_lengths[b]), int(input_lengths[b])
+		ext = np.full(2 * L + 1, blank, dtype = np.int64)
+		ext[1::2] = targets[b].numpy()
+		S = 2 * L + 1
+		diff = np.zeros(S, dtype = bool)
+		diff[2:] = ext[2:] != ext[:-2]
+		alpha = np.full(S + 2, zero, dtype = f16)
+		alpha[2] = lp[0, b, blank]
+		if S > 1:
+			alpha[3] = lp[0, b, ext[1]]
+		bp = np.zeros((T, S + 2), dtype = np.uint8)
+		for t in range(1, T):
+			prev = np.stack([alpha[2:], alpha[1:-1], np.where(diff, alpha[:-2], zero)])
+			m = prev.max(axis = 0)
+			ms = np.where(np.isinf(m), f16(0), m)
+			np.seterr(over = 'ignore')  # zero + log-prob may leave the fp16 range: -inf, as in the reference
+			d = (prev.astype(f32) - ms.astype(f32)).astype(f16)
+			e = np.exp(d.astype(f32)).astype(f16)
+			ssum = ((e[0].astype(f32) + e[1].astype(f32)) + e[2].astype(f32)).astype(f16)
+			lse = (np.log(ssum.astype(f32)).astype(f16).astype(f32) + ms.astype(f32)).astype(f16)
+			bp[t, 2:] = prev.argmax(axis = 0)
+			alpha = np.concatenate([alpha[:2], (lp[t, b, ext].astype(f32) + lse.astype(f32)).astype(f16)])
+		l1l2 = alpha[[2 + 2 * tl - 1, 2 + 2 * tl]]
+		path = np.zeros(T, dtype = np.int64)
+		path[il - 1] = 2 + 2 * tl - 1 + int(l1l2.argmax())
+		for t in range(T - 1, 0, -1):
+			idx = path[t]
+			path[t - 1] += idx - int(bp[t, idx])
+		full = np.zeros(S, dtype = np.int64)
+		for t in range(T):
 			full[max(path[t] - 2, 0)] = t
 		out[b] = full[1::2]
 	return torch.from_numpy(out)

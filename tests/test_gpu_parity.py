@@ -178,6 +178,23 @@ def test_ctc_loss_bench_shape_against_float64_oracle(dev):
 	assert torch.equal(loss2, loss.detach())
 
 
+def test_fp16_alignment_against_reference_golden(golden, dev):
+	"""fp16 log_probs (ctc.py:29): the native kernel rounds to fp16 after every operation of the recursion, like the reference
+	on an fp16 tensor; bit-exact against the reference's own fp16 outputs (tests/golden/ctc_fp16.pt) and the oracle"""
+	from convasr_b200 import ctc
+	for c in golden('ctc_fp16')['cases']:
+		al = ctc.alignment(c['log_probs'].to(dev), c['targets'].to(dev), c['input_lengths'].to(dev), c['target_lengths'].to(dev), blank = c['blank'])
+		assert al.dtype == torch.int64 and torch.equal(al.cpu(), c['alignment']), int((al.cpu() != c['alignment']).sum())
+	g = torch.Generator().manual_seed(4)
+	B, C, T, L = 5, 38, 400, 80
+	lp = (torch.randn(B, C, T, generator = g) * 3).log_softmax(1).half()
+	y = torch.randint(0, C - 1, (B, L), generator = g)
+	ylen, olen = torch.tensor([80, 41, 17, 0, 33]), torch.tensor([400, 350, 399, 400, 170])
+	ref = O.ctc_alignment(lp.permute(2, 0, 1), y, olen, ylen, C - 1)
+	got = ctc.alignment(lp.to(dev).permute(2, 0, 1), y.to(dev), olen.to(dev), ylen.to(dev), blank = C - 1)
+	assert torch.equal(got.cpu(), ref), int((got.cpu() != ref).sum())
+
+
 def test_alignment_against_golden_and_oracle(golden, dev):
 	from convasr_b200 import ctc
 	for c in golden('ctc')['cases']:

@@ -70,6 +70,18 @@ def test_alignment_matches_reference(golden):
 		assert torch.equal(al, c['alignment'])
 
 
+def test_fp16_alignment_matches_reference(golden):
+	"""ctc.alignment on fp16 log_probs (ctc.py:29): the reference's recursion runs in fp16; the restatement rounds after every
+	operation and must hit the same frames -- which differ from the fp32 answer on these inputs"""
+	differing = 0
+	for c in golden('ctc_fp16')['cases']:
+		assert c['log_probs'].dtype == torch.float16
+		al = O.ctc_alignment(c['log_probs'], c['targets'], c['input_lengths'], c['target_lengths'], c['blank'])
+		assert torch.equal(al, c['alignment'])
+		differing += int((O.ctc_alignment(c['log_probs'].float(), c['targets'], c['input_lengths'], c['target_lengths'], c['blank']) != c['alignment']).sum())
+	assert differing > 0
+
+
 def test_greedy_decode_and_generate(golden):
 	g = golden('decode')
 	tok = O.CharTokenizer(g['alphabet'])
