@@ -52,8 +52,12 @@ def unsupported_reason(model):
 		return 'two-head (bpe) decoder'
 	n_blocks = len(model.backbone)
 	for i, block in enumerate(model.backbone):
-		if block.activation.invertible:
-			return 'invertible (in-place) activation'
+		if block.activation.invertible and block.activation.nonlinearity[0] != 'leaky_relu':
+			# the reference's invertible activation exists for leaky_relu only (models.py:383).  The *Inplace families themselves
+			# train here: InplaceBatchNorm1d (models.py:411-433) is BatchNorm1d's arithmetic with the input re-derived from the
+			# output in the backward, the invertible leaky_relu (models.py:376-408) is leaky_relu -- a memory optimisation of the
+			# reference's implementation, not a different function; this path keeps both activations (180 GB of HBM).
+			return 'invertible activation other than leaky_relu'
 		if block.activation.nonlinearity[0] not in ('relu', 'hardtanh', 'leaky_relu'):
 			return f'nonlinearity {block.activation.nonlinearity!r}'
 		if len(block.conv_residual) + 1 > _lib.MAX_BN_BRANCHES:

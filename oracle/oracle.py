@@ -154,6 +154,8 @@ MODEL_CONFIGS = {
 	'JasperNetSeparable': dict(act = ('relu', ), residual = 'dense', dilation = 1, mask = True, groups = 128),
 	'JasperNetSmall': dict(act = ('relu', ), residual = 'dense', dilation = 1, mask = False),
 	'JasperNetBig': dict(act = ('relu', ), residual = 'dense', dilation = 1, mask = False),
+	# the *Inplace families compute BatchNorm1d + leaky_relu (models.py:376-433 only change how the backward gets its inputs)
+	'Wav2LetterDenseNoDilationInplace': dict(act = ('leaky_relu', 0.01), residual = 'dense', dilation = 1, mask = True),
 }
 
 

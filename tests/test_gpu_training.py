@@ -557,6 +557,32 @@ def test_training_step_matches_reference_train_mode_golden(golden, capsys):
 	assert not failures, failures
 
 
+def test_inplace_family_trains_natively_like_the_reference_twin(golden, capsys):
+	"""Wav2LetterDenseNoDilationInplace (section 8f rank 4) on the native training step: InplaceBatchNorm1d / the invertible
+	leaky_relu (models.py:376-433) compute BatchNorm1d / leaky_relu, so the golden is the reference's non-in-place twin
+	(tests/golden/train_inplace.pt; the in-place forward itself needs CUDA-only ATen operators).  Same bars as the other
+	kinked families."""
+	from test_oracle_golden import check_grads_against_golden
+	from convasr_b200 import training
+	dev = torch.device('cuda:0')
+	lines = []
+	for c in golden('train_inplace')['cases']:
+		for precision in ('fp32', 'bf16'):
+			out, grads, stats = _native_train_step(dev, c, precision)
+			assert torch.equal(out['olen'][0].cpu(), c['olen'])
+			e_logits = rel(out['logits'][0], c['logits'])
+			e_loss = float(((out['loss'].cpu() - c['loss']).abs() / c['loss'].abs()).max())
+			total, worst = check_grads_against_golden(grads, c['grads'], 1e9, (c['model'], precision))
+			e_stats = max(float((stats[k] - v).abs().max() / (v.abs().max() + 1e-6)) for k, v in c['stats'].items() if not k.endswith('num_batches_tracked'))
+			lines.append(f'{c["model"]} {precision}: logits {e_logits:.2e} loss {e_loss:.2e} grads total {total:.2e} worst tensor {worst:.2e} running stats {e_stats:.2e}')
+			if precision == 'fp32':
+				assert e_logits < 1e-3 and e_loss < 1e-3 and worst < 1e-1 and e_stats < 2e-3, lines[-1]
+			else:
+				assert e_logits < 0.2 and e_loss < 5e-2 and worst < 1.0 and e_stats < 5e-2, lines[-1]
+	with capsys.disabled():
+		print('\nnative training step, *Inplace family vs the reference twin:\n  ' + '\n  '.join(lines))
+
+
 def test_multi_branch_bn_kernels_against_autograd():
 	"""cab_bn_multi_act_mask_fwd / cab_act_mask_bwd_dz + per-branch BatchNorm backward == torch autograd of
 	act(BN0(y0) + BN1(y1) + y2) * mask (two BatchNorm branches and an identity branch), both tiers"""

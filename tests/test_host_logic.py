@@ -213,12 +213,17 @@ def test_bench_reference_arm_prints_the_contract_line():
 
 
 def test_native_training_coverage_by_model_class():
-	"""training.unsupported_reason(): every family of the model zoo trains on the native kernels except the in-place /
-	invertible variants (section 8f rank 4) and the instance-norm-with-running-stats class the reference itself cannot run;
-	there is no ATen path to fall back to -- the model raises instead."""
+	"""training.unsupported_reason(): every family of the model zoo trains on the native kernels, the *Inplace ones included
+	(section 8f rank 4: InplaceBatchNorm1d / the invertible leaky_relu compute BatchNorm1d / leaky_relu; only an invertible
+	activation other than leaky_relu, which the reference asserts against, is refused); there is no ATen path to fall back
+	to -- a module tree that is not covered raises instead."""
 	from convasr_b200 import models, training
 	reasons = {name: training.unsupported_reason(getattr(models, name)(64, [38], **(dict(base_width = 128) if 'Separable' in name else dict(base_width = 16)))) for name in ALL_MODELS}
 	refused = {n for n, r in reasons.items() if r is not None}
-	assert refused == {'Wav2LetterDenseNoDilationInplace', 'JasperNetBigInplace'}, reasons
+	assert refused == set(), reasons
+	m = models.Wav2LetterDenseNoDilationInplace(64, [38], base_width = 16)
+	assert all(b.activation.invertible for b in m.backbone)
+	m.backbone[1].activation.nonlinearity = ('relu', )
+	assert 'invertible' in training.unsupported_reason(m)
 	assert training.unsupported_reason(models.Wav2Letter(64, [38, 120], base_width = 16, decoder_type = 'bpe')) is not None
 	assert not hasattr(models.JasperNet, '_forward_training')

@@ -196,6 +196,21 @@ def test_train_mode_oracle_matches_reference_golden(golden):
 				assert torch.allclose(got, v, rtol = 1e-4, atol = 1e-5), k
 
 
+def test_inplace_family_oracle_matches_the_reference_twin(golden):
+	"""*Inplace model families (section 8f rank 4): the golden comes from the reference's non-in-place twin (the in-place forward
+	needs CUDA-only ATen operators, oracle/make_golden.py: golden_train_inplace); the restatement, told only the class name,
+	must reproduce it"""
+	for c in golden('train_inplace')['cases']:
+		logits, loss, grads, stats = oracle_train_step(c)
+		assert rel(logits, c['logits']) < 1e-4, (c['model'], rel(logits, c['logits']))
+		assert torch.allclose(loss, c['loss'], rtol = 1e-4, atol = 1e-4), c['model']
+		total, worst = check_grads_against_golden(grads, c['grads'], 5e-2, c['model'])  # leaky_relu has a kink at 0: see the test above
+		print(c['model'], 'oracle vs reference twin: total grad rel', total, 'worst tensor', worst)
+		for k, v in c['stats'].items():
+			if not k.endswith('num_batches_tracked'):
+				assert torch.allclose(stats[k], v, rtol = 1e-4, atol = 1e-5), k
+
+
 def test_misc_golden_novograd_uncertainty_bpe(golden):
 	g = golden('misc')
 	for c in g['novograd']:
