@@ -546,7 +546,7 @@ def measure(name, args, rank, world, local_rank, dev, steps, warmup, level):
 			bound = 'tensor', kernel = kernel_label, achieved = achieved, peak = tf_peak, unit = 'TFLOP/s', frac = achieved / tf_peak,
 			peak_source = 'MEASURED_PEAKS.json bf16_tflops_sustained (of measured)' if peaks else 'fallback 1.59 PFLOP/s (of fallback)',
 			peak_burst = peaks['bf16_tflops'] if peaks else None, frac_of_burst = (achieved / peaks['bf16_tflops']) if peaks else None, traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(name),
-			traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv); the kernels are L2-fed, not HBM-fed' if name in NCU_DRAM_BYTES_PER_LAUNCH else None,
+			traffic_source = 'ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of one step (profiles/r01_*_ncu_full.csv; round-2b capture of four dgrad launches with the folded BatchNorm-backward reduction: profiles/r02b_dgrad_fold_ncu.md -- the fold adds one read of y per dgrad launch, ~21 MB per launch averaged over the step); the kernels are L2-fed, not HBM-fed' if name in NCU_DRAM_BYTES_PER_LAUNCH else None,
 			launches_per_step = n_kern, kernel_ms_per_step = kern_ms, algorithmic_gflop_per_step = flops / 1e9, mma_passes_per_flop = 3 if precision == 'fp32' else 1
 		)
 	if config['cuda_graphs'] and kind != 'train':
