@@ -1177,6 +1177,13 @@ extern "C" int cab_bn_act_mask_bwd_apply(const void* y, const void* y_lo, const 
                        frozen, const_cast<double*>(partials), true, stream_);
 }
 
+extern "C" int cab_bn_bwd_apply_covers(int R, int ld, int split) {
+    StreamArgs sa{};
+    int threads = 0, grid_s = 0;
+    size_t smem = 0;
+    return stream_geometry(R, ld, split ? 4 : 2, sa, threads, grid_s, smem) ? 1 : 0;
+}
+
 extern "C" int cab_bn_multi_act_mask_fwd(const cab_bn_branch_t* branches, int n_branches, int B, int T, int C, int ld, int act,
                                          float act_a, float act_b, const float* xlen_frac, void* out, void* out_lo,
                                          float dropout_p, const int64_t* seed, int64_t salt, cab_stream_t stream_) {

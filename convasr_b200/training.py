@@ -494,7 +494,7 @@ class NativeStack(torch.autograd.Function):
 			code, a, b = rep.act
 			y, ss = rec['y'], rec['ss']
 			bn_reduce = None
-			if _FOLD_BN_REDUCE and not split and rec['branches'] is None and rep.dropout == 0 and cv.co_alloc % 8 == 0 and (cv.co_alloc // 8) <= 512:
+			if _FOLD_BN_REDUCE and not split and rec['branches'] is None and rep.dropout == 0 and lib.cab_bn_bwd_apply_covers(B * T_out, cv.co_alloc, 0) == 1:
 				bn_reduce = (y.hi, ss, cv.C_out, code, a, b, xlen if rep.mask else None, partials)
 			gx, folded = materialize(rep.out_id, T_out, cv.co_alloc, bn_reduce)
 			mask_ptr = ops._p(xlen if rep.mask else None)

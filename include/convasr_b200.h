@@ -228,6 +228,10 @@ int cab_bn_act_mask_bwd_apply(const void* y, const void* y_lo, const void* grad_
                               const float* xlen_frac, float* sums, void* grad_y, void* grad_y_lo, float dropout_p,
                               const int64_t* seed, int64_t salt, int frozen, const double* partials,
                               cab_stream_t stream);
+/* Host-only query (no device work): 1 when cab_bn_act_mask_bwd_apply covers an activation of R = B*T rows with row pitch ld in
+ * the given tier (split != 0: split-bf16), else 0 -- the caller then keeps the separate reduce pass (cab_bn_act_mask_bwd) instead of
+ * folding the reduction into the dgrad launch. */
+int cab_bn_bwd_apply_covers(int R, int ld, int split);
 /* cab_bn_finalize + cab_bn_act_mask_fwd in one launch: every CTA derives the coefficients of its channels from
  * the raw sums of the conv epilogue (raw_sums: fp32 [2][sums_ld]); CTA 0 also writes out_ss and moves the
  * running statistics. */

@@ -73,3 +73,15 @@ def test_ctypes_table_matches_header_prototypes():
 	assert _lib.ConvEpilogue.bnr_y.offset == _lib.ConvEpilogue.skip_frac.offset + 16
 	assert _lib.ConvEpilogue.bnr_C.offset == _lib.ConvEpilogue.bnr_y.offset + 32
 	assert ctypes.sizeof(_lib.ConvEpilogue) == _lib.ConvEpilogue.bnr_y.offset + 48
+
+
+def test_bn_backward_apply_coverage_query_is_host_only():
+	"""cab_bn_bwd_apply_covers decides (on the host, no device) whether the BatchNorm-backward reduction may be folded into the
+	dgrad launch: every row pitch of the model zoo is covered; a pitch the streamed kernel cannot tile keeps the separate pass"""
+	from convasr_b200 import _lib
+	lib = _lib.load()
+	for ld in (64, 256, 384, 512, 640, 768, 896, 1024, 2048):
+		assert lib.cab_bn_bwd_apply_covers(80 * 751, ld, 0) == 1, ld
+	assert lib.cab_bn_bwd_apply_covers(80 * 751, 1088, 0) == 0  # 136 channel vectors: no CTA size <= 512 threads is a multiple of 32
+	assert lib.cab_bn_bwd_apply_covers(80 * 751, 100, 0) == 0  # not a multiple of 8 channels
+	assert 'cab_bn_bwd_apply_covers' in _lib.HOST_ONLY and 'cab_bn_bwd_apply_covers' not in _lib.trace().names
