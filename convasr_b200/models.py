@@ -676,6 +676,41 @@ def rle1d(tensor):
 	return starts[:-1], starts[1:] - starts[:-1], tensor[starts[:-1]]
 
 
+def silence_space_mask(log_probs, speech, blank_idx, space_idx, kernel_size = 101):
+	"""models.py:768-775 (host-side helper, no caller in the reference): frames that are not speech and whose best class is the
+	blank, broadcast over every class except the space -> bool [B, C, T]"""
+	best = log_probs.argmax(dim = 1)
+	quiet = (~speech) & (best == blank_idx)
+	not_space = torch.ones(log_probs.shape[1], dtype = quiet.dtype, device = quiet.device)
+	not_space[space_idx] = False
+	return quiet.unsqueeze(1) * not_space.view(1, -1, 1)
+
+
+def sparse_topk(x, k, dim = -1, largest = True, indices_dtype = None, values_dtype = None, fill_value = 0.0):
+	"""models.py:789-801: the k largest (or smallest) entries along `dim` plus what is needed to put them back"""
+	top = x.topk(k, dim = dim, largest = largest)
+	return dict(k = k, dim = dim, largest = largest, shape = x.shape, dtype = x.dtype, device = x.device, fill_value = fill_value,
+				indices = top.indices.to(dtype = indices_dtype), values = top.values.to(dtype = values_dtype))
+
+
+def sparse_topk_todense(saved, device = None):
+	"""models.py:804-810: inverse of sparse_topk (everything else = fill_value)"""
+	device = device or saved['device']
+	dense = torch.full(saved['shape'], saved['fill_value'], dtype = saved['dtype'], device = device)
+	return dense.scatter_(saved['dim'], saved['indices'].to(dtype = torch.int64, device = device), saved['values'].to(dtype = saved['dtype'], device = device))
+
+
+def apply_dither(x, dither: float):
+	"""models.py:622-642; both call sites in the frontend are commented out in the reference (models.py:571,574)"""
+	return x + dither * torch.randn_like(x) if dither > 0.0 else x
+
+
+class InplaceBatchNorm1d(nn.BatchNorm1d):
+	"""models.py:402-433 by name.  In the reference this is BatchNorm1d's arithmetic with the input re-derived from the output in the
+	backward (memory saving, CUDA-only ATen operators); here the *Inplace model families hold plain BatchNorm1d modules (same
+	parameters, buffers and state_dict keys) and train on the native step (training.py), so this class is only the exported name."""
+
+
 class InputOutputTypeCast(nn.Module):
 	"""models.py:13-20"""
 

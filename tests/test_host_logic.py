@@ -227,3 +227,33 @@ def test_native_training_coverage_by_model_class():
 	assert 'invertible' in training.unsupported_reason(m)
 	assert training.unsupported_reason(models.Wav2Letter(64, [38, 120], base_width = 16, decoder_type = 'bpe')) is not None
 	assert not hasattr(models.JasperNet, '_forward_training')
+
+
+def test_small_host_helpers_match_the_live_reference():
+	"""silence_space_mask / sparse_topk / sparse_topk_todense (models.py:768-810): host-side helpers of the module surface"""
+	import pytest
+	import torch
+	from convasr_b200 import models
+	g = torch.Generator().manual_seed(3)
+	lp = torch.randn(2, 7, 40, generator = g).log_softmax(1)
+	speech = torch.rand(2, 40, generator = g) > 0.5
+	mask = models.silence_space_mask(lp, speech, blank_idx = 6, space_idx = 5)
+	assert mask.shape == (2, 7, 40) and not bool(mask[:, 5].any())
+	quiet = (~speech) & (lp.argmax(1) == 6)
+	assert torch.equal(mask[:, 0].bool(), quiet)
+	x = torch.randn(3, 9, 11, generator = g)
+	saved = models.sparse_topk(x, 2, dim = 1, indices_dtype = torch.int16, values_dtype = torch.float16, fill_value = -1.0)
+	dense = models.sparse_topk_todense(saved)
+	assert dense.shape == x.shape and int((dense != -1.0).sum()) == 3 * 2 * 11
+	assert torch.allclose(dense.max(1).values, x.max(1).values, atol = 2e-3)
+	assert issubclass(models.InplaceBatchNorm1d, torch.nn.BatchNorm1d) and models.apply_dither(x, 0.0) is x
+	from oracle import reference_shim
+	if not reference_shim.available():
+		pytest.skip('reference tree not present')
+	ref = reference_shim.load().models
+	assert torch.equal(mask.bool(), ref.silence_space_mask(lp, speech, 6, 5).bool())
+	r_saved = ref.sparse_topk(x, 2, dim = 1, indices_dtype = torch.int16, values_dtype = torch.float16, fill_value = -1.0)
+	assert torch.equal(saved['indices'], r_saved['indices']) and torch.equal(saved['values'], r_saved['values'])
+	assert torch.equal(dense, ref.sparse_topk_todense(r_saved))
+	missing = {n for n in dir(ref) if not n.startswith('_') and callable(getattr(ref, n)) and getattr(getattr(ref, n), '__module__', None) == ref.__name__ and not hasattr(models, n)}
+	assert missing <= {'OnnxWrapper', 'Wav2VecFrontend'}, missing  # ONNX runtime / fairseq backends: out of scope (SURVEY 2.1)
