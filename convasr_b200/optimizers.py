@@ -226,3 +226,19 @@ class PolynomialDecayLR(LRScheduler):
 			s = min(step - self.begin_decay_at, self.decay_steps)
 			lrs = [self.end_lr + (lr - self.end_lr) * ((self.decay_steps - s) / self.decay_steps)**self.power if s < self.decay_steps else self.end_lr for lr in lrs]
 		return lrs
+
+
+@torch.no_grad()
+def larc_(param_groups, larc_mode = 'clip', eps = 1e-7, min_update = 1e-7, larc_eta = 0.1):
+	"""optimizers.py:93-106 (no caller in the reference): layer-wise adaptive rate clipping / scaling of the gradients in place --
+	every gradient is multiplied by eta * |p| / (|g| + eps), in 'clip' mode relative to the group's lr and capped at 1"""
+	for group in param_groups:
+		for p in group['params']:
+			if p.grad is None:
+				continue
+			ratio = larc_eta * p.norm() / (p.grad.norm() + eps)
+			if larc_mode == 'clip':
+				ratio = torch.clamp(ratio / group['lr'], min = min_update, max = 1)
+			else:
+				ratio = torch.clamp(ratio, min = min_update)
+			p.grad.mul_(ratio)

@@ -257,3 +257,26 @@ def test_small_host_helpers_match_the_live_reference():
 	assert torch.equal(dense, ref.sparse_topk_todense(r_saved))
 	missing = {n for n in dir(ref) if not n.startswith('_') and callable(getattr(ref, n)) and getattr(getattr(ref, n), '__module__', None) == ref.__name__ and not hasattr(models, n)}
 	assert missing <= {'OnnxWrapper', 'Wav2VecFrontend'}, missing  # ONNX runtime / fairseq backends: out of scope
+
+
+def test_larc_matches_the_live_reference():
+	import pytest
+	import torch
+	from convasr_b200 import optimizers
+	from oracle import reference_shim
+	if not reference_shim.available():
+		pytest.skip('reference tree not present')
+	ref_opt = reference_shim.load().optimizers
+	g = torch.Generator().manual_seed(5)
+	for mode in ('clip', 'scale'):
+		ps = [torch.randn(4, 3, generator = g), torch.randn(7, generator = g) * 1e-3, torch.randn(2, 2, generator = g)]
+		gs = [torch.randn(4, 3, generator = g) * 10, torch.randn(7, generator = g), None]
+		out = []
+		for fn in (optimizers.larc_, ref_opt.larc_):
+			params = [p.clone().requires_grad_(True) for p in ps]
+			for p, gr in zip(params, gs):
+				p.grad = None if gr is None else gr.clone()
+			fn([dict(params = params, lr = 0.05)], larc_mode = mode)
+			out.append([None if p.grad is None else p.grad.clone() for p in params])
+		for a, b in zip(*out):
+			assert (a is None and b is None) or torch.allclose(a, b, rtol = 1e-6, atol = 0)
